@@ -1,0 +1,404 @@
+"""ctypes binding of libdvs_b200.so (C ABI: include/dvs_b200.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``make -C diverseseq_b200/csrc``.
+There is no CPU fallback: a missing library or a missing CUDA device is an error.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import pathlib
+import threading
+
+import numpy as np
+
+_HERE = pathlib.Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libdvs_b200.so"
+
+DVS_OK, DVS_ERR_VALUE, DVS_ERR_CUDA, DVS_ERR_ARG = 0, 1, 2, 3
+MODE_NMOST, MODE_MAX_STDEV, MODE_MAX_COV = 0, 1, 2
+
+_vp = C.c_void_p
+_u32, _u64, _i32, _f64 = C.c_uint32, C.c_uint64, C.c_int, C.c_double
+
+# name -> (restype, argtypes); every symbol include/dvs_b200.h declares
+SIGNATURES = {
+    "dvs_last_error": (C.c_char_p, []),
+    "dvs_version": (C.c_char_p, []),
+    "dvs_ctx_create": (_i32, [_i32, C.POINTER(_vp)]),
+    "dvs_ctx_destroy": (None, [_vp]),
+    "dvs_ctx_sync": (_i32, [_vp]),
+    "dvs_ctx_stream": (_vp, [_vp]),
+    "dvs_ctx_launch_count": (_u64, [_vp]),
+    "dvs_seqset_upload": (_i32, [_vp, _vp, _vp, _u32, C.POINTER(_vp)]),
+    "dvs_seqset_synth": (_i32, [_vp, _u64, _u32, _u32, _u64, C.POINTER(_vp)]),
+    "dvs_synth_host": (_i32, [_u64, _u32, _u32, _u64, _u32, _u32, _vp, _vp]),
+    "dvs_synth_lengths": (_i32, [_u64, _u32, _u64, _vp]),
+    "dvs_seqset_nrec": (_u32, [_vp]),
+    "dvs_seqset_total_bases": (_u64, [_vp]),
+    "dvs_seqset_offsets": (_i32, [_vp, _vp]),
+    "dvs_seqset_download": (_i32, [_vp, _vp, _u32, _u32, _vp]),
+    "dvs_seqset_free": (None, [_vp]),
+    "dvs_count_kmers": (_i32, [_vp, _vp, _i32, _i32, C.POINTER(_vp)]),
+    "dvs_kfreqs_from_rows": (_i32, [_vp, _vp, _vp, _u32, _u64, C.POINTER(_vp)]),
+    "dvs_kfreqs_nrec": (_u32, [_vp]),
+    "dvs_kfreqs_dim": (_u64, [_vp]),
+    "dvs_kfreqs_download": (_i32, [_vp, _vp, _u32, _u32, _vp, _vp, _vp, _vp]),
+    "dvs_kfreqs_free": (None, [_vp]),
+    "dvs_count_kmers_host": (_i32, [_vp, _vp, _vp, _u32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "dvs_select": (_i32, [_vp, _vp, _vp, _u32, _i32, _u32, _u32, _vp, _vp, _vp, C.POINTER(_u32)]),
+    "dvs_select_last_accepts": (_u32, [_vp]),
+    "dvs_summed_create": (_i32, [_vp, _vp, _vp, _u32, C.POINTER(_vp)]),
+    "dvs_summed_delta_jsd": (_i32, [_vp, _vp, _vp, _u32, _i32, C.POINTER(_f64)]),
+    "dvs_summed_result": (_i32, [_vp, _vp, _vp, _vp, _vp, C.POINTER(_u32), C.POINTER(_u32)]),
+    "dvs_summed_free": (None, [_vp]),
+    "dvs_mash_sketch": (_i32, [_vp, _vp, _i32, _u64, _i32, _i32, C.POINTER(_vp)]),
+    "dvs_sketches_from_host": (_i32, [_vp, _vp, _u32, _vp, _u32, C.POINTER(_vp)]),
+    "dvs_sketches_nrec": (_u32, [_vp]),
+    "dvs_sketches_stride": (_u32, [_vp]),
+    "dvs_sketches_download": (_i32, [_vp, _vp, _vp, _vp]),
+    "dvs_sketches_free": (None, [_vp]),
+    "dvs_mash_distances": (_i32, [_vp, _vp, _i32, _u64, _u32, _u32, _vp, _vp, _vp]),
+    "dvs_mash_sketch_host": (_i32, [_vp, _vp, _u64, _i32, _u64, _i32, _i32, _vp, _u64, C.POINTER(_u64)]),
+    "dvs_euclid_distances": (_i32, [_vp, _vp, _u32, _u32, _vp]),
+    "dvs_debug_log2": (_i32, [_vp, _vp, _vp, _u64]),
+    "dvs_debug_entropy": (_i32, [_vp, _vp, _u32, _u64, _vp, _vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load() -> C.CDLL:
+    """Load libdvs_b200.so (no GPU needed to load; needed to create a context)."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not LIB_PATH.exists():
+                raise RuntimeError(
+                    f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "or `make -C diverseseq_b200/csrc`. There is no CPU fallback."
+                )
+            lib = C.CDLL(str(LIB_PATH))
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)  # AttributeError here == header/library mismatch
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    return load().dvs_last_error().decode(errors="replace")
+
+
+def check(rc: int) -> None:
+    if rc == DVS_OK:
+        return
+    msg = last_error()
+    if rc == DVS_ERR_VALUE:
+        if msg == "division by zero":
+            raise ZeroDivisionError(msg)
+        raise ValueError(msg)  # what the reference raises for a Rust panic (src/lib.rs:36-57)
+    if rc == DVS_ERR_CUDA:
+        raise RuntimeError(msg)
+    raise TypeError(msg) if rc == DVS_ERR_ARG else RuntimeError(msg)
+
+
+def ptr(a):
+    """void* of a C-contiguous numpy array (or None)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_vp)
+
+
+class Context:
+    """One CUDA context/stream for the hot path on one GPU (dvs_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load()
+        h = _vp()
+        check(self._lib.dvs_ctx_create(int(device), C.byref(h)))
+        self.handle = h
+        self.device = int(device)
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            self._lib.dvs_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self) -> None:
+        check(self._lib.dvs_ctx_sync(self.handle))
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.dvs_ctx_stream(self.handle) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.dvs_ctx_launch_count(self.handle))
+
+
+_default_ctx: dict[int, Context] = {}
+
+
+def default_context(device: int | None = None) -> Context:
+    """Process-wide context per device; device defaults to $LOCAL_RANK or 0."""
+    import os
+
+    if device is None:
+        device = int(os.environ.get("DVS_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    ctx = _default_ctx.get(device)
+    if ctx is None or ctx.handle is None:
+        ctx = _default_ctx[device] = Context(device)
+    return ctx
+
+
+class _Handle:
+    _free = None
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx = ctx
+        self.handle = handle
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            getattr(self.ctx._lib, self._free)(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def as_u8(a) -> np.ndarray:
+    if isinstance(a, (bytes, bytearray, memoryview)):
+        return np.frombuffer(a, dtype=np.uint8)
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def concat(seqs) -> tuple[np.ndarray, np.ndarray]:
+    arrs = [as_u8(s) for s in seqs]
+    offsets = np.zeros(len(arrs) + 1, dtype=np.uint64)
+    if arrs:
+        offsets[1:] = np.cumsum([a.size for a in arrs], dtype=np.uint64)
+    flat = np.concatenate(arrs) if arrs and int(offsets[-1]) else np.zeros(0, dtype=np.uint8)
+    return np.ascontiguousarray(flat), offsets
+
+
+class SeqSet(_Handle):
+    """Device-resident batch of encoded sequences (dvs_seqset)."""
+
+    _free = "dvs_seqset_free"
+
+    @classmethod
+    def upload(cls, ctx: Context, flat: np.ndarray, offsets: np.ndarray) -> "SeqSet":
+        flat = as_u8(flat)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        h = _vp()
+        check(ctx._lib.dvs_seqset_upload(ctx.handle, ptr(flat) if flat.size else None, ptr(offsets),
+                                         len(offsets) - 1, C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def from_seqs(cls, ctx: Context, seqs) -> "SeqSet":
+        return cls.upload(ctx, *concat(seqs))
+
+    @classmethod
+    def synth(cls, ctx: Context, seed: int, nrec: int, nfam: int, mean_len: int) -> "SeqSet":
+        h = _vp()
+        check(ctx._lib.dvs_seqset_synth(ctx.handle, seed, nrec, nfam, mean_len, C.byref(h)))
+        return cls(ctx, h)
+
+    @property
+    def nrec(self) -> int:
+        return int(self.ctx._lib.dvs_seqset_nrec(self.handle))
+
+    @property
+    def total_bases(self) -> int:
+        return int(self.ctx._lib.dvs_seqset_total_bases(self.handle))
+
+    def offsets(self) -> np.ndarray:
+        out = np.zeros(self.nrec + 1, dtype=np.uint64)
+        check(self.ctx._lib.dvs_seqset_offsets(self.handle, ptr(out)))
+        return out
+
+    def download(self, first: int = 0, count: int | None = None, out: np.ndarray | None = None) -> np.ndarray:
+        count = self.nrec - first if count is None else count
+        off = self.offsets()
+        n = int(off[first + count] - off[first])
+        if out is None:
+            out = np.empty(max(n, 1), dtype=np.uint8)
+        check(self.ctx._lib.dvs_seqset_download(self.ctx.handle, self.handle, first, count, ptr(out)))
+        return out[:n]
+
+
+def synth_host(seed: int, nrec: int, nfam: int, mean_len: int, first: int = 0, count: int | None = None):
+    """host twin of SeqSet.synth: (flat bytes, offsets) of records [first, first+count)"""
+    lib = load()
+    count = nrec - first if count is None else count
+    lens = np.zeros(nrec, dtype=np.uint64)
+    check(lib.dvs_synth_lengths(seed, nrec, mean_len, ptr(lens)))
+    total = int(lens[first:first + count].sum())
+    flat = np.empty(max(total, 1), dtype=np.uint8)
+    offsets = np.zeros(count + 1, dtype=np.uint64)
+    check(lib.dvs_synth_host(seed, nrec, nfam, mean_len, first, count, ptr(flat), ptr(offsets)))
+    return flat[:total], offsets
+
+
+class KFreqs(_Handle):
+    """Device-resident k-mer frequency rows + entropies (dvs_kfreqs)."""
+
+    _free = "dvs_kfreqs_free"
+
+    @classmethod
+    def count(cls, ctx: Context, seqset: SeqSet, k: int, num_states: int = 4) -> "KFreqs":
+        h = _vp()
+        check(ctx._lib.dvs_count_kmers(ctx.handle, seqset.handle, int(k), int(num_states), C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def from_rows(cls, ctx: Context, rows: np.ndarray, entropies: np.ndarray | None = None) -> "KFreqs":
+        rows = np.ascontiguousarray(rows, dtype=np.float64)
+        ent = None if entropies is None else np.ascontiguousarray(entropies, dtype=np.float64)
+        h = _vp()
+        check(ctx._lib.dvs_kfreqs_from_rows(ctx.handle, ptr(rows), ptr(ent), rows.shape[0], rows.shape[1], C.byref(h)))
+        return cls(ctx, h)
+
+    @property
+    def nrec(self) -> int:
+        return int(self.ctx._lib.dvs_kfreqs_nrec(self.handle))
+
+    @property
+    def dim(self) -> int:
+        return int(self.ctx._lib.dvs_kfreqs_dim(self.handle))
+
+    def download(self, first: int = 0, count: int | None = None, counts=True, freqs=True):
+        count = self.nrec - first if count is None else count
+        d = self.dim
+        c = np.zeros((count, d), dtype=np.uint64) if counts else None
+        f = np.zeros((count, d), dtype=np.float64) if freqs else None
+        e = np.zeros(count, dtype=np.float64)
+        v = np.zeros(count, dtype=np.uint8)
+        check(self.ctx._lib.dvs_kfreqs_download(self.ctx.handle, self.handle, first, count, ptr(c), ptr(f), ptr(e), ptr(v)))
+        return c, f, e, v
+
+    def select(self, order, mode: int, min_size: int, max_size: int = 0):
+        """nmost / max selection; returns (row indices, delta_jsd, stats5)"""
+        order = np.ascontiguousarray(order, dtype=np.uint32)
+        cap = max(int(min_size), int(max_size), 1) + 1
+        idx = np.zeros(cap, dtype=np.uint32)
+        delta = np.zeros(cap, dtype=np.float64)
+        stats = np.zeros(5, dtype=np.float64)
+        size = _u32(0)
+        check(self.ctx._lib.dvs_select(self.ctx.handle, self.handle, ptr(order) if order.size else None, order.size,
+                                       int(mode), int(min_size), int(max_size), ptr(idx), ptr(delta), ptr(stats),
+                                       C.byref(size)))
+        n = size.value
+        return idx[:n].copy(), delta[:n].copy(), stats
+
+    def euclidean(self, row_begin: int = 0, row_end: int | None = None) -> np.ndarray:
+        row_end = self.nrec if row_end is None else row_end
+        out = np.zeros((row_end - row_begin, self.nrec), dtype=np.float64)
+        check(self.ctx._lib.dvs_euclid_distances(self.ctx.handle, self.handle, row_begin, row_end, ptr(out)))
+        return out
+
+
+class Summed(_Handle):
+    """Device-resident SummedRecords state (dvs_summed)."""
+
+    _free = "dvs_summed_free"
+
+    def __init__(self, ctx: Context, kfreqs: KFreqs, members):
+        members = np.ascontiguousarray(members, dtype=np.uint32)
+        h = _vp()
+        check(ctx._lib.dvs_summed_create(ctx.handle, kfreqs.handle, ptr(members) if members.size else None,
+                                         members.size, C.byref(h)))
+        super().__init__(ctx, h)
+        self.kfreqs = kfreqs  # keep alive
+        self.size = int(members.size)
+
+    def delta_jsd(self, query: KFreqs, row: int = 0, is_member: bool = False) -> float:
+        out = _f64(0.0)
+        check(self.ctx._lib.dvs_summed_delta_jsd(self.ctx.handle, self.handle, query.handle, row, int(is_member),
+                                                 C.byref(out)))
+        return out.value
+
+    def result(self):
+        idx = np.zeros(self.size, dtype=np.uint32)
+        delta = np.zeros(self.size, dtype=np.float64)
+        stats = np.zeros(5, dtype=np.float64)
+        size, low = _u32(0), _u32(0)
+        check(self.ctx._lib.dvs_summed_result(self.ctx.handle, self.handle, ptr(idx), ptr(delta), ptr(stats),
+                                              C.byref(size), C.byref(low)))
+        return idx[: size.value], delta[: size.value], stats, low.value
+
+
+class Sketches(_Handle):
+    """Device-resident MinHash sketches (dvs_sketches)."""
+
+    _free = "dvs_sketches_free"
+
+    @classmethod
+    def sketch(cls, ctx: Context, seqset: SeqSet, k: int, sketch_size: int, num_states: int = 4,
+               canonical: bool = False) -> "Sketches":
+        h = _vp()
+        check(ctx._lib.dvs_mash_sketch(ctx.handle, seqset.handle, int(k), int(sketch_size), int(num_states),
+                                       int(bool(canonical)), C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def from_host(cls, ctx: Context, sketches: np.ndarray, lens: np.ndarray) -> "Sketches":
+        sk = np.ascontiguousarray(sketches, dtype=np.uint32)
+        lens = np.ascontiguousarray(lens, dtype=np.uint32)
+        h = _vp()
+        check(ctx._lib.dvs_sketches_from_host(ctx.handle, ptr(sk), sk.shape[1], ptr(lens), sk.shape[0], C.byref(h)))
+        return cls(ctx, h)
+
+    @property
+    def nrec(self) -> int:
+        return int(self.ctx._lib.dvs_sketches_nrec(self.handle))
+
+    @property
+    def stride(self) -> int:
+        return int(self.ctx._lib.dvs_sketches_stride(self.handle))
+
+    def download(self):
+        sk = np.zeros((self.nrec, self.stride), dtype=np.uint32)
+        lens = np.zeros(self.nrec, dtype=np.uint32)
+        check(self.ctx._lib.dvs_sketches_download(self.ctx.handle, self.handle, ptr(sk), ptr(lens)))
+        return sk, lens
+
+    def distances(self, k: int, sketch_size: int, row_begin: int = 0, row_end: int | None = None,
+                  want_counts: bool = False):
+        row_end = self.nrec if row_end is None else row_end
+        shape = (row_end - row_begin, self.nrec)
+        dist = np.zeros(shape, dtype=np.float64)
+        inter = np.zeros(shape, dtype=np.uint32) if want_counts else None
+        uni = np.zeros(shape, dtype=np.uint32) if want_counts else None
+        check(self.ctx._lib.dvs_mash_distances(self.ctx.handle, self.handle, int(k), int(sketch_size), row_begin,
+                                               row_end, ptr(dist), ptr(inter), ptr(uni)))
+        return (dist, inter, uni) if want_counts else dist
+
+
+def debug_log2(ctx: Context, x: np.ndarray) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.zeros_like(x)
+    check(ctx._lib.dvs_debug_log2(ctx.handle, ptr(x), ptr(y), x.size))
+    return y
+
+
+def debug_entropy(ctx: Context, rows: np.ndarray):
+    rows = np.ascontiguousarray(rows, dtype=np.float64)
+    out = np.zeros(rows.shape[0], dtype=np.float64)
+    err = np.zeros(rows.shape[0], dtype=np.uint8)
+    check(ctx._lib.dvs_debug_entropy(ctx.handle, ptr(rows), rows.shape[0], rows.shape[1], ptr(out), ptr(err)))
+    return out, err

@@ -1,0 +1,127 @@
+// Shared plumbing for libdvs_b200: error reporting, context, launch accounting.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/dvs_b200.h"
+
+namespace dvs {
+
+constexpr double kEps = 2.220446049250313e-16;  // f64::EPSILON
+
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define DVS_CUDA_TRY(expr)                                                                   \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            ::dvs::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                             __LINE__);                                                      \
+            return DVS_ERR_CUDA;                                                             \
+        }                                                                                    \
+    } while (0)
+
+#define DVS_TRY(expr)            \
+    do {                         \
+        int _rc = (expr);        \
+        if (_rc != DVS_OK) return _rc; \
+    } while (0)
+
+// counts a launch and checks the launch error
+#define DVS_LAUNCHED(ctx)                                                                   \
+    do {                                                                                    \
+        (ctx)->launches++;                                                                  \
+        cudaError_t _e = cudaGetLastError();                                                \
+        if (_e != cudaSuccess) {                                                            \
+            ::dvs::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, \
+                             __LINE__);                                                     \
+            return DVS_ERR_CUDA;                                                            \
+        }                                                                                   \
+    } while (0)
+
+// RAII device buffer (cudaMalloc / cudaFree)
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    int alloc(size_t count) {
+        release();
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        if (e != cudaSuccess) {
+            set_error("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+            p = nullptr;
+            return DVS_ERR_CUDA;
+        }
+        n = count;
+        return DVS_OK;
+    }
+};
+
+}  // namespace dvs
+
+struct dvs_ctx {
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    uint32_t last_accepts = 0;
+    // pinned scratch for small device->host readbacks
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+};
+
+// Front padding (bytes) before the first sequence byte so aligned halo loads at (addr-16) stay in
+// the allocation, and tail slack so 16-byte loads covering the last byte do too.
+constexpr size_t kSeqFrontPad = 256;
+constexpr size_t kSeqTailPad = 256;
+
+struct dvs_seqset {
+    int device = 0;
+    uint32_t nrec = 0;
+    uint64_t total = 0;
+    dvs::DevBuf<uint8_t> raw;        // kSeqFrontPad + total + kSeqTailPad
+    dvs::DevBuf<uint64_t> offsets;   // nrec+1 (device)
+    std::vector<uint64_t> h_offsets;  // nrec+1 (host)
+    const uint8_t* data() const { return raw.p + kSeqFrontPad; }
+    uint8_t* data() { return raw.p + kSeqFrontPad; }
+};
+
+struct dvs_kfreqs {
+    int device = 0;
+    uint32_t nrec = 0;
+    uint64_t dim = 0;
+    int k = 0, num_states = 0;
+    dvs::DevBuf<uint32_t> counts;   // [nrec][dim]  (empty when built from rows)
+    dvs::DevBuf<uint64_t> totals;   // [nrec]
+    dvs::DevBuf<double> freqs;      // [nrec][dim]
+    dvs::DevBuf<double> entropy;    // [nrec]
+    dvs::DevBuf<uint8_t> valid;     // [nrec]  1 = has valid k-mers
+    dvs::DevBuf<uint8_t> err;       // [nrec]  1 = reference entropy() would panic (sum check)
+    dvs::DevBuf<double> err_total;  // [nrec]  the offending total
+    bool has_counts = false;
+};
+
+struct dvs_sketches {
+    int device = 0;
+    uint32_t nrec = 0;
+    uint32_t stride = 0;
+    dvs::DevBuf<uint32_t> data;  // [nrec][stride] ascending
+    dvs::DevBuf<uint32_t> lens;  // [nrec]
+};

@@ -1,0 +1,180 @@
+// Context, error reporting and sequence-set residency for libdvs_b200.
+#include <string.h>
+
+#include "common.cuh"
+
+namespace dvs {
+
+static thread_local std::string g_error;
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_error = buf;
+}
+
+const char* get_error() { return g_error.c_str(); }
+
+__global__ void k_fill_u8(uint8_t* p, size_t n, uint8_t v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+}  // namespace dvs
+
+using namespace dvs;
+
+extern "C" {
+
+const char* dvs_last_error(void) { return get_error(); }
+const char* dvs_version(void) { return "dvs_b200 0.1 (sm_100a)"; }
+
+int dvs_ctx_create(int device, dvs_ctx** out) {
+    if (!out) {
+        set_error("dvs_ctx_create: out is NULL");
+        return DVS_ERR_ARG;
+    }
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error("no CUDA device available (%s); libdvs_b200 has no CPU fallback",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return DVS_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        set_error("dvs_ctx_create: device %d out of range (have %d)", device, ndev);
+        return DVS_ERR_ARG;
+    }
+    DVS_CUDA_TRY(cudaSetDevice(device));
+    auto* ctx = new dvs_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    DVS_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    DVS_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->pinned_bytes = 1 << 20;
+    DVS_CUDA_TRY(cudaHostAlloc(&ctx->pinned, ctx->pinned_bytes, cudaHostAllocDefault));
+    *out = ctx;
+    return DVS_OK;
+}
+
+void dvs_ctx_destroy(dvs_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+    }
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    delete ctx;
+}
+
+int dvs_ctx_sync(dvs_ctx* ctx) {
+    DVS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return DVS_OK;
+}
+
+void* dvs_ctx_stream(dvs_ctx* ctx) { return (void*)ctx->stream; }
+uint64_t dvs_ctx_launch_count(dvs_ctx* ctx) { return ctx->launches; }
+
+// ---- sequence sets -----------------------------------------------------------------------
+
+static int seqset_alloc(dvs_ctx* ctx, const uint64_t* offsets, uint32_t nrec, dvs_seqset** out) {
+    for (uint32_t r = 0; r < nrec; ++r)
+        if (offsets[r + 1] < offsets[r]) {
+            set_error("offsets must be non-decreasing (record %u)", r);
+            return DVS_ERR_ARG;
+        }
+    if (offsets[0] != 0) {
+        set_error("offsets[0] must be 0");
+        return DVS_ERR_ARG;
+    }
+    DVS_CUDA_TRY(cudaSetDevice(ctx->device));
+    auto* s = new dvs_seqset();
+    s->device = ctx->device;
+    s->nrec = nrec;
+    s->total = offsets[nrec];
+    s->h_offsets.assign(offsets, offsets + nrec + 1);
+    int rc = s->raw.alloc(kSeqFrontPad + s->total + kSeqTailPad);
+    if (rc == DVS_OK) rc = s->offsets.alloc(nrec + 1);
+    if (rc != DVS_OK) {
+        delete s;
+        return rc;
+    }
+    // pads hold 0xFF (invalid for every num_states) so halo/tail vector loads never see a base
+    cudaMemsetAsync(s->raw.p, 0xFF, kSeqFrontPad, ctx->stream);
+    cudaMemsetAsync(s->raw.p + kSeqFrontPad + s->total, 0xFF, kSeqTailPad, ctx->stream);
+    cudaError_t e = cudaMemcpyAsync(s->offsets.p, offsets, (nrec + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice,
+                                    ctx->stream);
+    if (e != cudaSuccess) {
+        set_error("offset upload failed: %s", cudaGetErrorString(e));
+        delete s;
+        return DVS_ERR_CUDA;
+    }
+    *out = s;
+    return DVS_OK;
+}
+
+int dvs_seqset_alloc_internal(dvs_ctx* ctx, const uint64_t* offsets, uint32_t nrec, dvs_seqset** out) {
+    return seqset_alloc(ctx, offsets, nrec, out);
+}
+
+int dvs_seqset_upload(dvs_ctx* ctx, const uint8_t* seqs, const uint64_t* offsets, uint32_t nrec,
+                      dvs_seqset** out) {
+    if (!ctx || !offsets || !out || (!seqs && offsets[nrec] > 0)) {
+        set_error("dvs_seqset_upload: NULL argument");
+        return DVS_ERR_ARG;
+    }
+    dvs_seqset* s = nullptr;
+    DVS_TRY(seqset_alloc(ctx, offsets, nrec, &s));
+    if (s->total) {
+        cudaError_t e = cudaMemcpyAsync(s->data(), seqs, s->total, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) {
+            set_error("sequence upload failed: %s", cudaGetErrorString(e));
+            delete s;
+            return DVS_ERR_CUDA;
+        }
+    }
+    // the host buffers (seqs, offsets) may be pageable and reused by the caller: finish the copies
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        set_error("sequence upload failed: %s", cudaGetErrorString(e));
+        delete s;
+        return DVS_ERR_CUDA;
+    }
+    *out = s;
+    return DVS_OK;
+}
+
+uint32_t dvs_seqset_nrec(const dvs_seqset* s) { return s->nrec; }
+uint64_t dvs_seqset_total_bases(const dvs_seqset* s) { return s->total; }
+
+int dvs_seqset_offsets(const dvs_seqset* s, uint64_t* offsets_out) {
+    memcpy(offsets_out, s->h_offsets.data(), (s->nrec + 1) * sizeof(uint64_t));
+    return DVS_OK;
+}
+
+int dvs_seqset_download(dvs_ctx* ctx, const dvs_seqset* s, uint32_t first, uint32_t count, uint8_t* seqs_out) {
+    if (first + (uint64_t)count > s->nrec) {
+        set_error("dvs_seqset_download: range out of bounds");
+        return DVS_ERR_ARG;
+    }
+    uint64_t b = s->h_offsets[first], e = s->h_offsets[first + count];
+    DVS_CUDA_TRY(cudaSetDevice(ctx->device));
+    if (e > b) DVS_CUDA_TRY(cudaMemcpyAsync(seqs_out, s->data() + b, e - b, cudaMemcpyDeviceToHost, ctx->stream));
+    DVS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return DVS_OK;
+}
+
+void dvs_seqset_free(dvs_seqset* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    delete s;
+}
+
+}  // extern "C"

@@ -1,0 +1,469 @@
+// k-mer counting -> frequency rows -> exact entropies.
+//
+// Replaces SeqRecord::to_kcounts / to_kmerseq and entropy of the reference
+// (/root/reference/src/record.rs:31-84, 124-141, 86-106).
+//
+// Counting semantics (record.rs:41-84 == run-length form): a k-mer ending
+// at position p is counted iff the k bytes p-k+1..p all lie inside the record and are
+// < num_states; its bin is the base-num_states value of those bytes, first byte most significant.
+//
+// Kernel shape: sequence bytes stream from HBM with coalesced 16-byte loads (thread t owns the
+// 16-byte block t of an 8 KB stripe; the k-1 byte halo comes from the preceding 16-byte block,
+// an L1 hit).  For num_states == 4 a block of 16 valid bases is packed to 32 bits with four
+// integer multiplies and each k-mer index is one funnel shift + mask.  Bins live in a
+// shared-memory histogram (u32) when num_states^k * 4 B fits; otherwise the bin range is split
+// into `nparts` shared-memory passes (k=8) or, for larger tables, updated with global RED.ADD.
+// Work is (record, part, 16B-aligned byte range) items pulled from a global queue by persistent
+// CTAs, so long records are split across CTAs and merged with one global atomic per non-empty bin.
+#include <algorithm>
+
+#include "common.cuh"
+#include "entropy.cuh"
+
+namespace dvs {
+
+struct CountWork {
+    uint64_t begin;  // 16-byte aligned absolute byte range [begin, end) inside seqset data
+    uint64_t end;
+    uint32_t rec;
+    uint32_t part;
+};
+
+constexpr int kCountThreads = 512;
+
+__device__ __forceinline__ uint32_t pack4(uint32_t w) {
+    // bytes b0..b3 (memory order, each 0..3) -> b0<<6 | b1<<4 | b2<<2 | b3
+    return (w * 0x40100401u) >> 24;
+}
+__device__ __forceinline__ uint32_t pack16(uint4 v) {
+    return (pack4(v.x) << 24) | (pack4(v.y) << 16) | (pack4(v.z) << 8) | pack4(v.w);
+}
+
+__device__ __forceinline__ uint4 ldg16(const uint8_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+// SMEM: bins [part*part_bins, (part+1)*part_bins) in shared memory; else global atomics.
+template <bool NS4, bool SMEM>
+__global__ void __launch_bounds__(kCountThreads)
+k_count(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offsets, const CountWork* __restrict__ work,
+        uint32_t nwork, uint32_t* __restrict__ next_item, int k, uint32_t num_states, uint64_t dim,
+        uint32_t part_bins, uint32_t* __restrict__ counts) {
+    extern __shared__ uint32_t hist[];
+    __shared__ uint32_t s_item;
+    const int tid = threadIdx.x;
+    const uint32_t mask = (k >= 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
+
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(next_item, 1u);
+        __syncthreads();
+        const uint32_t item = s_item;
+        if (item >= nwork) break;
+        const CountWork w = work[item];
+        const uint64_t start = offsets[w.rec], end = offsets[w.rec + 1];
+        const uint32_t part_base = w.part * part_bins;
+        uint32_t* grow = counts + (size_t)w.rec * dim;
+        if (SMEM) {
+            for (uint32_t i = tid; i < part_bins; i += kCountThreads) hist[i] = 0;
+            __syncthreads();
+        }
+        auto bump = [&](uint32_t idx) {
+            if (SMEM) {
+                uint32_t local = idx - part_base;
+                if (local < part_bins) atomicAdd(&hist[local], 1u);
+            } else {
+                atomicAdd(&grow[idx], 1u);
+            }
+        };
+
+        for (uint64_t a = w.begin + (uint64_t)tid * 16; a < w.end; a += (uint64_t)kCountThreads * 16) {
+            const uint4 cur = ldg16(seqs + a);
+            const uint4 prev = ldg16(seqs + a - 16);  // front pad keeps a-16 inside the allocation
+            bool fast = false;
+            if (NS4) {
+                uint32_t any = cur.x | cur.y | cur.z | cur.w | prev.x | prev.y | prev.z | prev.w;
+                fast = ((any & 0xFCFCFCFCu) == 0) && (a >= start + 16) && (a + 16 <= end);
+            }
+            if (fast) {
+                const uint32_t pc = pack16(cur), pp = pack16(prev);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    uint32_t idx = __funnelshift_r(pc, pp, 2 * (15 - j)) & mask;
+                    bump(idx);
+                }
+            } else {
+                // per-byte path: invalid bytes, record edges, or num_states != 4
+                const uint32_t wv[8] = {prev.x, prev.y, prev.z, prev.w, cur.x, cur.y, cur.z, cur.w};
+                uint32_t run = 0;
+                uint64_t idx = 0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const uint64_t p = a - 16 + i;
+                    uint32_t b = (wv[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+                    if (p < start || p >= end) b = 0xFFu;
+                    if (b >= num_states) {
+                        run = 0;
+                        idx = 0;
+                    } else {
+                        if (NS4)
+                            idx = ((idx << 2) | b) & mask;
+                        else
+                            idx = (idx * num_states + b) % dim;
+                        ++run;
+                        if (i >= 16 && run >= (uint32_t)k) bump((uint32_t)idx);
+                    }
+                }
+            }
+        }
+        if (SMEM) {
+            __syncthreads();
+            for (uint32_t i = tid; i < part_bins; i += kCountThreads) {
+                uint32_t c = hist[i];
+                if (c && (uint64_t)part_base + i < dim) atomicAdd(&grow[part_base + i], c);
+            }
+        }
+        __syncthreads();  // s_item / hist reuse
+    }
+}
+
+// one block per record: total, validity, frequency row, exact entropy
+__global__ void __launch_bounds__(kEntThreads)
+k_freq_entropy(const uint32_t* __restrict__ counts, uint64_t dim, double* __restrict__ freqs,
+               uint64_t* __restrict__ totals, double* __restrict__ entropy, uint8_t* __restrict__ valid,
+               uint8_t* __restrict__ err, double* __restrict__ err_total) {
+    extern __shared__ double ent_smem[];
+    __shared__ unsigned long long s_total;
+    const uint32_t r = blockIdx.x;
+    const uint32_t* c = counts + (size_t)r * dim;
+    double* f = freqs + (size_t)r * dim;
+    if (threadIdx.x == 0) s_total = 0ULL;
+    __syncthreads();
+    unsigned long long part = 0;
+    for (uint64_t i = threadIdx.x; i < dim; i += blockDim.x) part += c[i];
+    for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_total, part);
+    __syncthreads();
+    const unsigned long long total_u = s_total;
+    const double total = (double)total_u;  // `sum::<usize>() as f64`
+    for (uint64_t i = threadIdx.x; i < dim; i += blockDim.x) f[i] = __ddiv_rn((double)c[i], total);  // NaN row if 0
+    if (total_u == 0ULL) {
+        if (threadIdx.x == 0) {
+            totals[r] = 0;
+            entropy[r] = 0.0;
+            valid[r] = 0;
+            err[r] = 0;
+            err_total[r] = 0.0;
+        }
+        return;
+    }
+    EntropyResult h = block_entropy_exact(dim, [&](uint64_t i) { return __ddiv_rn((double)c[i], total); }, ent_smem);
+    if (threadIdx.x == 0) {
+        totals[r] = total_u;
+        entropy[r] = h.e;
+        valid[r] = 1;
+        bool bad = entropy_total_bad(h.t, dim);
+        err[r] = bad ? 1 : 0;
+        err_total[r] = h.t;
+    }
+}
+
+// rows supplied by the caller: entropy as KmerSeq::new computes it (record.rs:157-168)
+__global__ void __launch_bounds__(kEntThreads)
+k_rows_entropy(const double* __restrict__ freqs, uint64_t dim, double* __restrict__ entropy,
+               uint8_t* __restrict__ err, double* __restrict__ err_total, int write_entropy) {
+    extern __shared__ double ent_smem[];
+    const uint32_t r = blockIdx.x;
+    const double* f = freqs + (size_t)r * dim;
+    EntropyResult h = block_entropy_exact(dim, [&](uint64_t i) { return f[i]; }, ent_smem);
+    if (threadIdx.x == 0) {
+        if (write_entropy) entropy[r] = h.e;
+        bool bad = entropy_total_bad(h.t, dim);
+        err[r] = bad ? 1 : 0;
+        err_total[r] = h.t;
+    }
+}
+
+__global__ void k_log2(const double* x, double* y, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = dvs_log2(x[i]);
+}
+
+static bool pow_dim(int num_states, int k, uint64_t* dim) {
+    uint64_t d = 1;
+    for (int i = 0; i < k; ++i) {
+        d *= (uint64_t)num_states;
+        if (d > (1ULL << 32)) return false;
+    }
+    *dim = d;
+    return true;
+}
+
+static int kfreqs_alloc(dvs_ctx* ctx, uint32_t nrec, uint64_t dim, bool with_counts, dvs_kfreqs** out) {
+    DVS_CUDA_TRY(cudaSetDevice(ctx->device));
+    auto* f = new dvs_kfreqs();
+    f->device = ctx->device;
+    f->nrec = nrec;
+    f->dim = dim;
+    f->has_counts = with_counts;
+    int rc = DVS_OK;
+    if (with_counts) rc = f->counts.alloc((size_t)nrec * dim);
+    if (rc == DVS_OK) rc = f->freqs.alloc((size_t)nrec * dim);
+    if (rc == DVS_OK) rc = f->totals.alloc(nrec);
+    if (rc == DVS_OK) rc = f->entropy.alloc(nrec);
+    if (rc == DVS_OK) rc = f->valid.alloc(nrec);
+    if (rc == DVS_OK) rc = f->err.alloc(nrec);
+    if (rc == DVS_OK) rc = f->err_total.alloc(nrec);
+    if (rc != DVS_OK) {
+        delete f;
+        return rc;
+    }
+    *out = f;
+    return DVS_OK;
+}
+
+}  // namespace dvs
+
+using namespace dvs;
+
+extern "C" {
+
+int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dvs_kfreqs** out) {
+    if (!ctx || !s || !out) {
+        set_error("dvs_count_kmers: NULL argument");
+        return DVS_ERR_ARG;
+    }
+    if (k == 0) {
+        set_error("k cannot be 0");  // record.rs:126
+        return DVS_ERR_VALUE;
+    }
+    if (k < 0 || k > 16 || num_states < 1 || num_states > 255) {
+        set_error("dvs_count_kmers: unsupported k=%d / num_states=%d (need 1<=k<=16, 1<=num_states<=255)", k,
+                  num_states);
+        return DVS_ERR_ARG;
+    }
+    uint64_t dim = 0;
+    if (!pow_dim(num_states, k, &dim)) {
+        set_error("dvs_count_kmers: num_states^k = %d^%d does not fit a dense u32-indexed table", num_states, k);
+        return DVS_ERR_ARG;
+    }
+    DVS_CUDA_TRY(cudaSetDevice(ctx->device));
+    size_t free_b = 0, total_b = 0;
+    DVS_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    const double need = (double)s->nrec * (double)dim * 12.0;
+    if (need > 0.9 * (double)free_b) {
+        set_error("dvs_count_kmers: dense rows need %.1f GB (nrec=%u, dim=%llu) but only %.1f GB are free", need / 1e9,
+                  s->nrec, (unsigned long long)dim, free_b / 1e9);
+        return DVS_ERR_ARG;
+    }
+    dvs_kfreqs* f = nullptr;
+    DVS_TRY(kfreqs_alloc(ctx, s->nrec, dim, true, &f));
+    f->k = k;
+    f->num_states = num_states;
+    cudaStream_t st = ctx->stream;
+    auto fail = [&](int rc) {
+        dvs_kfreqs_free(f);
+        return rc;
+    };
+#define TRY_F(expr)                                                          \
+    do {                                                                     \
+        cudaError_t _e = (expr);                                             \
+        if (_e != cudaSuccess) {                                             \
+            set_error("%s failed: %s", #expr, cudaGetErrorString(_e));       \
+            return fail(DVS_ERR_CUDA);                                       \
+        }                                                                    \
+    } while (0)
+
+    TRY_F(cudaMemsetAsync(f->counts.p, 0, (size_t)s->nrec * dim * sizeof(uint32_t), st));
+
+    // ---- histogram placement ----
+    const bool ns4 = (num_states == 4);
+    const size_t max_hist_bytes = std::min<size_t>(ctx->smem_optin > 4096 ? ctx->smem_optin - 2048 : 0, 128 * 1024);
+    uint32_t nparts = 1, part_bins = (uint32_t)std::min<uint64_t>(dim, 1u << 31);
+    bool smem = true;
+    if (dim * 4 > max_hist_bytes) {
+        uint64_t bins_per = max_hist_bytes / 4;
+        uint64_t np = (dim + bins_per - 1) / bins_per;
+        if (np <= 2) {
+            nparts = (uint32_t)np;
+            part_bins = (uint32_t)((dim + np - 1) / np);
+        } else {
+            smem = false;
+        }
+    }
+    const size_t hist_bytes = smem ? (size_t)part_bins * 4 : 0;
+
+    // ---- work list: (record, part, aligned range) ----
+    const int ctas_per_sm = smem ? (hist_bytes <= 32 * 1024 ? 3 : (hist_bytes <= 100 * 1024 ? 2 : 1)) : 4;
+    const uint32_t grid = (uint32_t)(ctx->sm_count * ctas_per_sm);
+    uint64_t chunk = 1 << 20;
+    {
+        // aim for >= 8 items per CTA, chunks between 64 KB and 1 MB, multiples of the 8 KB stripe
+        uint64_t want_items = (uint64_t)grid * 8;
+        uint64_t c = (s->total + want_items - 1) / std::max<uint64_t>(want_items, 1);
+        c = std::max<uint64_t>(64 << 10, std::min<uint64_t>(c, 1 << 20));
+        chunk = (c + 8191) / 8192 * 8192;
+    }
+    std::vector<CountWork> work;
+    for (uint32_t r = 0; r < s->nrec; ++r) {
+        uint64_t b = s->h_offsets[r], e = s->h_offsets[r + 1];
+        if (e <= b) continue;
+        uint64_t a0 = b & ~15ULL, a1 = (e + 15) & ~15ULL;
+        for (uint64_t a = a0; a < a1; a += chunk)
+            for (uint32_t p = 0; p < nparts; ++p) work.push_back({a, std::min(a + chunk, a1), r, p});
+    }
+    DevBuf<CountWork> d_work;
+    DevBuf<uint32_t> d_next;
+    if (!work.empty()) {
+        if (d_work.alloc(work.size()) != DVS_OK || d_next.alloc(1) != DVS_OK) return fail(DVS_ERR_CUDA);
+        TRY_F(cudaMemcpyAsync(d_work.p, work.data(), work.size() * sizeof(CountWork), cudaMemcpyHostToDevice, st));
+        TRY_F(cudaMemsetAsync(d_next.p, 0, sizeof(uint32_t), st));
+        auto launch = [&](auto kern) -> cudaError_t {
+            if (hist_bytes > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes);
+                if (e != cudaSuccess) return e;
+            }
+            uint32_t g = (uint32_t)std::min<size_t>(grid, work.size());
+            kern<<<g, kCountThreads, hist_bytes, st>>>(s->data(), s->offsets.p, d_work.p, (uint32_t)work.size(),
+                                                       d_next.p, k, (uint32_t)num_states, dim, part_bins,
+                                                       f->counts.p);
+            ctx->launches++;
+            return cudaGetLastError();
+        };
+        cudaError_t e;
+        if (ns4)
+            e = smem ? launch(k_count<true, true>) : launch(k_count<true, false>);
+        else
+            e = smem ? launch(k_count<false, true>) : launch(k_count<false, false>);
+        if (e != cudaSuccess) {
+            set_error("k_count launch failed: %s", cudaGetErrorString(e));
+            return fail(DVS_ERR_CUDA);
+        }
+    }
+    if (s->nrec) {
+        k_freq_entropy<<<s->nrec, kEntThreads, kEntSmemBytes, st>>>(f->counts.p, dim, f->freqs.p, f->totals.p,
+                                                                    f->entropy.p, f->valid.p, f->err.p,
+                                                                    f->err_total.p);
+        ctx->launches++;
+        TRY_F(cudaGetLastError());
+    }
+    // the work list is freed on return: wait for the kernels that read it
+    TRY_F(cudaStreamSynchronize(st));
+#undef TRY_F
+    *out = f;
+    return DVS_OK;
+}
+
+int dvs_kfreqs_from_rows(dvs_ctx* ctx, const double* rows, const double* entropies_or_null, uint32_t nrec,
+                         uint64_t dim, dvs_kfreqs** out) {
+    if (!ctx || !rows || !out || dim == 0) {
+        set_error("dvs_kfreqs_from_rows: bad argument");
+        return DVS_ERR_ARG;
+    }
+    dvs_kfreqs* f = nullptr;
+    DVS_TRY(kfreqs_alloc(ctx, nrec, dim, false, &f));
+    cudaStream_t st = ctx->stream;
+    cudaError_t e = cudaSuccess;
+    if (nrec) {
+        e = cudaMemcpyAsync(f->freqs.p, rows, (size_t)nrec * dim * sizeof(double), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess && entropies_or_null)
+            e = cudaMemcpyAsync(f->entropy.p, entropies_or_null, nrec * sizeof(double), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(f->valid.p, 1, nrec, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(f->totals.p, 0, nrec * sizeof(uint64_t), st);
+        if (e == cudaSuccess) {
+            k_rows_entropy<<<nrec, kEntThreads, kEntSmemBytes, st>>>(f->freqs.p, dim, f->entropy.p, f->err.p,
+                                                                     f->err_total.p, entropies_or_null ? 0 : 1);
+            ctx->launches++;
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    if (e != cudaSuccess) {
+        set_error("dvs_kfreqs_from_rows failed: %s", cudaGetErrorString(e));
+        dvs_kfreqs_free(f);
+        return DVS_ERR_CUDA;
+    }
+    *out = f;
+    return DVS_OK;
+}
+
+uint32_t dvs_kfreqs_nrec(const dvs_kfreqs* f) { return f->nrec; }
+uint64_t dvs_kfreqs_dim(const dvs_kfreqs* f) { return f->dim; }
+
+int dvs_kfreqs_download(dvs_ctx* ctx, const dvs_kfreqs* f, uint32_t first, uint32_t count, uint64_t* counts,
+                        double* freqs, double* entropies, uint8_t* valid) {
+    if (first + (uint64_t)count > f->nrec) {
+        set_error("dvs_kfreqs_download: range out of bounds");
+        return DVS_ERR_ARG;
+    }
+    if (count == 0) return DVS_OK;
+    DVS_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t n = (size_t)count * f->dim;
+    std::vector<uint32_t> tmp;
+    if (counts) {
+        if (!f->has_counts) {
+            set_error("dvs_kfreqs_download: this kfreqs was built from rows and holds no counts");
+            return DVS_ERR_ARG;
+        }
+        tmp.resize(n);
+        DVS_CUDA_TRY(cudaMemcpyAsync(tmp.data(), f->counts.p + (size_t)first * f->dim, n * sizeof(uint32_t),
+                                     cudaMemcpyDeviceToHost, st));
+    }
+    if (freqs)
+        DVS_CUDA_TRY(cudaMemcpyAsync(freqs, f->freqs.p + (size_t)first * f->dim, n * sizeof(double),
+                                     cudaMemcpyDeviceToHost, st));
+    if (entropies)
+        DVS_CUDA_TRY(cudaMemcpyAsync(entropies, f->entropy.p + first, count * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (valid) DVS_CUDA_TRY(cudaMemcpyAsync(valid, f->valid.p + first, count, cudaMemcpyDeviceToHost, st));
+    DVS_CUDA_TRY(cudaStreamSynchronize(st));
+    if (counts)
+        for (size_t i = 0; i < n; ++i) counts[i] = tmp[i];
+    return DVS_OK;
+}
+
+void dvs_kfreqs_free(dvs_kfreqs* f) {
+    if (!f) return;
+    cudaSetDevice(f->device);
+    delete f;
+}
+
+int dvs_count_kmers_host(dvs_ctx* ctx, const uint8_t* seqs, const uint64_t* offsets, uint32_t nrec, int k,
+                         int num_states, uint64_t* counts, double* freqs, double* entropies, uint8_t* valid) {
+    dvs_seqset* s = nullptr;
+    DVS_TRY(dvs_seqset_upload(ctx, seqs, offsets, nrec, &s));
+    dvs_kfreqs* f = nullptr;
+    int rc = dvs_count_kmers(ctx, s, k, num_states, &f);
+    if (rc == DVS_OK) rc = dvs_kfreqs_download(ctx, f, 0, nrec, counts, freqs, entropies, valid);
+    dvs_kfreqs_free(f);
+    dvs_seqset_free(s);
+    return rc;
+}
+
+int dvs_debug_log2(dvs_ctx* ctx, const double* x, double* y, uint64_t n) {
+    if (n == 0) return DVS_OK;
+    DVS_CUDA_TRY(cudaSetDevice(ctx->device));
+    DevBuf<double> dx, dy;
+    DVS_TRY(dx.alloc(n));
+    DVS_TRY(dy.alloc(n));
+    DVS_CUDA_TRY(cudaMemcpyAsync(dx.p, x, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    k_log2<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dx.p, dy.p, n);
+    DVS_LAUNCHED(ctx);
+    DVS_CUDA_TRY(cudaMemcpyAsync(y, dy.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    DVS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return DVS_OK;
+}
+
+int dvs_debug_entropy(dvs_ctx* ctx, const double* rows, uint32_t nrec, uint64_t dim, double* out, uint8_t* err) {
+    dvs_kfreqs* f = nullptr;
+    DVS_TRY(dvs_kfreqs_from_rows(ctx, rows, nullptr, nrec, dim, &f));
+    int rc = DVS_OK;
+    cudaError_t e = cudaMemcpyAsync(out, f->entropy.p, nrec * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && err) e = cudaMemcpyAsync(err, f->err.p, nrec, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        set_error("dvs_debug_entropy failed: %s", cudaGetErrorString(e));
+        rc = DVS_ERR_CUDA;
+    }
+    dvs_kfreqs_free(f);
+    return rc;
+}
+
+}  // extern "C"

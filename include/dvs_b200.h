@@ -1,0 +1,161 @@
+/* dvs_b200.h — C ABI of libdvs_b200.so: the B200 (sm_100a) implementation of diverse-seq's
+ * data-parallel hot path.  This is the drop-in boundary: every entry point replaces one
+ * function of the reference's PyO3 module `diverse_seq._dvs` (or the pure-Python pair loops
+ * of diverse_seq/distance.py) and is what a reference-side FFI binding would bind; see
+ * INTEGRATION.md for the Rust `extern "C"` / ctypes stubs.  File:line citations are into
+ * /root/reference.
+ *
+ * Conventions
+ *   - plain pointers + sizes, caller-owned HOST buffers unless a parameter says "device";
+ *     the library never frees caller memory; opaque handles are freed by their *_free.
+ *   - sequences are the reference's uint8 index arrays (1 byte/base; T,C,A,G = 0..3 for DNA;
+ *     any byte >= num_states is invalid and breaks every k-mer that contains it), all records
+ *     concatenated in `seqs`, record r = seqs[offsets[r] .. offsets[r+1]).
+ *   - k-mer index is positional base-num_states, first base most significant
+ *     (src/record.rs:10-29); a count/frequency row has num_states^k entries.
+ *   - return 0 on success.  DVS_ERR_VALUE carries a message the reference raises as
+ *     ValueError (a Rust panic, src/lib.rs:36-57); DVS_ERR_CUDA is a CUDA runtime failure
+ *     (-> RuntimeError); DVS_ERR_ARG is API misuse.  dvs_last_error() returns the text
+ *     (thread-local).  There is NO CPU fallback: without a CUDA device dvs_ctx_create fails.
+ *   - one dvs_ctx per host thread/process per GPU; calls on one ctx are not re-entrant.
+ */
+#ifndef DVS_B200_H
+#define DVS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DVS_OK 0
+#define DVS_ERR_VALUE 1
+#define DVS_ERR_CUDA 2
+#define DVS_ERR_ARG 3
+
+/* selection modes for dvs_select */
+#define DVS_MODE_NMOST 0     /* select_nmost_divergent   src/records.rs:311-342 */
+#define DVS_MODE_MAX_STDEV 1 /* select_max_divergent, Stat::Std  src/records.rs:390-454 */
+#define DVS_MODE_MAX_COV 2   /* select_max_divergent, Stat::Cov */
+
+typedef struct dvs_ctx dvs_ctx;       /* device, streams, scratch */
+typedef struct dvs_seqset dvs_seqset; /* device-resident batch of encoded sequences */
+typedef struct dvs_kfreqs dvs_kfreqs; /* device-resident [nrec][num_states^k] rows + entropies */
+typedef struct dvs_summed dvs_summed; /* device-resident SummedRecords state */
+typedef struct dvs_sketches dvs_sketches; /* device-resident bottom-s MinHash sketches */
+
+const char* dvs_last_error(void);
+const char* dvs_version(void);
+
+/* ---- context --------------------------------------------------------------------------- */
+int dvs_ctx_create(int device, dvs_ctx** out);
+void dvs_ctx_destroy(dvs_ctx* ctx);
+int dvs_ctx_sync(dvs_ctx* ctx);
+/* the CUDA stream (cudaStream_t) every kernel of this ctx is launched on, for event timing */
+void* dvs_ctx_stream(dvs_ctx* ctx);
+/* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
+uint64_t dvs_ctx_launch_count(dvs_ctx* ctx);
+
+/* ---- sequences: what ZarrStore::read_uint8_array hands the hot path (src/zarr_io.rs:309) - */
+int dvs_seqset_upload(dvs_ctx* ctx, const uint8_t* seqs, const uint64_t* offsets, uint32_t nrec,
+                      dvs_seqset** out);
+/* synthetic genomes generated on the device (bench / tests): `nfam` family
+ * ancestors from order-2 Markov chains, members = ancestor prefix with per-base substitutions,
+ * invalid runs at ~1e-4.  Deterministic in (seed, record, position); lengths in
+ * [mean_len*0.75, mean_len*1.25].  dvs_synth_host() is the bit-identical host generator. */
+int dvs_seqset_synth(dvs_ctx* ctx, uint64_t seed, uint32_t nrec, uint32_t nfam, uint64_t mean_len,
+                     dvs_seqset** out);
+int dvs_synth_host(uint64_t seed, uint32_t nrec, uint32_t nfam, uint64_t mean_len, uint32_t first,
+                   uint32_t count, uint8_t* seqs_out, uint64_t* offsets_out);
+int dvs_synth_lengths(uint64_t seed, uint32_t nrec, uint64_t mean_len, uint64_t* lens_out);
+uint32_t dvs_seqset_nrec(const dvs_seqset* s);
+uint64_t dvs_seqset_total_bases(const dvs_seqset* s);
+int dvs_seqset_offsets(const dvs_seqset* s, uint64_t* offsets_out /* nrec+1 */);
+int dvs_seqset_download(dvs_ctx* ctx, const dvs_seqset* s, uint32_t first, uint32_t count,
+                        uint8_t* seqs_out);
+void dvs_seqset_free(dvs_seqset* s);
+
+/* ---- k-mer counting + frequencies + entropy -------------------------------------------------
+ * SeqRecord::to_kcounts / to_kmerseq / entropy  (src/record.rs:41-84, 124-141, 86-106).
+ * Result rows stay in HBM.  A record with no valid k-mer is marked valid=0 (the reference
+ * returns Err and callers skip it, src/records.rs:302,333).  Entropy is evaluated in the
+ * reference's sequential order with glibc's log2 algorithm, so it is bit-identical. */
+int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dvs_kfreqs** out);
+/* rows already computed elsewhere, e.g. SummedRecordsResult.records of per-chunk results fed to
+ * final_nmost / final_max (src/records.rs:344-360): entropy is recomputed from the stored
+ * frequencies exactly as KmerSeq::new does.  entropies_or_null == NULL -> recompute. */
+int dvs_kfreqs_from_rows(dvs_ctx* ctx, const double* rows, const double* entropies_or_null, uint32_t nrec,
+                         uint64_t dim, dvs_kfreqs** out);
+uint32_t dvs_kfreqs_nrec(const dvs_kfreqs* f);
+uint64_t dvs_kfreqs_dim(const dvs_kfreqs* f);
+/* any output may be NULL.  counts: uint64 like Rust usize (LazySeq.get_kcounts, src/record.rs:247);
+ * freqs: count/total as f64 (NaN row when total==0, like LazySeq.get_kfreqs src/record.rs:256). */
+int dvs_kfreqs_download(dvs_ctx* ctx, const dvs_kfreqs* f, uint32_t first, uint32_t count, uint64_t* counts,
+                        double* freqs, double* entropies, uint8_t* valid);
+void dvs_kfreqs_free(dvs_kfreqs* f);
+/* one-call host->host form (upload, count, download) */
+int dvs_count_kmers_host(dvs_ctx* ctx, const uint8_t* seqs, const uint64_t* offsets, uint32_t nrec, int k,
+                         int num_states, uint64_t* counts, double* freqs, double* entropies, uint8_t* valid);
+
+/* ---- nmost / max selection ------------------------------------------------------------------
+ * select_nmost_divergent / select_max_divergent and their *_final forms (src/records.rs:311-507)
+ * over the rows of `f`, examined in `order` (order[i] = row index at position i; the row index is
+ * the record identity, i.e. stands in for seqid).  Single-pass, order-dependent semantics of the
+ * reference with numprocs=1.  Outputs, in the reference's final Vec order: sel_idx[size],
+ * sel_delta[size] (delta_jsd per record), stats = {total_jsd, mean_delta_jsd, std_delta_jsd,
+ * cov_delta_jsd, summed_entropies}.  sel_idx/sel_delta need capacity max(min_size, max_size). */
+int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_t num, int mode,
+               uint32_t min_size, uint32_t max_size, uint32_t* sel_idx, double* sel_delta, double* stats5,
+               uint32_t* size_out);
+/* number of candidates that changed the set during the last dvs_select on this ctx */
+uint32_t dvs_select_last_accepts(dvs_ctx* ctx);
+
+/* SummedRecords::new over the listed rows + delta_jsd queries: make_summed_records and
+ * SummedRecordsWrapper (src/records.rs:509-524, src/records_py.rs:90-125) */
+int dvs_summed_create(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* members, uint32_t n, dvs_summed** out);
+/* delta_jsd of row `q_row` of `q` against the state (src/records.rs:70-84); is_member != 0 means the
+ * query's seqid is already in the set -> 0.0 */
+int dvs_summed_delta_jsd(dvs_ctx* ctx, dvs_summed* s, const dvs_kfreqs* q, uint32_t q_row, int is_member,
+                         double* out);
+int dvs_summed_result(dvs_ctx* ctx, dvs_summed* s, uint32_t* sel_idx, double* sel_delta, double* stats5,
+                      uint32_t* size_out, uint32_t* lowest_out);
+void dvs_summed_free(dvs_summed* s);
+
+/* ---- MinHash sketches + mash distances ------------------------------------------------------
+ * mash_sketch (src/distance.rs:151-182: reference hash src/distance.rs:21-87, distinct hashes,
+ * bottom-s ascending) for every record, and mash_distance for all pairs
+ * (diverse_seq/distance.py:230-291, matrix conventions :163-175). */
+int dvs_mash_sketch(dvs_ctx* ctx, const dvs_seqset* s, int k, uint64_t sketch_size, int num_states,
+                    int canonical, dvs_sketches** out);
+int dvs_sketches_from_host(dvs_ctx* ctx, const uint32_t* sketches, uint32_t stride, const uint32_t* lens,
+                           uint32_t nrec, dvs_sketches** out);
+uint32_t dvs_sketches_nrec(const dvs_sketches* sk);
+uint32_t dvs_sketches_stride(const dvs_sketches* sk);
+int dvs_sketches_download(dvs_ctx* ctx, const dvs_sketches* sk, uint32_t* sketches /* [nrec][stride] */,
+                          uint32_t* lens);
+void dvs_sketches_free(dvs_sketches* sk);
+/* rows [row_begin,row_end) of the symmetric nrec x nrec matrix (2-D sharding hook); outputs are
+ * (row_end-row_begin) x nrec, row-major; inter/uni may be NULL. */
+int dvs_mash_distances(dvs_ctx* ctx, const dvs_sketches* sk, int k, uint64_t sketch_size, uint32_t row_begin,
+                       uint32_t row_end, double* dist, uint32_t* inter, uint32_t* uni);
+/* host->host single record, mirrors _dvs.mash_sketch(seq_array, k, sketch_size, num_states, canonical) */
+int dvs_mash_sketch_host(dvs_ctx* ctx, const uint8_t* seq, uint64_t len, int k, uint64_t sketch_size,
+                         int num_states, int canonical, uint32_t* out, uint64_t cap, uint64_t* out_len);
+
+/* ---- Euclidean k-mer distance matrix --------------------------------------------------------
+ * euclidean_distances (diverse_seq/distance.py:294-336, cluster.py:647-680): ||f_i - f_j||_2 over
+ * frequency rows, rows [row_begin,row_end) x all columns, zero diagonal. */
+int dvs_euclid_distances(dvs_ctx* ctx, const dvs_kfreqs* f, uint32_t row_begin, uint32_t row_end, double* dist);
+
+/* ---- test hooks ---------------------------------------------------------------------------- */
+/* device evaluation of the glibc-log2 restatement on n doubles */
+int dvs_debug_log2(dvs_ctx* ctx, const double* x, double* y, uint64_t n);
+/* exact (reference-order) entropy of each host row on the device; err[r]=1 when the reference
+ * would panic (sum check, src/record.rs:101-104) */
+int dvs_debug_entropy(dvs_ctx* ctx, const double* rows, uint32_t nrec, uint64_t dim, double* out, uint8_t* err);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DVS_B200_H */
