@@ -1,0 +1,347 @@
+#!/usr/bin/env python3
+"""bench.py — the hot path's headline measurement (BASELINE.json configs[1]).
+
+Workload: "prep + nmost -n 100 k=6, 10.5k synthetic microbial genomes (~4 Mbp each), 1 B200".
+One step = k-mer counting (k=6) of every genome into 4^k frequency rows + Shannon entropies,
+followed by the order-preserving nmost (n=100) selection over the shuffled record order.
+Metric = whole-step throughput in Gbp/s (bases consumed / step time).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N>1 is launched by torchrun (one rank per GPU, NCCL); each rank counts its own 10.5k-genome
+shard (weak scaling), the rows are all-gathered and every rank replays the same selection over
+the union.  `value` times the step with inputs already in HBM; `e2e` times the same step through
+the public host-buffer API (pinned host -> device copy + result read-back inside the timed region).
+`--impl reference` times the CPU restatement of the reference (oracle/) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import pathlib
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+SEED = 20261017
+METRIC = "prep_nmost_throughput"
+UNIT = "Gbp/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nrec", type=int, default=10500)
+    ap.add_argument("--mean-len", type=int, default=4_000_000)
+    ap.add_argument("--nfam", type=int, default=64)
+    ap.add_argument("--k", type=int, default=6)
+    ap.add_argument("--n", type=int, default=100)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of one CPU sample")
+    return ap.parse_args()
+
+
+def workload_config(a, world):
+    return {
+        "workload": f"prep+nmost: count k={a.k} + entropy + nmost n={a.n} over {a.nrec} synthetic genomes "
+                    f"(~{a.mean_len / 1e6:g} Mbp each, {a.nfam} Markov families, invalid runs 1e-4) per GPU "
+                    "[BASELINE.json configs[1]]",
+        "nrec_per_gpu": a.nrec, "mean_len": a.mean_len, "k": a.k, "n": a.n, "seed": SEED,
+        "parallelism": f"records sharded x{world}, rows all-gathered, selection replicated" if world > 1 else "1 GPU",
+        "l2": "inputs (~42 GB/GPU) are far larger than the 126 MB L2, no flush needed",
+    }
+
+
+# --------------------------------------------------------------------------- clocks ----
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load": samples in the upper half of the observed power range
+        thr = (max(pw) + min(pw)) / 2
+        load = [s for s, p in zip(sm, pw) if p >= thr] or sm
+        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------- CPU (oracle) leg ----
+def cpu_sample_run(flat, offsets, k, n, threads):
+    """the reference's path on the host: count+freq+entropy over all host threads, then the (serial)
+    nmost selection — returns seconds"""
+    from oracle import oracle as orc
+
+    nrec = len(offsets) - 1
+    t0 = time.perf_counter()
+    _, freqs, ent, valid = orc.count_batch(flat, offsets, k, threads=threads, want_counts=False)
+    t1 = time.perf_counter()
+    order = np.random.default_rng(SEED).permutation(nrec)
+    nn = min(n, max(2, nrec // 2))
+    orc.select_rows(freqs, ent, order, "nmost", nn, valid=valid)
+    t2 = time.perf_counter()
+    return t2 - t0, t1 - t0, t2 - t1, nn
+
+
+def make_cpu_sample(a, want_records, seqset=None):
+    """first `want_records` genomes of the synthetic set as host arrays"""
+    from diverseseq_b200 import _lib
+
+    if seqset is not None:
+        off = seqset.offsets()
+        flat = seqset.download(0, want_records)
+        return flat, (off[: want_records + 1] - off[0]).astype(np.uint64)
+    return _lib.synth_host(SEED, a.nrec, a.nfam, a.mean_len, 0, want_records)
+
+
+def cpu_baseline(a, seqset=None, target_s=12.0):
+    from oracle import oracle as orc
+
+    threads = max(1, orc.hardware_threads())
+    probe_n = min(a.nrec, max(2, threads))
+    flat, off = make_cpu_sample(a, probe_n, seqset)
+    dt, *_ = cpu_sample_run(flat, off, a.k, a.n, threads)
+    rate = float(off[-1]) / max(dt, 1e-6)  # bases/s on the probe
+    avail = 8e9
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable"):
+                avail = float(ln.split()[1]) * 1024
+    except OSError:
+        pass
+    want_bases = min(rate * target_s, 0.25 * avail)
+    want = int(min(a.nrec, max(probe_n, want_bases / a.mean_len)))
+    flat, off = make_cpu_sample(a, want, seqset)
+    dt, t_count, t_sel, nn = cpu_sample_run(flat, off, a.k, a.n, threads)
+    bases = float(off[-1])
+    return {"value": bases / dt / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"first {want} of {a.nrec} genomes ({bases / 1e9:.2f} Gbp): count+entropy on {threads} threads "
+                      f"{t_count:.2f}s + serial nmost n={nn} {t_sel:.2f}s",
+            "seconds": dt}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    seqset = None
+    try:
+        from diverseseq_b200 import _lib
+        ctx = _lib.Context(int(os.environ.get("LOCAL_RANK", "0")))
+        seqset = _lib.SeqSet.synth(ctx, SEED, a.nrec, a.nfam, a.mean_len)  # generator only; timing is CPU-only
+    except Exception:
+        seqset = None
+    vals = []
+    base = None
+    for i in range(a.warmup + a.steps):
+        base = cpu_baseline(a, seqset, target_s=a.cpu_seconds if i >= a.warmup else a.cpu_seconds / 4)
+        if i >= a.warmup:
+            vals.append(base)
+    dt = float(np.mean([v["seconds"] for v in vals]))
+    v = float(np.mean([v["value"] for v in vals]))
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8 counts / f64 entropy", "data": "synthetic",
+            "config": workload_config(a, 1),
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")} | {"value": v},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------ B200 leg ----
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        return run_reference(a)
+
+    import torch
+    import torch.distributed as dist
+
+    from diverseseq_b200 import _lib, shard
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    ctx = _lib.Context(local)
+    ctx.enable_timing(True)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=device)
+
+    # ---- synthetic inputs, resident in HBM (rank r holds records of seed SEED+r) ----
+    seqset = _lib.SeqSet.synth(ctx, SEED + rank, a.nrec, a.nfam, a.mean_len)
+    bases = seqset.total_bases
+    total_bases = shard.sum_over_ranks(bases, device)
+    order = shard.global_order(SEED, a.nrec * world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    phase = {}
+
+    def step(ss):
+        kf = _lib.KFreqs.count(ctx, ss, a.k)
+        phase["count_ms"] = ctx.phase_ms(_lib.PHASE_COUNT_KERNEL)
+        phase["freq_entropy_ms"] = ctx.phase_ms(_lib.PHASE_FREQ_ENTROPY)
+        allf = shard.all_gather_kfreqs(ctx, kf, device) if world > 1 else kf
+        idx, delta, stats = allf.select(order, _lib.MODE_NMOST, a.n)
+        phase["select_ms"] = ctx.phase_ms(_lib.PHASE_SELECT)
+        return idx, delta, stats
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record(stream)
+        barrier()
+        return shard.max_over_ranks(e0.elapsed_time(e1), device) / steps, out
+
+    for _ in range(a.warmup):
+        step(seqset)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count
+    count_ms, fe_ms, sel_ms = [], [], []
+
+    def step_resident():
+        r = step(seqset)
+        count_ms.append(phase["count_ms"]); fe_ms.append(phase["freq_entropy_ms"]); sel_ms.append(phase["select_ms"])
+        return r
+
+    ms_step, (idx, delta, stats) = timed(step_resident, a.steps)
+    launches = (ctx.launch_count - launches0) // max(a.steps, 1)
+    clocks = sampler.stop() if rank == 0 else None
+    accepts = int(ctx._lib.dvs_select_last_accepts(ctx.handle))
+    value = total_bases / (ms_step * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel (k_count), timed live by CUDA events on its stream ----
+    kc_ms = float(np.mean(count_ms))
+    dim = 4 ** a.k
+    algo_bytes = bases + a.nrec * (8 * dim + 8)  # L + 8*4^k + 8 per record
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = algo_bytes / (kc_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_count", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
+                "kernel_ms": kc_ms, "algorithmic_bytes_per_launch": algo_bytes}
+
+    # ---- end to end through the host-buffer API: pinned host -> device copy inside the timed region ----
+    e2e = None
+    if not a.no_e2e:
+        try:
+            pinned = torch.empty(int(bases) + 64, dtype=torch.uint8, pin_memory=True)
+            host = pinned.numpy()
+            seqset.download(0, a.nrec, out=host)
+            offsets = seqset.offsets()
+            del seqset
+            seqset = None
+
+            def step_e2e():
+                ss = _lib.SeqSet.upload(ctx, host[: int(bases)], offsets)
+                r = step(ss)
+                ss.close()
+                return r
+
+            step_e2e()
+            ms_e2e, (idx2, _d2, _s2) = timed(step_e2e, max(1, min(a.steps, 2)))
+            assert idx2.tolist() == idx.tolist(), "e2e selection differs from the resident-input run"
+            d2h = idx.nbytes + delta.nbytes + 5 * 8 + 4
+            e2e = {"value": total_bases / (ms_e2e * 1e-3) / 1e9, "unit": UNIT,
+                   "h2d_bytes_per_step": int(bases + offsets.nbytes + order.nbytes), "d2h_bytes_per_step": int(d2h),
+                   "ms_per_step": ms_e2e, "upload_ms": ctx.phase_ms(_lib.PHASE_UPLOAD),
+                   "note": "pinned host buffer -> cudaMemcpyAsync -> count -> nmost -> read back indices/deltas"}
+        except Exception as exc:  # e.g. not enough host memory to pin the whole input
+            e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                   "error": f"{type(exc).__name__}: {exc}"}
+
+    base = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        if seqset is None:
+            seqset = _lib.SeqSet.synth(ctx, SEED, a.nrec, a.nfam, a.mean_len)
+        base = cpu_baseline(a, seqset, a.cpu_seconds)
+        base = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u8 bases -> u32 counts -> f64 frequencies/entropy/JSD", "data": "synthetic",
+                "config": workload_config(a, world), "roofline": roofline, "cpu_baseline": base, "e2e": e2e,
+                "gpu_launches": int(launches), "clocks": clocks,
+                "extra": {"count_kernel_gbp_per_s": bases / (kc_ms * 1e-3) / 1e9, "count_kernel_ms": kc_ms,
+                          "freq_entropy_ms": float(np.mean(fe_ms)), "nmost_wall_s": float(np.mean(sel_ms)) * 1e-3,
+                          "nmost_accepts": accepts, "total_gbp": total_bases / 1e9,
+                          "selected_head": idx[:8].tolist(), "total_jsd": float(stats[0])}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

@@ -16,6 +16,7 @@ LIB_PATH = _HERE / "libdvs_b200.so"
 
 DVS_OK, DVS_ERR_VALUE, DVS_ERR_CUDA, DVS_ERR_ARG = 0, 1, 2, 3
 MODE_NMOST, MODE_MAX_STDEV, MODE_MAX_COV = 0, 1, 2
+PHASE_COUNT_KERNEL, PHASE_FREQ_ENTROPY, PHASE_SELECT, PHASE_SKETCH, PHASE_MASH_PAIRS, PHASE_EUCLID, PHASE_UPLOAD = range(7)
 
 _vp = C.c_void_p
 _u32, _u64, _i32, _f64 = C.c_uint32, C.c_uint64, C.c_int, C.c_double
@@ -29,6 +30,8 @@ SIGNATURES = {
     "dvs_ctx_sync": (_i32, [_vp]),
     "dvs_ctx_stream": (_vp, [_vp]),
     "dvs_ctx_launch_count": (_u64, [_vp]),
+    "dvs_ctx_enable_timing": (_i32, [_vp, _i32]),
+    "dvs_ctx_phase_ms": (_f64, [_vp, _i32]),
     "dvs_seqset_upload": (_i32, [_vp, _vp, _vp, _u32, C.POINTER(_vp)]),
     "dvs_seqset_synth": (_i32, [_vp, _u64, _u32, _u32, _u64, C.POINTER(_vp)]),
     "dvs_synth_host": (_i32, [_u64, _u32, _u32, _u64, _u32, _u32, _vp, _vp]),
@@ -40,6 +43,8 @@ SIGNATURES = {
     "dvs_seqset_free": (None, [_vp]),
     "dvs_count_kmers": (_i32, [_vp, _vp, _i32, _i32, C.POINTER(_vp)]),
     "dvs_kfreqs_from_rows": (_i32, [_vp, _vp, _vp, _u32, _u64, C.POINTER(_vp)]),
+    "dvs_kfreqs_device_ptrs": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "dvs_kfreqs_from_device": (_i32, [_vp, _vp, _vp, _vp, _u32, _u64, C.POINTER(_vp)]),
     "dvs_kfreqs_nrec": (_u32, [_vp]),
     "dvs_kfreqs_dim": (_u64, [_vp]),
     "dvs_kfreqs_download": (_i32, [_vp, _vp, _u32, _u32, _vp, _vp, _vp, _vp]),
@@ -135,6 +140,12 @@ class Context:
 
     def sync(self) -> None:
         check(self._lib.dvs_ctx_sync(self.handle))
+
+    def enable_timing(self, on: bool = True) -> None:
+        check(self._lib.dvs_ctx_enable_timing(self.handle, int(on)))
+
+    def phase_ms(self, phase: int) -> float:
+        return float(self._lib.dvs_ctx_phase_ms(self.handle, int(phase)))
 
     @property
     def stream(self) -> int:
@@ -272,6 +283,19 @@ class KFreqs(_Handle):
         h = _vp()
         check(ctx._lib.dvs_kfreqs_from_rows(ctx.handle, ptr(rows), ptr(ent), rows.shape[0], rows.shape[1], C.byref(h)))
         return cls(ctx, h)
+
+    @classmethod
+    def from_device(cls, ctx: Context, rows_ptr: int, ent_ptr: int, valid_ptr: int, nrec: int, dim: int) -> "KFreqs":
+        """device-to-device copy from gathered device buffers (raw pointers on ctx's GPU)"""
+        h = _vp()
+        check(ctx._lib.dvs_kfreqs_from_device(ctx.handle, _vp(rows_ptr), _vp(ent_ptr), _vp(valid_ptr), nrec, dim,
+                                              C.byref(h)))
+        return cls(ctx, h)
+
+    def device_ptrs(self) -> tuple[int, int, int]:
+        a, b, c = _vp(), _vp(), _vp()
+        check(self.ctx._lib.dvs_kfreqs_device_ptrs(self.handle, C.byref(a), C.byref(b), C.byref(c)))
+        return int(a.value or 0), int(b.value or 0), int(c.value or 0)
 
     @property
     def nrec(self) -> int:

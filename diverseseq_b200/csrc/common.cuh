@@ -75,8 +75,15 @@ struct DevBuf {
 
 }  // namespace dvs
 
+constexpr int kNumPhases = 8;
+
 struct dvs_ctx {
     int device = 0;
+    // optional per-phase CUDA-event timing on the launching stream (dvs_ctx_enable_timing)
+    bool timing = false;
+    cudaEvent_t ev_start[kNumPhases] = {};
+    cudaEvent_t ev_stop[kNumPhases] = {};
+    bool ev_valid[kNumPhases] = {};
     int sm_count = 0;
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;
@@ -85,6 +92,26 @@ struct dvs_ctx {
     // pinned scratch for small device->host readbacks
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
+};
+
+// Records start/stop events for one phase around a scope when timing is enabled.
+struct PhaseTimer {
+    dvs_ctx* ctx;
+    int phase;
+    PhaseTimer(dvs_ctx* c, int ph) : ctx(c), phase(ph) {
+        if (ctx->timing) {
+            cudaEventRecord(ctx->ev_start[phase], ctx->stream);
+            ctx->ev_valid[phase] = false;
+        }
+    }
+    void stop() {
+        if (ctx && ctx->timing) {
+            cudaEventRecord(ctx->ev_stop[phase], ctx->stream);
+            ctx->ev_valid[phase] = true;
+        }
+        ctx = nullptr;
+    }
+    ~PhaseTimer() { stop(); }
 };
 
 // Front padding (bytes) before the first sequence byte so aligned halo loads at (addr-16) stay in

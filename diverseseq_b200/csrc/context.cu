@@ -71,12 +71,35 @@ void dvs_ctx_destroy(dvs_ctx* ctx) {
         cudaStreamDestroy(ctx->stream);
     }
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (int i = 0; i < kNumPhases; ++i) {
+        if (ctx->ev_start[i]) cudaEventDestroy(ctx->ev_start[i]);
+        if (ctx->ev_stop[i]) cudaEventDestroy(ctx->ev_stop[i]);
+    }
     delete ctx;
 }
 
 int dvs_ctx_sync(dvs_ctx* ctx) {
     DVS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return DVS_OK;
+}
+
+int dvs_ctx_enable_timing(dvs_ctx* ctx, int on) {
+    DVS_CUDA_TRY(cudaSetDevice(ctx->device));
+    if (on && !ctx->ev_start[0])
+        for (int i = 0; i < kNumPhases; ++i) {
+            DVS_CUDA_TRY(cudaEventCreate(&ctx->ev_start[i]));
+            DVS_CUDA_TRY(cudaEventCreate(&ctx->ev_stop[i]));
+        }
+    ctx->timing = on != 0;
+    return DVS_OK;
+}
+
+double dvs_ctx_phase_ms(dvs_ctx* ctx, int phase) {
+    if (phase < 0 || phase >= kNumPhases || !ctx->ev_valid[phase]) return -1.0;
+    if (cudaEventSynchronize(ctx->ev_stop[phase]) != cudaSuccess) return -1.0;
+    float ms = -1.0f;
+    if (cudaEventElapsedTime(&ms, ctx->ev_start[phase], ctx->ev_stop[phase]) != cudaSuccess) return -1.0;
+    return (double)ms;
 }
 
 void* dvs_ctx_stream(dvs_ctx* ctx) { return (void*)ctx->stream; }
@@ -132,6 +155,7 @@ int dvs_seqset_upload(dvs_ctx* ctx, const uint8_t* seqs, const uint64_t* offsets
     }
     dvs_seqset* s = nullptr;
     DVS_TRY(seqset_alloc(ctx, offsets, nrec, &s));
+    PhaseTimer pt(ctx, DVS_PHASE_UPLOAD);
     if (s->total) {
         cudaError_t e = cudaMemcpyAsync(s->data(), seqs, s->total, cudaMemcpyHostToDevice, ctx->stream);
         if (e != cudaSuccess) {
@@ -140,6 +164,7 @@ int dvs_seqset_upload(dvs_ctx* ctx, const uint8_t* seqs, const uint64_t* offsets
             return DVS_ERR_CUDA;
         }
     }
+    pt.stop();
     // the host buffers (seqs, offsets) may be pageable and reused by the caller: finish the copies
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {

@@ -328,16 +328,19 @@ int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dv
             return cudaGetLastError();
         };
         cudaError_t e;
+        PhaseTimer pt(ctx, DVS_PHASE_COUNT_KERNEL);
         if (ns4)
             e = smem ? launch(k_count<true, true>) : launch(k_count<true, false>);
         else
             e = smem ? launch(k_count<false, true>) : launch(k_count<false, false>);
+        pt.stop();
         if (e != cudaSuccess) {
             set_error("k_count launch failed: %s", cudaGetErrorString(e));
             return fail(DVS_ERR_CUDA);
         }
     }
     if (s->nrec) {
+        PhaseTimer pt(ctx, DVS_PHASE_FREQ_ENTROPY);
         k_freq_entropy<<<s->nrec, kEntThreads, kEntSmemBytes, st>>>(f->counts.p, dim, f->freqs.p, f->totals.p,
                                                                     f->entropy.p, f->valid.p, f->err.p,
                                                                     f->err_total.p);
@@ -377,6 +380,41 @@ int dvs_kfreqs_from_rows(dvs_ctx* ctx, const double* rows, const double* entropi
     }
     if (e != cudaSuccess) {
         set_error("dvs_kfreqs_from_rows failed: %s", cudaGetErrorString(e));
+        dvs_kfreqs_free(f);
+        return DVS_ERR_CUDA;
+    }
+    *out = f;
+    return DVS_OK;
+}
+
+int dvs_kfreqs_device_ptrs(const dvs_kfreqs* f, void** freqs, void** entropies, void** valid) {
+    if (freqs) *freqs = f->freqs.p;
+    if (entropies) *entropies = f->entropy.p;
+    if (valid) *valid = f->valid.p;
+    return DVS_OK;
+}
+
+int dvs_kfreqs_from_device(dvs_ctx* ctx, const void* d_rows, const void* d_entropies, const void* d_valid,
+                           uint32_t nrec, uint64_t dim, dvs_kfreqs** out) {
+    if (!ctx || !d_rows || !d_entropies || !d_valid || !out || dim == 0) {
+        set_error("dvs_kfreqs_from_device: bad argument");
+        return DVS_ERR_ARG;
+    }
+    dvs_kfreqs* f = nullptr;
+    DVS_TRY(kfreqs_alloc(ctx, nrec, dim, false, &f));
+    cudaStream_t st = ctx->stream;
+    cudaError_t e = cudaSuccess;
+    if (nrec) {
+        e = cudaMemcpyAsync(f->freqs.p, d_rows, (size_t)nrec * dim * sizeof(double), cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(f->entropy.p, d_entropies, nrec * sizeof(double), cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(f->valid.p, d_valid, nrec, cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(f->err.p, 0, nrec, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(f->err_total.p, 0, nrec * sizeof(double), st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(f->totals.p, 0, nrec * sizeof(uint64_t), st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    if (e != cudaSuccess) {
+        set_error("dvs_kfreqs_from_device failed: %s", cudaGetErrorString(e));
         dvs_kfreqs_free(f);
         return DVS_ERR_CUDA;
     }

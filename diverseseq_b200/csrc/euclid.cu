@@ -92,7 +92,9 @@ extern "C" int dvs_euclid_distances(dvs_ctx* ctx, const dvs_kfreqs* f, uint32_t 
     DevBuf<double> d_out;
     DVS_TRY(d_out.alloc(nrows * n));
     dim3 grid((unsigned)((n + kEuT - 1) / kEuT), (unsigned)((nrows + kEuT - 1) / kEuT));
+    PhaseTimer pt(ctx, DVS_PHASE_EUCLID);
     k_euclid_tiles<<<grid, 256, 0, ctx->stream>>>(f->freqs.p, f->dim, (uint32_t)n, row_begin, row_end, d_out.p);
+    pt.stop();
     DVS_LAUNCHED(ctx);
     DVS_CUDA_TRY(cudaMemcpyAsync(dist, d_out.p, nrows * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     DVS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));

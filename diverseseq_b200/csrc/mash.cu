@@ -438,6 +438,7 @@ int dvs_mash_sketch(dvs_ctx* ctx, const dvs_seqset* s, int k, uint64_t sketch_si
         }                                                              \
     } while (0)
     TRY_S(cudaMemsetAsync(sk->lens.p, 0, nrec * sizeof(uint32_t), st));
+    PhaseTimer pt(ctx, DVS_PHASE_SKETCH);
 
     const bool fast = (num_states == 4 && k <= 16);
     // per-record threshold / capacity; only records with k-mers take part
@@ -603,10 +604,12 @@ int dvs_mash_distances(dvs_ctx* ctx, const dvs_sketches* sk, int k, uint64_t ske
     DVS_TRY(d_err.alloc(1));
     DVS_CUDA_TRY(cudaMemsetAsync(d_err.p, 0, sizeof(int), st));
     const size_t total = nrows * n;
+    PhaseTimer pt(ctx, DVS_PHASE_MASH_PAIRS);
     k_mash_pairs<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(sk->data.p, sk->lens.p, sk->stride, (uint32_t)n, k,
                                                                    sketch_size, row_begin, row_end, d_dist.p,
                                                                    inter ? d_inter.p : nullptr, uni ? d_uni.p : nullptr,
                                                                    d_err.p);
+    pt.stop();
     DVS_LAUNCHED(ctx);
     int h_err = 0;
     DVS_CUDA_TRY(cudaMemcpyAsync(dist, d_dist.p, total * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -376,6 +376,7 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
     k_set_members<<<(unsigned)((init.size() + 255) / 256), 256, 0, st>>>(is_member.p, d_init.p, (unsigned)init.size(), 1);
     DVS_LAUNCHED(ctx);
 
+    PhaseTimer pt(ctx, DVS_PHASE_SELECT);
     Selector sel{ctx, f, dim, st, (SelScal*)ctx->pinned};
     SelState* cur = &A;
     SelState* alt = &B;

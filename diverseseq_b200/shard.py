@@ -1,0 +1,98 @@
+"""Multi-GPU sharding of the hot path: one process per GPU, torch.distributed
+for the plumbing (NCCL on GPUs, gloo in the CPU tests).
+
+* counting / sketching: records are independent -> each rank counts its own shard, no collective.
+* nmost / max: the selection state is tiny and every decision is order dependent, so the per-rank
+  frequency rows (N x 4^k f64) are all-gathered once and every rank replays the same selection on
+  the full row set (replicated state, identical results on every rank, no per-step exchange).
+* distance matrices: rows of the symmetric matrix are block-partitioned; each rank computes its
+  row block against all columns and the blocks are all-gathered for the (CPU) clustering.
+
+The functions here only touch torch tensors / python ints so they run unchanged under gloo.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_bounds(n_items: int, world: int, rank: int) -> tuple[int, int]:
+    """contiguous block partition [begin, end) of n_items over world ranks (sizes differ by <= 1)"""
+    base, rem = divmod(n_items, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def global_order(seed: int, n_total: int) -> np.ndarray:
+    """the shuffled examination order, identical on every rank (cli.py:445-446 uses default_rng(seed))"""
+    return np.random.default_rng(seed).permutation(n_total).astype(np.uint32)
+
+
+def all_gather_concat(t, group=None):
+    """all-gather equally shaped tensors and concatenate along dim 0 in rank order"""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t.contiguous(), group=group) if t.is_cuda else \
+        dist.all_gather(list(out.chunk(world, dim=0)), t.contiguous(), group=group)
+    return out
+
+
+def max_over_ranks(value: float, device=None, group=None) -> float:
+    """timing rule: a multi-GPU duration is the max over ranks"""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item())
+
+
+def sum_over_ranks(value: float, device=None, group=None) -> float:
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return float(t.item())
+
+
+class DeviceArray:
+    """zero-copy torch view of a raw device pointer owned by libdvs_b200 (via __cuda_array_interface__)"""
+
+    def __init__(self, ptr: int, shape: tuple, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def kfreqs_as_tensors(kf, device):
+    """(rows [nrec, dim] f64, entropies [nrec] f64, valid [nrec] u8) torch views of a KFreqs"""
+    import torch
+
+    rows_p, ent_p, val_p = kf.device_ptrs()
+    n, d = kf.nrec, kf.dim
+    rows = torch.as_tensor(DeviceArray(rows_p, (n, d), "<f8"), device=device)
+    ent = torch.as_tensor(DeviceArray(ent_p, (n,), "<f8"), device=device)
+    valid = torch.as_tensor(DeviceArray(val_p, (n,), "|u1"), device=device)
+    return rows, ent, valid
+
+
+def all_gather_kfreqs(ctx, kf, device, group=None):
+    """every rank ends up with a KFreqs holding the rows of all ranks, in rank order"""
+    import torch
+
+    from . import _lib
+
+    rows, ent, valid = kfreqs_as_tensors(kf, device)
+    ctx.sync()  # the rows were produced on the library's stream
+    g_rows = all_gather_concat(rows, group)
+    g_ent = all_gather_concat(ent, group)
+    g_valid = all_gather_concat(valid, group)
+    torch.cuda.synchronize(device)
+    return _lib.KFreqs.from_device(ctx, g_rows.data_ptr(), g_ent.data_ptr(), g_valid.data_ptr(),
+                                   g_rows.shape[0], g_rows.shape[1])

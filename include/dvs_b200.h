@@ -57,6 +57,19 @@ void* dvs_ctx_stream(dvs_ctx* ctx);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 uint64_t dvs_ctx_launch_count(dvs_ctx* ctx);
 
+/* per-phase device timing with CUDA events recorded on the ctx stream around the named kernels
+ * (bench.py's roofline numbers).  dvs_ctx_phase_ms returns the duration of the most recent
+ * occurrence of the phase in milliseconds, or a negative value if it has not run. */
+#define DVS_PHASE_COUNT_KERNEL 0   /* k_count: the k-mer histogram kernel alone */
+#define DVS_PHASE_FREQ_ENTROPY 1   /* k_freq_entropy: rows + exact entropies */
+#define DVS_PHASE_SELECT 2         /* all device work of one dvs_select */
+#define DVS_PHASE_SKETCH 3         /* all device work of one dvs_mash_sketch */
+#define DVS_PHASE_MASH_PAIRS 4     /* k_mash_pairs */
+#define DVS_PHASE_EUCLID 5         /* k_euclid_tiles */
+#define DVS_PHASE_UPLOAD 6         /* host->device sequence copy of dvs_seqset_upload */
+int dvs_ctx_enable_timing(dvs_ctx* ctx, int on);
+double dvs_ctx_phase_ms(dvs_ctx* ctx, int phase);
+
 /* ---- sequences: what ZarrStore::read_uint8_array hands the hot path (src/zarr_io.rs:309) - */
 int dvs_seqset_upload(dvs_ctx* ctx, const uint8_t* seqs, const uint64_t* offsets, uint32_t nrec,
                       dvs_seqset** out);
@@ -87,6 +100,13 @@ int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dv
  * frequencies exactly as KmerSeq::new does.  entropies_or_null == NULL -> recompute. */
 int dvs_kfreqs_from_rows(dvs_ctx* ctx, const double* rows, const double* entropies_or_null, uint32_t nrec,
                          uint64_t dim, dvs_kfreqs** out);
+/* multi-GPU plumbing: raw DEVICE pointers of the row matrix [nrec][dim] f64, the
+ * entropies [nrec] f64 and the validity flags [nrec] u8, so a collective library (NCCL) can
+ * all-gather shards; and the inverse, a kfreqs built by device-to-device copy from gathered
+ * device buffers that live on ctx's GPU. */
+int dvs_kfreqs_device_ptrs(const dvs_kfreqs* f, void** freqs, void** entropies, void** valid);
+int dvs_kfreqs_from_device(dvs_ctx* ctx, const void* d_rows, const void* d_entropies, const void* d_valid,
+                           uint32_t nrec, uint64_t dim, dvs_kfreqs** out);
 uint32_t dvs_kfreqs_nrec(const dvs_kfreqs* f);
 uint64_t dvs_kfreqs_dim(const dvs_kfreqs* f);
 /* any output may be NULL.  counts: uint64 like Rust usize (LazySeq.get_kcounts, src/record.rs:247);
