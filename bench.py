@@ -237,12 +237,17 @@ def main():
     phase = {}
 
     def step(ss):
+        t0 = time.perf_counter()
         kf = _lib.KFreqs.count(ctx, ss, a.k)
+        t1 = time.perf_counter()
         phase["count_ms"] = ctx.phase_ms(_lib.PHASE_COUNT_KERNEL)
         phase["freq_entropy_ms"] = ctx.phase_ms(_lib.PHASE_FREQ_ENTROPY)
         allf = shard.all_gather_kfreqs(ctx, kf, device) if world > 1 else kf
+        t2 = time.perf_counter()
         idx, delta, stats = allf.select(order, _lib.MODE_NMOST, a.n)
+        t3 = time.perf_counter()
         phase["select_ms"] = ctx.phase_ms(_lib.PHASE_SELECT)
+        phase["host_wall_ms"] = {"count_call": (t1 - t0) * 1e3, "gather": (t2 - t1) * 1e3, "select_call": (t3 - t2) * 1e3}
         return idx, delta, stats
 
     def timed(fn, steps):
@@ -336,7 +341,8 @@ def main():
                 "extra": {"count_kernel_gbp_per_s": bases / (kc_ms * 1e-3) / 1e9, "count_kernel_ms": kc_ms,
                           "freq_entropy_ms": float(np.mean(fe_ms)), "nmost_wall_s": float(np.mean(sel_ms)) * 1e-3,
                           "nmost_accepts": accepts, "total_gbp": total_bases / 1e9,
-                          "selected_head": idx[:8].tolist(), "total_jsd": float(stats[0])}}
+                          "selected_head": idx[:8].tolist(), "total_jsd": float(stats[0]),
+                          "host_wall_ms_last_step": phase.get("host_wall_ms")}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

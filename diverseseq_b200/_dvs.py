@@ -181,6 +181,12 @@ def _stat_mode(stat: str) -> int:
     return _lib.MODE_MAX_STDEV if stat == "stdev" else _lib.MODE_MAX_COV
 
 
+def _read_array(store, seqid: str) -> np.ndarray:
+    """sequence bytes of `seqid` from any store exposing the reference's `read(seqid)` (src/zarr_py.rs:181)"""
+    fast = getattr(store, "_array", None)
+    return fast(seqid) if fast is not None else np.frombuffer(bytes(store.read(seqid)), dtype=np.uint8)
+
+
 def _rows_and_order(seqids):
     """distinct seqids -> row index; order[i] = row of seqids[i] (the seqid is the identity)"""
     row_of: dict[str, int] = {}
@@ -194,7 +200,7 @@ def _select_from_store(store, seqids, k, num_states, mode, min_size, max_size) -
     ctx = _lib.default_context()
     seqids = list(store.unique_seqids if seqids is None else seqids)
     names, order = _rows_and_order(seqids)
-    seqset = _lib.SeqSet.from_seqs(ctx, [store._array(n) for n in names])
+    seqset = _lib.SeqSet.from_seqs(ctx, [_read_array(store, n) for n in names])
     if k == 0:
         raise ValueError("k cannot be 0")
     if len(seqids) < min_size:  # before any counting, like records.rs:323-325
@@ -320,7 +326,7 @@ class LazySeq:
         if k == 0:
             raise ValueError("k cannot be 0")
         ctx = _lib.default_context()
-        seqset = _lib.SeqSet.from_seqs(ctx, [self._storage._array(self._seqid)])
+        seqset = _lib.SeqSet.from_seqs(ctx, [_read_array(self._storage, self._seqid)])
         return _lib.KFreqs.count(ctx, seqset, k, self._num_states)
 
     def get_kcounts(self, k: int) -> list[int]:

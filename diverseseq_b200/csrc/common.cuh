@@ -45,26 +45,37 @@ const char* get_error();
         }                                                                                   \
     } while (0)
 
-// RAII device buffer (cudaMalloc / cudaFree)
+// Stream used for stream-ordered allocation by the API call running on this thread (set by
+// dvs::enter).  Allocations come from the device's default memory pool (cudaMallocAsync) whose
+// release threshold is raised at context creation, so the per-call scratch and result buffers of
+// repeated calls are recycled instead of paying cudaMalloc/cudaFree (which synchronise the device).
+extern thread_local cudaStream_t tl_stream;
+
+// RAII device buffer
 template <class T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    cudaStream_t stream = nullptr;  // stream the block was allocated on (nullptr: plain cudaMalloc)
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
+        if (p) {
+            if (stream) cudaFreeAsync(p, stream); else cudaFree(p);
+        }
         p = nullptr;
         n = 0;
     }
     int alloc(size_t count) {
         release();
         if (count == 0) count = 1;
-        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        stream = tl_stream;
+        cudaError_t e = stream ? cudaMallocAsync((void**)&p, count * sizeof(T), stream)
+                               : cudaMalloc((void**)&p, count * sizeof(T));
         if (e != cudaSuccess) {
-            set_error("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+            set_error("device allocation of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
             p = nullptr;
             return DVS_ERR_CUDA;
         }
@@ -93,6 +104,14 @@ struct dvs_ctx {
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
 };
+
+namespace dvs {
+// every API entry: select the device and route this thread's allocations to the ctx stream
+inline cudaError_t enter(dvs_ctx* ctx) {
+    tl_stream = ctx->stream;
+    return cudaSetDevice(ctx->device);
+}
+}  // namespace dvs
 
 // Records start/stop events for one phase around a scope when timing is enabled.
 struct PhaseTimer {

@@ -6,6 +6,7 @@
 namespace dvs {
 
 static thread_local std::string g_error;
+thread_local cudaStream_t tl_stream = nullptr;
 
 void set_error(const char* fmt, ...) {
     char buf[1024];
@@ -57,6 +58,12 @@ int dvs_ctx_create(int device, dvs_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     DVS_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    {
+        cudaMemPool_t pool;
+        DVS_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = ~0ULL;  // never trim: freed blocks stay in the pool for the next call
+        DVS_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     ctx->pinned_bytes = 1 << 20;
     DVS_CUDA_TRY(cudaHostAlloc(&ctx->pinned, ctx->pinned_bytes, cudaHostAllocDefault));
     *out = ctx;
@@ -65,7 +72,7 @@ int dvs_ctx_create(int device, dvs_ctx** out) {
 
 void dvs_ctx_destroy(dvs_ctx* ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
+    dvs::enter(ctx);
     if (ctx->stream) {
         cudaStreamSynchronize(ctx->stream);
         cudaStreamDestroy(ctx->stream);
@@ -117,7 +124,7 @@ static int seqset_alloc(dvs_ctx* ctx, const uint64_t* offsets, uint32_t nrec, dv
         set_error("offsets[0] must be 0");
         return DVS_ERR_ARG;
     }
-    DVS_CUDA_TRY(cudaSetDevice(ctx->device));
+    DVS_CUDA_TRY(dvs::enter(ctx));
     auto* s = new dvs_seqset();
     s->device = ctx->device;
     s->nrec = nrec;
@@ -190,7 +197,7 @@ int dvs_seqset_download(dvs_ctx* ctx, const dvs_seqset* s, uint32_t first, uint3
         return DVS_ERR_ARG;
     }
     uint64_t b = s->h_offsets[first], e = s->h_offsets[first + count];
-    DVS_CUDA_TRY(cudaSetDevice(ctx->device));
+    DVS_CUDA_TRY(dvs::enter(ctx));
     if (e > b) DVS_CUDA_TRY(cudaMemcpyAsync(seqs_out, s->data() + b, e - b, cudaMemcpyDeviceToHost, ctx->stream));
     DVS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return DVS_OK;

@@ -41,17 +41,16 @@ __device__ __forceinline__ uint32_t pack16(uint4 v) {
 
 __device__ __forceinline__ uint4 ldg16(const uint8_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
+// ---- generic kernel (any num_states): per-byte path only ----------------------------------------
 // SMEM: bins [part*part_bins, (part+1)*part_bins) in shared memory; else global atomics.
-template <bool NS4, bool SMEM>
+template <bool SMEM>
 __global__ void __launch_bounds__(kCountThreads)
-k_count(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offsets, const CountWork* __restrict__ work,
-        uint32_t nwork, uint32_t* __restrict__ next_item, int k, uint32_t num_states, uint64_t dim,
-        uint32_t part_bins, uint32_t* __restrict__ counts) {
+k_count_generic(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offsets,
+                const CountWork* __restrict__ work, uint32_t nwork, uint32_t* __restrict__ next_item, int k,
+                uint32_t num_states, uint64_t dim, uint32_t part_bins, uint32_t* __restrict__ counts) {
     extern __shared__ uint32_t hist[];
     __shared__ uint32_t s_item;
     const int tid = threadIdx.x;
-    const uint32_t mask = (k >= 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
-
     for (;;) {
         if (tid == 0) s_item = atomicAdd(next_item, 1u);
         __syncthreads();
@@ -65,50 +64,30 @@ k_count(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offsets, 
             for (uint32_t i = tid; i < part_bins; i += kCountThreads) hist[i] = 0;
             __syncthreads();
         }
-        auto bump = [&](uint32_t idx) {
-            if (SMEM) {
-                uint32_t local = idx - part_base;
-                if (local < part_bins) atomicAdd(&hist[local], 1u);
-            } else {
-                atomicAdd(&grow[idx], 1u);
-            }
-        };
-
         for (uint64_t a = w.begin + (uint64_t)tid * 16; a < w.end; a += (uint64_t)kCountThreads * 16) {
             const uint4 cur = ldg16(seqs + a);
             const uint4 prev = ldg16(seqs + a - 16);  // front pad keeps a-16 inside the allocation
-            bool fast = false;
-            if (NS4) {
-                uint32_t any = cur.x | cur.y | cur.z | cur.w | prev.x | prev.y | prev.z | prev.w;
-                fast = ((any & 0xFCFCFCFCu) == 0) && (a >= start + 16) && (a + 16 <= end);
-            }
-            if (fast) {
-                const uint32_t pc = pack16(cur), pp = pack16(prev);
+            const uint32_t wv[8] = {prev.x, prev.y, prev.z, prev.w, cur.x, cur.y, cur.z, cur.w};
+            uint32_t run = 0;
+            uint64_t idx = 0;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    uint32_t idx = __funnelshift_r(pc, pp, 2 * (15 - j)) & mask;
-                    bump(idx);
-                }
-            } else {
-                // per-byte path: invalid bytes, record edges, or num_states != 4
-                const uint32_t wv[8] = {prev.x, prev.y, prev.z, prev.w, cur.x, cur.y, cur.z, cur.w};
-                uint32_t run = 0;
-                uint64_t idx = 0;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const uint64_t p = a - 16 + i;
-                    uint32_t b = (wv[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-                    if (p < start || p >= end) b = 0xFFu;
-                    if (b >= num_states) {
-                        run = 0;
-                        idx = 0;
-                    } else {
-                        if (NS4)
-                            idx = ((idx << 2) | b) & mask;
-                        else
-                            idx = (idx * num_states + b) % dim;
-                        ++run;
-                        if (i >= 16 && run >= (uint32_t)k) bump((uint32_t)idx);
+            for (int i = 0; i < 32; ++i) {
+                const uint64_t p = a - 16 + i;
+                uint32_t b = (wv[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+                if (p < start || p >= end) b = 0xFFu;
+                if (b >= num_states) {
+                    run = 0;
+                    idx = 0;
+                } else {
+                    idx = (idx * num_states + b) % dim;
+                    ++run;
+                    if (i >= 16 && run >= (uint32_t)k) {
+                        if (SMEM) {
+                            uint32_t local = (uint32_t)idx - part_base;
+                            if (local < part_bins) atomicAdd(&hist[local], 1u);
+                        } else {
+                            atomicAdd(&grow[idx], 1u);
+                        }
                     }
                 }
             }
@@ -118,6 +97,158 @@ k_count(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offsets, 
             for (uint32_t i = tid; i < part_bins; i += kCountThreads) {
                 uint32_t c = hist[i];
                 if (c && (uint64_t)part_base + i < dim) atomicAdd(&grow[part_base + i], c);
+            }
+        }
+        __syncthreads();  // s_item / hist reuse
+    }
+}
+
+// ---- num_states == 4 kernel ------------------------------------------------------------------------
+// MODE 0: shared-memory histogram of 4^k bins, one ATOMS per k-mer            (k = 7)
+// MODE 1: as 0 but only bins of part `w.part` (several passes over the bytes)   (k = 8)
+// MODE 2: global RED.ADD into the record's row                                  (k >= 9)
+// MODE 3: SUPER-K-MERS: histogram the (k+1)-mers ending at ODD positions (4^(k+1) bins); each one
+//         carries two k-mers (its prefix and its suffix), so the ATOMS count halves.  (k+1)-windows
+//         that contain an invalid byte / cross the record start fall back to a small side histogram
+//         of single k-mers.  The flush folds both into k-mer counts:
+//         cnt[x] = side[x] + sum_b h[(x<<2)|b] + sum_a h[(a<<2k)|x].             (k <= 6)
+// Each warp walks a contiguous span of its work item in 512-byte steps (lane l owns bytes
+// [16l,16l+16)); the k-byte halo of lane l is the packed block of lane l-1 (warp shuffle), lane 0
+// keeps lane 31's block of the previous step, so every sequence byte is loaded exactly once.
+constexpr int MODE_SMEM = 0, MODE_SMEM_PARTS = 1, MODE_GLOBAL = 2, MODE_SUPER = 3;
+
+template <int MODE>
+__global__ void __launch_bounds__(kCountThreads)
+k_count(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offsets, const CountWork* __restrict__ work,
+        uint32_t nwork, uint32_t* __restrict__ next_item, int k, uint64_t dim, uint32_t part_bins,
+        uint32_t* __restrict__ counts) {
+    extern __shared__ uint32_t hist[];
+    __shared__ uint32_t s_item;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int kWarps = kCountThreads / 32;
+    const int kk = (MODE == MODE_SUPER) ? k + 1 : k;                       // bases per histogrammed word
+    const uint32_t mask = (kk >= 16) ? 0xFFFFFFFFu : ((1u << (2 * kk)) - 1u);
+    const uint32_t mask_k = (k >= 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
+    const uint32_t hist_words = (MODE == MODE_SUPER) ? (uint32_t)(dim * 4 + dim) : part_bins;
+    uint32_t* side = hist + dim * 4;  // MODE_SUPER only: single k-mer histogram after the (k+1)-mer table
+
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(next_item, 1u);
+        __syncthreads();
+        const uint32_t item = s_item;
+        if (item >= nwork) break;
+        const CountWork w = work[item];
+        const uint64_t start = offsets[w.rec], end = offsets[w.rec + 1];
+        const uint32_t part_base = (MODE == MODE_SMEM_PARTS) ? w.part * part_bins : 0u;
+        uint32_t* grow = counts + (size_t)w.rec * dim;
+        if (MODE != MODE_GLOBAL) {
+            for (uint32_t i = tid; i < hist_words; i += kCountThreads) hist[i] = 0;
+            __syncthreads();
+        }
+        auto bump = [&](uint32_t idx) {  // one k-mer (MODE 0/1/2) or one (k+1)-mer (MODE 3)
+            if (MODE == MODE_SMEM || MODE == MODE_SUPER) {
+                atomicAdd(&hist[idx], 1u);
+            } else if (MODE == MODE_SMEM_PARTS) {
+                uint32_t local = idx - part_base;
+                if (local < part_bins) atomicAdd(&hist[local], 1u);
+            } else {
+                atomicAdd(&grow[idx], 1u);
+            }
+        };
+        auto bump_single = [&](uint32_t idx_k) {  // MODE 3 fallback: one k-mer into the side table
+            atomicAdd(&side[idx_k], 1u);
+        };
+
+        // this warp's contiguous span of the item, in 512-byte steps
+        const uint64_t bytes = w.end - w.begin;
+        const uint64_t span = ((bytes + kWarps - 1) / kWarps + 511) & ~511ULL;
+        const uint64_t s0 = w.begin + (uint64_t)warp * span;
+        const uint64_t s1 = min(w.end, s0 + span);
+        uint32_t carry_pc = 0;
+        bool carry_ok = false;
+        uint4 cur = make_uint4(~0u, ~0u, ~0u, ~0u);
+        if (s0 < s1) {
+            if (s0 + 16 * lane < s1) cur = ldg16(seqs + s0 + 16 * lane);
+            // halo of lane 0 for the first step: the 16 bytes before the span
+            const uint4 h = ldg16(seqs + s0 - 16);  // front pad keeps this inside the allocation
+            carry_ok = (((h.x | h.y | h.z | h.w) & 0xFCFCFCFCu) == 0) && (s0 >= start + 16) && (s0 <= end);
+            carry_pc = pack16(h);
+        }
+        for (uint64_t pos = s0; pos < s1; pos += 512) {
+            const uint64_t a = pos + 16 * lane;
+            // prefetch the next step while this one is histogrammed
+            uint4 nxt = make_uint4(~0u, ~0u, ~0u, ~0u);
+            if (a + 512 < s1) nxt = ldg16(seqs + a + 512);
+            const bool ok = (((cur.x | cur.y | cur.z | cur.w) & 0xFCFCFCFCu) == 0) && (a >= start) && (a + 16 <= end) &&
+                            (a < s1);
+            const uint32_t pc = pack16(cur);
+            uint32_t pp = __shfl_up_sync(0xffffffffu, pc, 1);
+            bool prev_ok = __shfl_up_sync(0xffffffffu, (int)ok, 1) != 0;
+            if (lane == 0) {
+                pp = carry_pc;
+                prev_ok = carry_ok;
+            }
+            carry_pc = __shfl_sync(0xffffffffu, pc, 31);
+            carry_ok = __shfl_sync(0xffffffffu, (int)ok, 31) != 0;
+            if (a < s1) {
+                if (ok && prev_ok) {
+                    if (MODE == MODE_SUPER) {
+#pragma unroll
+                        for (int j = 1; j < 16; j += 2) bump(__funnelshift_r(pc, pp, 2 * (15 - j)) & mask);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) bump(__funnelshift_r(pc, pp, 2 * (15 - j)) & mask);
+                    }
+                } else {
+                    // per-byte path: invalid bytes or record edges inside [a-16, a+16)
+                    const uint4 prev = ldg16(seqs + a - 16);
+                    const uint32_t wv[8] = {prev.x, prev.y, prev.z, prev.w, cur.x, cur.y, cur.z, cur.w};
+                    uint32_t run = 0, idx = 0, run_even = 0, idx_even = 0;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const uint64_t p = a - 16 + i;
+                        uint32_t b = (wv[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+                        if (p < start || p >= end) b = 0xFFu;
+                        if (b >= 4u) {
+                            run = 0;
+                            idx = 0;
+                        } else {
+                            idx = ((idx << 2) | b) & mask;
+                            ++run;
+                        }
+                        if (i < 16) continue;
+                        if (MODE != MODE_SUPER) {
+                            if (run >= (uint32_t)k) bump(idx);
+                        } else if ((i & 1) == 0) {  // even position: decided together with its odd partner
+                            run_even = run;
+                            idx_even = idx;
+                        } else if (run >= (uint32_t)(k + 1)) {
+                            bump(idx);  // both k-mers valid: one (k+1)-mer
+                        } else {
+                            if (run_even >= (uint32_t)k) bump_single(idx_even & mask_k);
+                            if (run >= (uint32_t)k) bump_single(idx & mask_k);
+                        }
+                    }
+                }
+            }
+            cur = nxt;
+        }
+        if (MODE != MODE_GLOBAL) {
+            __syncthreads();
+            if (MODE == MODE_SUPER) {
+                for (uint32_t x = tid; x < (uint32_t)dim; x += kCountThreads) {
+                    uint32_t c = side[x];
+#pragma unroll
+                    for (uint32_t b = 0; b < 4; ++b) c += hist[(x << 2) | b];          // x is the prefix k-mer
+#pragma unroll
+                    for (uint32_t a4 = 0; a4 < 4; ++a4) c += hist[(a4 << (2 * k)) | x];  // x is the suffix k-mer
+                    if (c) atomicAdd(&grow[x], c);
+                }
+            } else {
+                for (uint32_t i = tid; i < part_bins; i += kCountThreads) {
+                    uint32_t c = hist[i];
+                    if (c && (uint64_t)part_base + i < dim) atomicAdd(&grow[part_base + i], c);
+                }
             }
         }
         __syncthreads();  // s_item / hist reuse
@@ -197,7 +328,7 @@ static bool pow_dim(int num_states, int k, uint64_t* dim) {
 }
 
 static int kfreqs_alloc(dvs_ctx* ctx, uint32_t nrec, uint64_t dim, bool with_counts, dvs_kfreqs** out) {
-    DVS_CUDA_TRY(cudaSetDevice(ctx->device));
+    DVS_CUDA_TRY(dvs::enter(ctx));
     auto* f = new dvs_kfreqs();
     f->device = ctx->device;
     f->nrec = nrec;
@@ -244,7 +375,7 @@ int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dv
         set_error("dvs_count_kmers: num_states^k = %d^%d does not fit a dense u32-indexed table", num_states, k);
         return DVS_ERR_ARG;
     }
-    DVS_CUDA_TRY(cudaSetDevice(ctx->device));
+    DVS_CUDA_TRY(dvs::enter(ctx));
     size_t free_b = 0, total_b = 0;
     DVS_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
     const double need = (double)s->nrec * (double)dim * 12.0;
@@ -277,21 +408,29 @@ int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dv
     const bool ns4 = (num_states == 4);
     const size_t max_hist_bytes = std::min<size_t>(ctx->smem_optin > 4096 ? ctx->smem_optin - 2048 : 0, 128 * 1024);
     uint32_t nparts = 1, part_bins = (uint32_t)std::min<uint64_t>(dim, 1u << 31);
-    bool smem = true;
-    if (dim * 4 > max_hist_bytes) {
+    int mode = MODE_SMEM;
+    size_t hist_bytes = (size_t)dim * 4;
+    if (ns4 && dim * 20 <= 96 * 1024) {  // (k+1)-mer table + side table: k <= 6 -> at most 80 KB
+        mode = MODE_SUPER;
+        hist_bytes = (size_t)dim * 20;
+    } else if (dim * 4 > max_hist_bytes) {
         uint64_t bins_per = max_hist_bytes / 4;
         uint64_t np = (dim + bins_per - 1) / bins_per;
         if (np <= 2) {
+            mode = MODE_SMEM_PARTS;
             nparts = (uint32_t)np;
             part_bins = (uint32_t)((dim + np - 1) / np);
+            hist_bytes = (size_t)part_bins * 4;
         } else {
-            smem = false;
+            mode = MODE_GLOBAL;
+            hist_bytes = 0;
         }
     }
-    const size_t hist_bytes = smem ? (size_t)part_bins * 4 : 0;
+    const bool smem = (mode != MODE_GLOBAL);
 
     // ---- work list: (record, part, aligned range) ----
-    const int ctas_per_sm = smem ? (hist_bytes <= 32 * 1024 ? 3 : (hist_bytes <= 100 * 1024 ? 2 : 1)) : 4;
+    int ctas_per_sm = 4;
+    if (smem) ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (ctx->smem_optin + 1024) / (hist_bytes + 1024)));
     const uint32_t grid = (uint32_t)(ctx->sm_count * ctas_per_sm);
     uint64_t chunk = 1 << 20;
     {
@@ -315,12 +454,23 @@ int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dv
         if (d_work.alloc(work.size()) != DVS_OK || d_next.alloc(1) != DVS_OK) return fail(DVS_ERR_CUDA);
         TRY_F(cudaMemcpyAsync(d_work.p, work.data(), work.size() * sizeof(CountWork), cudaMemcpyHostToDevice, st));
         TRY_F(cudaMemsetAsync(d_next.p, 0, sizeof(uint32_t), st));
-        auto launch = [&](auto kern) -> cudaError_t {
-            if (hist_bytes > 48 * 1024) {
-                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes);
-                if (e != cudaSuccess) return e;
-            }
-            uint32_t g = (uint32_t)std::min<size_t>(grid, work.size());
+        const uint32_t g = (uint32_t)std::min<size_t>(grid, work.size());
+        auto set_smem = [&](auto kern) -> cudaError_t {
+            return hist_bytes > 48 * 1024
+                       ? cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes)
+                       : cudaSuccess;
+        };
+        auto launch4 = [&](auto kern) -> cudaError_t {
+            cudaError_t e = set_smem(kern);
+            if (e != cudaSuccess) return e;
+            kern<<<g, kCountThreads, hist_bytes, st>>>(s->data(), s->offsets.p, d_work.p, (uint32_t)work.size(),
+                                                       d_next.p, k, dim, part_bins, f->counts.p);
+            ctx->launches++;
+            return cudaGetLastError();
+        };
+        auto launch_generic = [&](auto kern) -> cudaError_t {
+            cudaError_t e = set_smem(kern);
+            if (e != cudaSuccess) return e;
             kern<<<g, kCountThreads, hist_bytes, st>>>(s->data(), s->offsets.p, d_work.p, (uint32_t)work.size(),
                                                        d_next.p, k, (uint32_t)num_states, dim, part_bins,
                                                        f->counts.p);
@@ -329,10 +479,16 @@ int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dv
         };
         cudaError_t e;
         PhaseTimer pt(ctx, DVS_PHASE_COUNT_KERNEL);
-        if (ns4)
-            e = smem ? launch(k_count<true, true>) : launch(k_count<true, false>);
+        if (!ns4)
+            e = smem ? launch_generic(k_count_generic<true>) : launch_generic(k_count_generic<false>);
+        else if (mode == MODE_SUPER)
+            e = launch4(k_count<MODE_SUPER>);
+        else if (mode == MODE_SMEM)
+            e = launch4(k_count<MODE_SMEM>);
+        else if (mode == MODE_SMEM_PARTS)
+            e = launch4(k_count<MODE_SMEM_PARTS>);
         else
-            e = smem ? launch(k_count<false, true>) : launch(k_count<false, false>);
+            e = launch4(k_count<MODE_GLOBAL>);
         pt.stop();
         if (e != cudaSuccess) {
             set_error("k_count launch failed: %s", cudaGetErrorString(e));
@@ -432,7 +588,7 @@ int dvs_kfreqs_download(dvs_ctx* ctx, const dvs_kfreqs* f, uint32_t first, uint3
         return DVS_ERR_ARG;
     }
     if (count == 0) return DVS_OK;
-    DVS_CUDA_TRY(cudaSetDevice(ctx->device));
+    DVS_CUDA_TRY(dvs::enter(ctx));
     cudaStream_t st = ctx->stream;
     const size_t n = (size_t)count * f->dim;
     std::vector<uint32_t> tmp;
@@ -477,7 +633,7 @@ int dvs_count_kmers_host(dvs_ctx* ctx, const uint8_t* seqs, const uint64_t* offs
 
 int dvs_debug_log2(dvs_ctx* ctx, const double* x, double* y, uint64_t n) {
     if (n == 0) return DVS_OK;
-    DVS_CUDA_TRY(cudaSetDevice(ctx->device));
+    DVS_CUDA_TRY(dvs::enter(ctx));
     DevBuf<double> dx, dy;
     DVS_TRY(dx.alloc(n));
     DVS_TRY(dy.alloc(n));

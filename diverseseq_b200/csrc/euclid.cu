@@ -88,7 +88,7 @@ extern "C" int dvs_euclid_distances(dvs_ctx* ctx, const dvs_kfreqs* f, uint32_t 
     }
     const size_t nrows = row_end - row_begin, n = f->nrec;
     if (nrows == 0 || n == 0) return DVS_OK;
-    DVS_CUDA_TRY(cudaSetDevice(ctx->device));
+    DVS_CUDA_TRY(dvs::enter(ctx));
     DevBuf<double> d_out;
     DVS_TRY(d_out.alloc(nrows * n));
     dim3 grid((unsigned)((n + kEuT - 1) / kEuT), (unsigned)((nrows + kEuT - 1) / kEuT));

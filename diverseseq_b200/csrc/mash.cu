@@ -410,7 +410,7 @@ int dvs_mash_sketch(dvs_ctx* ctx, const dvs_seqset* s, int k, uint64_t sketch_si
         set_error("dvs_mash_sketch: unsupported k=%d / num_states=%d", k, num_states);
         return DVS_ERR_ARG;
     }
-    DVS_CUDA_TRY(cudaSetDevice(ctx->device));
+    DVS_CUDA_TRY(dvs::enter(ctx));
     cudaStream_t st = ctx->stream;
     const uint32_t nrec = s->nrec;
     std::vector<uint64_t> nk(nrec);
@@ -542,7 +542,7 @@ int dvs_sketches_from_host(dvs_ctx* ctx, const uint32_t* sketches, uint32_t stri
         set_error("dvs_sketches_from_host: bad argument");
         return DVS_ERR_ARG;
     }
-    DVS_CUDA_TRY(cudaSetDevice(ctx->device));
+    DVS_CUDA_TRY(dvs::enter(ctx));
     auto* sk = new dvs_sketches();
     sk->device = ctx->device;
     sk->nrec = nrec;
@@ -570,7 +570,7 @@ uint32_t dvs_sketches_nrec(const dvs_sketches* sk) { return sk->nrec; }
 uint32_t dvs_sketches_stride(const dvs_sketches* sk) { return sk->stride; }
 
 int dvs_sketches_download(dvs_ctx* ctx, const dvs_sketches* sk, uint32_t* sketches, uint32_t* lens) {
-    DVS_CUDA_TRY(cudaSetDevice(ctx->device));
+    DVS_CUDA_TRY(dvs::enter(ctx));
     if (sk->nrec == 0) return DVS_OK;
     if (sketches)
         DVS_CUDA_TRY(cudaMemcpyAsync(sketches, sk->data.p, (size_t)sk->nrec * sk->stride * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -593,7 +593,7 @@ int dvs_mash_distances(dvs_ctx* ctx, const dvs_sketches* sk, int k, uint64_t ske
     }
     const size_t nrows = row_end - row_begin, n = sk->nrec;
     if (nrows == 0 || n == 0) return DVS_OK;
-    DVS_CUDA_TRY(cudaSetDevice(ctx->device));
+    DVS_CUDA_TRY(dvs::enter(ctx));
     cudaStream_t st = ctx->stream;
     DevBuf<double> d_dist;
     DevBuf<uint32_t> d_inter, d_uni;

@@ -82,99 +82,102 @@ __global__ void k_sel_sum(const double* __restrict__ F, const double* __restrict
     }
 }
 
-// drop_lowest + push on summed_kfreqs (records.rs:103-108, :131-133); scalars follow in k_sel_total
-__global__ void k_sel_replace_vec(const double* __restrict__ F, uint64_t dim, const unsigned* __restrict__ members,
-                                  const SelScal* __restrict__ sc, unsigned cand_row, double* __restrict__ S) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= dim) return;
-    const unsigned low_row = members[sc->lowest];
-    double s = __dsub_rn(S[i], F[(size_t)low_row * dim + i]);
-    if (s <= kEps) s = 0.0;
-    S[i] = __dadd_rn(s, F[(size_t)cand_row * dim + i]);
-}
-
-// total_jsd = H(S/n) - E/n  (records.rs:136-138).  When replace_row >= 0 first finishes a
-// replace_lowest: E -= H_low; E += H_c; Vec::remove(lowest); push(c)  (records.rs:95-101,126-135).
-__global__ void __launch_bounds__(kEntThreads)
-k_sel_total(const double* __restrict__ H, uint64_t dim, const double* __restrict__ S, unsigned* __restrict__ members,
-            uint8_t* __restrict__ is_member, SelScal* sc, int replace_row) {
-    extern __shared__ double ent_smem[];
-    if (replace_row >= 0) {
-        if (threadIdx.x == 0) {
-            const unsigned n = sc->n, low = sc->lowest;
-            const unsigned low_row = members[low];
-            double e = __dsub_rn(sc->E, H[low_row]);
-            e = __dadd_rn(e, H[replace_row]);
-            sc->E = e;
-            for (unsigned j = low; j + 1 < n; ++j) members[j] = members[j + 1];
-            members[n - 1] = (unsigned)replace_row;
-            is_member[low_row] = 0;
-            is_member[replace_row] = 1;
-        }
-        __syncthreads();
+// replace_lowest (records.rs:94-135): drop_lowest + push on summed_kfreqs, elementwise; the LAST
+// CTA to finish then updates the scalars and the member Vec: E -= H_low; E += H_c;
+// Vec::remove(lowest); push(c).
+__global__ void k_sel_replace_vec(const double* __restrict__ F, const double* __restrict__ H, uint64_t dim,
+                                  unsigned* __restrict__ members, uint8_t* __restrict__ is_member, SelScal* sc,
+                                  unsigned cand_row, double* __restrict__ S) {
+    __shared__ unsigned s_last;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned low = sc->lowest;
+    const unsigned low_row = members[low];
+    if (i < dim) {
+        double s = __dsub_rn(S[i], F[(size_t)low_row * dim + i]);
+        if (s <= kEps) s = 0.0;
+        S[i] = __dadd_rn(s, F[(size_t)cand_row * dim + i]);
     }
-    const double nd = (double)sc->n;
-    EntropyResult h = block_entropy_exact(dim, [&](uint64_t i) { return __ddiv_rn(S[i], nd); }, ent_smem);
+    __syncthreads();  // every read of members[]/lowest by this CTA is done
     if (threadIdx.x == 0) {
-        sc->total_jsd = __dsub_rn(h.e, __ddiv_rn(sc->E, nd));
-        if (entropy_total_bad(h.t, dim) && sc->panic == 0) {
-            sc->panic = 1;
-            sc->panic_total = h.t;
+        __threadfence();
+        s_last = (atomicAdd(&sc->ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        const unsigned n = sc->n;
+        double e = __dsub_rn(sc->E, H[low_row]);
+        sc->E = __dadd_rn(e, H[cand_row]);
+        for (unsigned j = low; j + 1 < n; ++j) members[j] = members[j + 1];
+        members[n - 1] = cand_row;
+        if (is_member) {
+            is_member[low_row] = 0;
+            is_member[cand_row] = 1;
         }
         sc->ticket = 0;
     }
 }
 
-// get_lowest_record_index (records.rs:220-252): one CTA per member computes its delta_jsd; the
-// last CTA to finish does the strict-< argmin and the mean/std/cov statistics (:153-172).
+// total_jsd and get_lowest_record_index in one launch (records.rs:136-146, 220-252): CTA j < n
+// evaluates member j's leave-one-out entropy, CTA n evaluates H(S/n); none of these entropies
+// depends on another, only the final scalar arithmetic does, so the last CTA to finish forms
+// total_jsd = H(S/n) - E/n, delta_j = total_jsd - (H(m_j) - (E - H_j)/(n-1)), the strict-<
+// argmin and the mean/std/cov statistics (:153-172) in the reference's order.
 __global__ void __launch_bounds__(kEntThreads)
-k_sel_member_delta(const double* __restrict__ F, const double* __restrict__ H, uint64_t dim,
-                   const double* __restrict__ S, const unsigned* __restrict__ members, double* __restrict__ mdelta,
-                   SelScal* sc) {
+k_sel_update(const double* __restrict__ F, const double* __restrict__ H, uint64_t dim, const double* __restrict__ S,
+             const unsigned* __restrict__ members, double* __restrict__ mdelta, SelScal* sc) {
     extern __shared__ double ent_smem[];
     __shared__ unsigned s_last;
     const unsigned j = blockIdx.x, n = sc->n;
-    const unsigned row = members[j];
-    const double div = __dsub_rn((double)n, 1.0);
-    const double* f = F + (size_t)row * dim;
-    EntropyResult h = block_entropy_exact(
-        dim,
-        [&](uint64_t i) {
-            double m = __ddiv_rn(__dsub_rn(S[i], f[i]), div);
-            return (m <= kEps) ? 0.0 : m;  // updated_mean_freqs clamp, records.rs:281-284
-        },
-        ent_smem);
-    if (threadIdx.x == 0) {
-        const double mean_entropy = __ddiv_rn(__dsub_rn(sc->E, H[row]), div);
-        const double jsd = __dsub_rn(h.e, mean_entropy);
-        mdelta[j] = __dsub_rn(sc->total_jsd, jsd);
-        if (entropy_total_bad(h.t, dim)) {
-            // the reference panics at the FIRST member (in order) whose check fails; any is fatal
-            if (atomicCAS(&sc->panic, 0u, 1u) == 0u) sc->panic_total = h.t;
+    const double nd = (double)n;
+    if (j == n) {
+        EntropyResult h = block_entropy_exact(dim, [&](uint64_t i) { return __ddiv_rn(S[i], nd); }, ent_smem);
+        if (threadIdx.x == 0) {
+            sc->total_jsd = __dsub_rn(h.e, __ddiv_rn(sc->E, nd));
+            if (entropy_total_bad(h.t, dim) && atomicCAS(&sc->panic, 0u, 1u) == 0u) sc->panic_total = h.t;
         }
+    } else {
+        const unsigned row = members[j];
+        const double div = __dsub_rn(nd, 1.0);
+        const double* f = F + (size_t)row * dim;
+        EntropyResult h = block_entropy_exact(
+            dim,
+            [&](uint64_t i) {
+                double m = __ddiv_rn(__dsub_rn(S[i], f[i]), div);
+                return (m <= kEps) ? 0.0 : m;  // updated_mean_freqs clamp, records.rs:281-284
+            },
+            ent_smem);
+        if (threadIdx.x == 0) {
+            const double mean_entropy = __ddiv_rn(__dsub_rn(sc->E, H[row]), div);
+            mdelta[j] = __dsub_rn(h.e, mean_entropy);  // jsd without record j; delta formed below
+            // the reference panics at the first member whose sum check fails; any failure is fatal
+            if (entropy_total_bad(h.t, dim) && atomicCAS(&sc->panic, 0u, 1u) == 0u) sc->panic_total = h.t;
+        }
+    }
+    if (threadIdx.x == 0) {
         __threadfence();
-        s_last = (atomicAdd(&sc->ticket, 1u) == n - 1) ? 1u : 0u;
+        s_last = (atomicAdd(&sc->ticket, 1u) == n) ? 1u : 0u;
     }
     __syncthreads();
     if (s_last && threadIdx.x == 0) {
         __threadfence();
-        const volatile double* md = mdelta;
+        volatile double* md = mdelta;
+        const double total_jsd = *(volatile double*)&sc->total_jsd;
         double mn = 1e6;
         unsigned low = 0;
         double sum = 0.0;
         for (unsigned t = 0; t < n; ++t) {
-            double d = md[t];
+            const double d = __dsub_rn(total_jsd, md[t]);
+            md[t] = d;
             if (d < mn) {
                 mn = d;
                 low = t;
             }
             sum = __dadd_rn(sum, d);
         }
-        const double nd = (double)n;
         const double mean = __ddiv_rn(sum, nd);
         double ss = 0.0;
         for (unsigned t = 0; t < n; ++t) {
-            double d = __dsub_rn(md[t], mean);
+            const double d = __dsub_rn(md[t], mean);
             ss = __dadd_rn(ss, __dmul_rn(d, d));
         }
         const double sd = __dsqrt_rn(__ddiv_rn(ss, __dsub_rn(nd, 1.0)));
@@ -253,31 +256,24 @@ struct Selector {
         return DVS_OK;
     }
 
-    // SummedRecords::new over `members` (+ optional pushed row): sum, total_jsd, member deltas
-    int build(SelState& s, const unsigned* d_members, unsigned n, int extra_row, uint8_t* is_member) {
+    // SummedRecords::new over `members` (+ optional pushed row): sums, then total_jsd + member deltas
+    int build(SelState& s, const unsigned* d_members, unsigned n, int extra_row) {
         k_sel_sum<<<vec_grid(), 256, 0, st>>>(f->freqs.p, f->entropy.p, dim, d_members, n, extra_row, s.S.p,
                                               s.members.p, s.sc.p);
         DVS_LAUNCHED(ctx);
-        return refresh(s, -1, is_member);
+        return update(s, n + (extra_row >= 0 ? 1u : 0u));
     }
-    // total_jsd + get_lowest_record_index after the vector update
-    int refresh(SelState& s, int replace_row, uint8_t* is_member) {
-        k_sel_total<<<1, kEntThreads, kEntSmemBytes, st>>>(f->entropy.p, dim, s.S.p, s.members.p, is_member,
-                                                            s.sc.p, replace_row);
-        DVS_LAUNCHED(ctx);
-        return DVS_OK;
-    }
-    int member_delta(SelState& s, unsigned n) {
-        k_sel_member_delta<<<n, kEntThreads, kEntSmemBytes, st>>>(f->freqs.p, f->entropy.p, dim, s.S.p,
-                                                                   s.members.p, s.mdelta.p, s.sc.p);
+    int update(SelState& s, unsigned n) {
+        k_sel_update<<<n + 1, kEntThreads, kEntSmemBytes, st>>>(f->freqs.p, f->entropy.p, dim, s.S.p, s.members.p,
+                                                                 s.mdelta.p, s.sc.p);
         DVS_LAUNCHED(ctx);
         return DVS_OK;
     }
     int replace(SelState& s, unsigned n, unsigned cand_row, uint8_t* is_member) {
-        k_sel_replace_vec<<<vec_grid(), 256, 0, st>>>(f->freqs.p, dim, s.members.p, s.sc.p, cand_row, s.S.p);
+        k_sel_replace_vec<<<vec_grid(), 256, 0, st>>>(f->freqs.p, f->entropy.p, dim, s.members.p, is_member,
+                                                      s.sc.p, cand_row, s.S.p);
         DVS_LAUNCHED(ctx);
-        DVS_TRY(refresh(s, (int)cand_row, is_member));
-        return member_delta(s, n);
+        return update(s, n);
     }
     int scan(SelState& s, const dvs_kfreqs* q, const uint8_t* is_member, const unsigned* d_order, unsigned pos0,
              unsigned count, double* delta_out) {
@@ -325,7 +321,7 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
             set_error("dvs_select: order[%u]=%u out of range (nrec=%u)", i, order[i], f->nrec);
             return DVS_ERR_ARG;
         }
-    DVS_CUDA_TRY(cudaSetDevice(ctx->device));
+    DVS_CUDA_TRY(dvs::enter(ctx));
     cudaStream_t st = ctx->stream;
     const uint64_t dim = f->dim;
 
@@ -381,8 +377,7 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
     SelState* cur = &A;
     SelState* alt = &B;
     unsigned n = (unsigned)init.size();
-    DVS_TRY(sel.build(*cur, d_init.p, n, -1, is_member.p));
-    DVS_TRY(sel.member_delta(*cur, n));
+    DVS_TRY(sel.build(*cur, d_init.p, n, -1));
 
     const unsigned window_max = std::max(64u, (unsigned)ctx->sm_count * 12u);
     unsigned cursor = min_size;
@@ -414,8 +409,7 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
             continue;
         }
         // records.rs:434-451: nw = clone(); nw.push(rec); keep whichever has the larger statistic
-        DVS_TRY(sel.build(*alt, cur->members.p, n, (int)row, is_member.p));
-        DVS_TRY(sel.member_delta(*alt, n + 1));
+        DVS_TRY(sel.build(*alt, cur->members.p, n, (int)row));
         DVS_TRY(sel.read(*alt));
         const SelScal hb = *sel.h_sc;
         if (hb.panic) return panic_error(hb);
@@ -468,7 +462,7 @@ int dvs_summed_create(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* members
             set_error("dvs_summed_create: member %u out of range", members[i]);
             return DVS_ERR_ARG;
         }
-    DVS_CUDA_TRY(cudaSetDevice(ctx->device));
+    DVS_CUDA_TRY(dvs::enter(ctx));
     auto* s = new dvs_summed();
     s->device = ctx->device;
     s->f = f;
@@ -484,8 +478,7 @@ int dvs_summed_create(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* members
         }
     }
     Selector sel{ctx, f, f->dim, ctx->stream, (SelScal*)ctx->pinned};
-    if (rc == DVS_OK) rc = sel.build(s->st, d_m.p, n, -1, nullptr);
-    if (rc == DVS_OK) rc = sel.member_delta(s->st, n);
+    if (rc == DVS_OK) rc = sel.build(s->st, d_m.p, n, -1);
     if (rc == DVS_OK) rc = sel.read(s->st);
     if (rc == DVS_OK && sel.h_sc->panic) rc = panic_error(*sel.h_sc);
     if (rc != DVS_OK) {
@@ -506,7 +499,7 @@ int dvs_summed_delta_jsd(dvs_ctx* ctx, dvs_summed* s, const dvs_kfreqs* q, uint3
         *out = 0.0;
         return DVS_OK;
     }
-    DVS_CUDA_TRY(cudaSetDevice(ctx->device));
+    DVS_CUDA_TRY(dvs::enter(ctx));
     Selector sel{ctx, s->f, s->f->dim, ctx->stream, (SelScal*)ctx->pinned};
     DevBuf<double> d_out;
     DVS_TRY(d_out.alloc(1));
@@ -524,7 +517,7 @@ int dvs_summed_delta_jsd(dvs_ctx* ctx, dvs_summed* s, const dvs_kfreqs* q, uint3
 
 int dvs_summed_result(dvs_ctx* ctx, dvs_summed* s, uint32_t* sel_idx, double* sel_delta, double* stats5,
                       uint32_t* size_out, uint32_t* lowest_out) {
-    DVS_CUDA_TRY(cudaSetDevice(ctx->device));
+    DVS_CUDA_TRY(dvs::enter(ctx));
     Selector sel{ctx, s->f, s->f->dim, ctx->stream, (SelScal*)ctx->pinned};
     DVS_TRY(sel.read(s->st));
     const SelScal h = *sel.h_sc;

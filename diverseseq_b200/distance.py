@@ -36,8 +36,7 @@ class NamedDistances:
 
 
 def _seqset(ctx, seq_arrays):
-    return _lib.SeqSet.from_seqs(ctx, [s._storage._array(s.seqid) if hasattr(s, "_storage") else s.get_seq()
-                                       for s in seq_arrays])
+    return _lib.SeqSet.from_seqs(ctx, [s.get_seq() for s in seq_arrays])  # LazySeq.get_seq, src/record.rs:263
 
 
 def mash_sketches(seq_arrays, k: int, sketch_size: int, num_states: int, *, mash_canonical: bool = False,
