@@ -52,6 +52,7 @@ SIGNATURES = {
     "dvs_count_kmers_host": (_i32, [_vp, _vp, _vp, _u32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "dvs_select": (_i32, [_vp, _vp, _vp, _u32, _i32, _u32, _u32, _vp, _vp, _vp, C.POINTER(_u32)]),
     "dvs_select_last_accepts": (_u32, [_vp]),
+    "dvs_select_last_exact_evals": (_u32, [_vp]),
     "dvs_summed_create": (_i32, [_vp, _vp, _vp, _u32, C.POINTER(_vp)]),
     "dvs_summed_delta_jsd": (_i32, [_vp, _vp, _vp, _u32, _i32, C.POINTER(_f64)]),
     "dvs_summed_result": (_i32, [_vp, _vp, _vp, _vp, _vp, C.POINTER(_u32), C.POINTER(_u32)]),

@@ -100,6 +100,7 @@ struct dvs_ctx {
     cudaStream_t stream = nullptr;
     uint64_t launches = 0;
     uint32_t last_accepts = 0;
+    uint32_t last_exact_evals = 0;  // exact re-evaluations forced by the fast path's error bound
     // pinned scratch for small device->host readbacks
     void* pinned = nullptr;
     size_t pinned_bytes = 0;

@@ -15,6 +15,8 @@
 // into `nparts` shared-memory passes (k=8) or, for larger tables, updated with global RED.ADD.
 // Work is (record, part, 16B-aligned byte range) items pulled from a global queue by persistent
 // CTAs, so long records are split across CTAs and merged with one global atomic per non-empty bin.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -30,6 +32,7 @@ struct CountWork {
 };
 
 constexpr int kCountThreads = 512;
+constexpr int kPrefetch = 4;  // 512-byte steps in flight per warp
 
 __device__ __forceinline__ uint32_t pack4(uint32_t w) {
     // bytes b0..b3 (memory order, each 0..3) -> b0<<6 | b1<<4 | b2<<2 | b3
@@ -117,7 +120,22 @@ k_count_generic(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ o
 // keeps lane 31's block of the previous step, so every sequence byte is loaded exactly once.
 constexpr int MODE_SMEM = 0, MODE_SMEM_PARTS = 1, MODE_GLOBAL = 2, MODE_SUPER = 3;
 
-template <int MODE>
+// 16 packed bases from 16 bytes: four multiplies put each word's 8 bits in its top byte, three
+// PRMTs gather the top bytes (first base most significant)
+__device__ __forceinline__ uint32_t pack16p(uint4 v) {
+    const uint32_t p0 = v.x * 0x40100401u, p1 = v.y * 0x40100401u, p2 = v.z * 0x40100401u, p3 = v.w * 0x40100401u;
+    const uint32_t hi = __byte_perm(p1, p0, 0x7300);  // byte3 = p0.b3, byte2 = p1.b3
+    const uint32_t lo = __byte_perm(p3, p2, 0x0073);  // byte1 = p2.b3, byte0 = p3.b3
+    return __byte_perm(lo, hi, 0x7610);
+}
+
+// SCR: bank scrambling.  The bank of a bin is its low 5 index bits = the last 2.5 bases, whose
+// distribution is as skewed as the genome's composition, so ATOMS bank conflicts grow with the skew
+// (ncu: 4.9 wavefronts per instruction on the benchmark set vs 2.6 for uniform bins).  Storing bin
+// `idx` at slot `idx ^ (idx >> 5)` (a bijection) folds the next 2.5 bases into the bank bits.
+__device__ __forceinline__ uint32_t scr_word(uint32_t idx) { return idx ^ (idx >> 5); }
+
+template <int MODE, bool SCR>
 __global__ void __launch_bounds__(kCountThreads)
 k_count(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offsets, const CountWork* __restrict__ work,
         uint32_t nwork, uint32_t* __restrict__ next_item, int k, uint64_t dim, uint32_t part_bins,
@@ -126,11 +144,14 @@ k_count(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offsets, 
     __shared__ uint32_t s_item;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int kWarps = kCountThreads / 32;
+    constexpr uint32_t kFull = 0xffffffffu;
     const int kk = (MODE == MODE_SUPER) ? k + 1 : k;                       // bases per histogrammed word
     const uint32_t mask = (kk >= 16) ? 0xFFFFFFFFu : ((1u << (2 * kk)) - 1u);
+    const uint32_t mask4 = mask << 2;                                       // same, as a byte offset
     const uint32_t mask_k = (k >= 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
     const uint32_t hist_words = (MODE == MODE_SUPER) ? (uint32_t)(dim * 4 + dim) : part_bins;
     uint32_t* side = hist + dim * 4;  // MODE_SUPER only: single k-mer histogram after the (k+1)-mer table
+    char* const hist_b = reinterpret_cast<char*>(hist);
 
     for (;;) {
         if (tid == 0) s_item = atomicAdd(next_item, 1u);
@@ -145,93 +166,115 @@ k_count(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offsets, 
             for (uint32_t i = tid; i < hist_words; i += kCountThreads) hist[i] = 0;
             __syncthreads();
         }
-        auto bump = [&](uint32_t idx) {  // one k-mer (MODE 0/1/2) or one (k+1)-mer (MODE 3)
+        // idx4 = 4 * bin: one k-mer (MODE 0/1/2) or one (k+1)-mer (MODE 3)
+        auto bump4 = [&](uint32_t idx4) {
             if (MODE == MODE_SMEM || MODE == MODE_SUPER) {
-                atomicAdd(&hist[idx], 1u);
+                if (SCR) idx4 ^= (idx4 >> 5) & ~3u;
+                atomicAdd(reinterpret_cast<uint32_t*>(hist_b + idx4), 1u);
             } else if (MODE == MODE_SMEM_PARTS) {
-                uint32_t local = idx - part_base;
-                if (local < part_bins) atomicAdd(&hist[local], 1u);
+                uint32_t local = (idx4 >> 2) - part_base;
+                if (local < part_bins) atomicAdd(&hist[SCR ? scr_word(local) : local], 1u);
             } else {
-                atomicAdd(&grow[idx], 1u);
+                atomicAdd(&grow[idx4 >> 2], 1u);
             }
-        };
-        auto bump_single = [&](uint32_t idx_k) {  // MODE 3 fallback: one k-mer into the side table
-            atomicAdd(&side[idx_k], 1u);
         };
 
-        // this warp's contiguous span of the item, in 512-byte steps
-        const uint64_t bytes = w.end - w.begin;
-        const uint64_t span = ((bytes + kWarps - 1) / kWarps + 511) & ~511ULL;
-        const uint64_t s0 = w.begin + (uint64_t)warp * span;
-        const uint64_t s1 = min(w.end, s0 + span);
+        // item-relative 32-bit coordinates (items are <= 1 MB): bytes [rs, re) belong to the record
+        const uint32_t item_len = (uint32_t)(w.end - w.begin);
+        const uint32_t rs = start > w.begin ? (uint32_t)min(start - w.begin, (uint64_t)item_len) : 0u;
+        const uint32_t re = end < w.end ? (end > w.begin ? (uint32_t)(end - w.begin) : 0u) : item_len;
+        // this warp's contiguous span of the item, walked in 512-byte steps
+        const uint32_t span = ((item_len + kWarps - 1) / kWarps + 511u) & ~511u;
+        const uint32_t r0 = min(item_len, (uint32_t)warp * span);
+        const uint32_t r1 = min(item_len, r0 + span);
+        const uint8_t* base = seqs + w.begin;
         uint32_t carry_pc = 0;
         bool carry_ok = false;
-        uint4 cur = make_uint4(~0u, ~0u, ~0u, ~0u);
-        if (s0 < s1) {
-            if (s0 + 16 * lane < s1) cur = ldg16(seqs + s0 + 16 * lane);
-            // halo of lane 0 for the first step: the 16 bytes before the span
-            const uint4 h = ldg16(seqs + s0 - 16);  // front pad keeps this inside the allocation
-            carry_ok = (((h.x | h.y | h.z | h.w) & 0xFCFCFCFCu) == 0) && (s0 >= start + 16) && (s0 <= end);
-            carry_pc = pack16(h);
+        // register ring of kPrefetch steps in flight per lane: with 32 warps/SM one step ahead leaves
+        // only ~16 KB outstanding per SM, well short of what 6.5 TB/s x ~0.8 us latency needs (~35 KB)
+        uint4 ring[kPrefetch];
+#pragma unroll
+        for (int u = 0; u < kPrefetch; ++u) {
+            const uint32_t a = r0 + 512u * u + 16 * lane;
+            ring[u] = (a < r1) ? ldg16(base + a) : make_uint4(~0u, ~0u, ~0u, ~0u);
         }
-        for (uint64_t pos = s0; pos < s1; pos += 512) {
-            const uint64_t a = pos + 16 * lane;
-            // prefetch the next step while this one is histogrammed
-            uint4 nxt = make_uint4(~0u, ~0u, ~0u, ~0u);
-            if (a + 512 < s1) nxt = ldg16(seqs + a + 512);
-            const bool ok = (((cur.x | cur.y | cur.z | cur.w) & 0xFCFCFCFCu) == 0) && (a >= start) && (a + 16 <= end) &&
-                            (a < s1);
-            const uint32_t pc = pack16(cur);
-            uint32_t pp = __shfl_up_sync(0xffffffffu, pc, 1);
-            bool prev_ok = __shfl_up_sync(0xffffffffu, (int)ok, 1) != 0;
-            if (lane == 0) {
-                pp = carry_pc;
-                prev_ok = carry_ok;
-            }
-            carry_pc = __shfl_sync(0xffffffffu, pc, 31);
-            carry_ok = __shfl_sync(0xffffffffu, (int)ok, 31) != 0;
-            if (a < s1) {
+        if (r0 < r1) {
+            // halo of lane 0 for the first step: the 16 bytes before the span
+            const uint4 h = ldg16(base + r0 - 16);  // front pad keeps this inside the allocation
+            const uint64_t a0 = w.begin + r0;
+            carry_ok = (((h.x | h.y | h.z | h.w) & 0xFCFCFCFCu) == 0) && (a0 >= start + 16) && (a0 <= end);
+            carry_pc = pack16p(h);
+        }
+        for (uint32_t rbase = r0; rbase < r1; rbase += 512u * kPrefetch) {
+#pragma unroll
+          for (int u = 0; u < kPrefetch; ++u) {
+            const uint32_t r = rbase + 512u * u;
+            if (r >= r1) break;  // warp-uniform
+            const uint32_t a = r + 16 * lane;
+            const uint4 cur = ring[u];
+            // refill this slot with the step kPrefetch ahead
+            ring[u] = (a + 512u * kPrefetch < r1) ? ldg16(base + a + 512u * kPrefetch) : make_uint4(~0u, ~0u, ~0u, ~0u);
+            const bool ok = (((cur.x | cur.y | cur.z | cur.w) & 0xFCFCFCFCu) == 0) && (a >= rs) && (a + 16 <= re) && (a < r1);
+            const uint32_t pc = pack16p(cur);
+            uint32_t pp = __shfl_up_sync(kFull, pc, 1);
+            if (lane == 0) pp = carry_pc;
+            const uint32_t okmask = __ballot_sync(kFull, ok);
+            const bool all_fast = (okmask == kFull) && carry_ok;  // warp-uniform: the common case
+            if (all_fast) {
+                if (MODE == MODE_SUPER) {
+#pragma unroll
+                    for (int j = 1; j < 15; j += 2) bump4(__funnelshift_r(pc, pp, 2 * (15 - j) - 2) & mask4);
+                    bump4((pc << 2) & mask4);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 15; ++j) bump4(__funnelshift_r(pc, pp, 2 * (15 - j) - 2) & mask4);
+                    bump4((pc << 2) & mask4);
+                }
+            } else if (a < r1) {
+                const bool prev_ok = lane == 0 ? carry_ok : ((okmask >> (lane - 1)) & 1u) != 0;
                 if (ok && prev_ok) {
                     if (MODE == MODE_SUPER) {
 #pragma unroll
-                        for (int j = 1; j < 16; j += 2) bump(__funnelshift_r(pc, pp, 2 * (15 - j)) & mask);
+                        for (int j = 1; j < 16; j += 2) bump4((__funnelshift_r(pc, pp, 2 * (15 - j)) & mask) << 2);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) bump(__funnelshift_r(pc, pp, 2 * (15 - j)) & mask);
+                        for (int j = 0; j < 16; ++j) bump4((__funnelshift_r(pc, pp, 2 * (15 - j)) & mask) << 2);
                     }
                 } else {
                     // per-byte path: invalid bytes or record edges inside [a-16, a+16)
-                    const uint4 prev = ldg16(seqs + a - 16);
+                    const uint4 prev = ldg16(base + a - 16);
                     const uint32_t wv[8] = {prev.x, prev.y, prev.z, prev.w, cur.x, cur.y, cur.z, cur.w};
                     uint32_t run = 0, idx = 0, run_even = 0, idx_even = 0;
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        const uint64_t p = a - 16 + i;
-                        uint32_t b = (wv[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-                        if (p < start || p >= end) b = 0xFFu;
-                        if (b >= 4u) {
+                        const uint64_t p = w.begin + a + i - 16;  // absolute position (halo bytes may precede the item)
+                        uint32_t bb = (wv[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+                        if (p < start || p >= end) bb = 0xFFu;
+                        if (bb >= 4u) {
                             run = 0;
                             idx = 0;
                         } else {
-                            idx = ((idx << 2) | b) & mask;
+                            idx = ((idx << 2) | bb) & mask;
                             ++run;
                         }
                         if (i < 16) continue;
                         if (MODE != MODE_SUPER) {
-                            if (run >= (uint32_t)k) bump(idx);
+                            if (run >= (uint32_t)k) bump4(idx << 2);
                         } else if ((i & 1) == 0) {  // even position: decided together with its odd partner
                             run_even = run;
                             idx_even = idx;
                         } else if (run >= (uint32_t)(k + 1)) {
-                            bump(idx);  // both k-mers valid: one (k+1)-mer
-                        } else {
-                            if (run_even >= (uint32_t)k) bump_single(idx_even & mask_k);
-                            if (run >= (uint32_t)k) bump_single(idx & mask_k);
+                            bump4(idx << 2);  // both k-mers valid: one (k+1)-mer
+                        } else {              // fall back to single k-mers in the side table
+                            if (run_even >= (uint32_t)k) atomicAdd(&side[idx_even & mask_k], 1u);
+                            if (run >= (uint32_t)k) atomicAdd(&side[idx & mask_k], 1u);
                         }
                     }
                 }
             }
-            cur = nxt;
+            carry_pc = __shfl_sync(kFull, pc, 31);
+            carry_ok = (okmask >> 31) != 0;
+          }
         }
         if (MODE != MODE_GLOBAL) {
             __syncthreads();
@@ -239,14 +282,20 @@ k_count(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offsets, 
                 for (uint32_t x = tid; x < (uint32_t)dim; x += kCountThreads) {
                     uint32_t c = side[x];
 #pragma unroll
-                    for (uint32_t b = 0; b < 4; ++b) c += hist[(x << 2) | b];          // x is the prefix k-mer
+                    for (uint32_t b = 0; b < 4; ++b) {  // x is the prefix k-mer
+                        const uint32_t y = (x << 2) | b;
+                        c += hist[SCR ? scr_word(y) : y];
+                    }
 #pragma unroll
-                    for (uint32_t a4 = 0; a4 < 4; ++a4) c += hist[(a4 << (2 * k)) | x];  // x is the suffix k-mer
+                    for (uint32_t a4 = 0; a4 < 4; ++a4) {  // x is the suffix k-mer
+                        const uint32_t y = (a4 << (2 * k)) | x;
+                        c += hist[SCR ? scr_word(y) : y];
+                    }
                     if (c) atomicAdd(&grow[x], c);
                 }
             } else {
                 for (uint32_t i = tid; i < part_bins; i += kCountThreads) {
-                    uint32_t c = hist[i];
+                    uint32_t c = hist[SCR ? scr_word(i) : i];
                     if (c && (uint64_t)part_base + i < dim) atomicAdd(&grow[part_base + i], c);
                 }
             }
@@ -427,6 +476,10 @@ int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dv
         }
     }
     const bool smem = (mode != MODE_GLOBAL);
+    // bank scrambling needs a power-of-two table (always true for num_states == 4); DVS_COUNT_SCRAMBLE=0
+    // turns it off for A/B measurements
+    const char* scr_env = getenv("DVS_COUNT_SCRAMBLE");
+    const bool scramble = !(scr_env && scr_env[0] == '0');
 
     // ---- work list: (record, part, aligned range) ----
     int ctas_per_sm = 4;
@@ -482,13 +535,13 @@ int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dv
         if (!ns4)
             e = smem ? launch_generic(k_count_generic<true>) : launch_generic(k_count_generic<false>);
         else if (mode == MODE_SUPER)
-            e = launch4(k_count<MODE_SUPER>);
+            e = scramble ? launch4(k_count<MODE_SUPER, true>) : launch4(k_count<MODE_SUPER, false>);
         else if (mode == MODE_SMEM)
-            e = launch4(k_count<MODE_SMEM>);
+            e = scramble ? launch4(k_count<MODE_SMEM, true>) : launch4(k_count<MODE_SMEM, false>);
         else if (mode == MODE_SMEM_PARTS)
-            e = launch4(k_count<MODE_SMEM_PARTS>);
+            e = scramble ? launch4(k_count<MODE_SMEM_PARTS, true>) : launch4(k_count<MODE_SMEM_PARTS, false>);
         else
-            e = launch4(k_count<MODE_GLOBAL>);
+            e = launch4(k_count<MODE_GLOBAL, false>);
         pt.stop();
         if (e != cudaSuccess) {
             set_error("k_count launch failed: %s", cudaGetErrorString(e));

@@ -14,6 +14,7 @@
 // reduction (atomicMin) finds it; the state update then runs as three small kernels.
 #include <limits.h>
 #include <stddef.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -35,19 +36,37 @@ struct SelScal {
     unsigned first_panic;    // scan result: first position whose evaluation panics
     unsigned panic;          // 0 none; 1 = entropy sum check failed while updating the state
     unsigned ticket;         // last-block-done counter
+    // ---- bounded-error fast path (see "fast path" below) ----
+    double total_bound;      // |total_jsd - exact total_jsd| <= total_bound (0 when exact)
+    unsigned first_unsure;   // scan result: first position the fast scan could not decide
+    unsigned state_unsure;   // fast update could not certify lowest_index / the sum checks
+    unsigned exact;          // 1 when total_jsd / mdelta / lowest come from the exact kernel
+    unsigned pad_;
 };
 
 struct SelState {
-    DevBuf<double> S;          // summed_kfreqs [dim]
-    DevBuf<unsigned> members;  // row indices in Vec order [cap]
+    // S and the member list are double buffered: the fused fast replace+update kernel reads one copy
+    // and writes the other, so it needs no grid-wide barrier between "update S" and "use S"
+    DevBuf<double> Sbuf[2];          // summed_kfreqs [dim]
+    DevBuf<unsigned> membuf[2];      // row indices in Vec order [cap]
+    int which = 0;
     DevBuf<double> mdelta;     // delta_jsd per member [cap]
+    DevBuf<double> mbound;     // fast path: error bound of each member's value [cap]
     DevBuf<SelScal> sc;
     unsigned cap = 0;
+    double* S() { return Sbuf[which].p; }
+    unsigned* members() { return membuf[which].p; }
+    double* S_other() { return Sbuf[which ^ 1].p; }
+    unsigned* members_other() { return membuf[which ^ 1].p; }
+    void flip() { which ^= 1; }
     int alloc(uint64_t dim, unsigned capacity) {
         cap = capacity;
-        DVS_TRY(S.alloc(dim));
-        DVS_TRY(members.alloc(capacity));
+        for (int b = 0; b < 2; ++b) {
+            DVS_TRY(Sbuf[b].alloc(dim));
+            DVS_TRY(membuf[b].alloc(capacity));
+        }
         DVS_TRY(mdelta.alloc(capacity));
+        DVS_TRY(mbound.alloc(capacity));
         DVS_TRY(sc.alloc(1));
         return DVS_OK;
     }
@@ -79,6 +98,10 @@ __global__ void k_sel_sum(const double* __restrict__ F, const double* __restrict
         sc->ticket = 0;
         sc->first_true = kNone;
         sc->first_panic = kNone;
+        sc->first_unsure = kNone;
+        sc->state_unsure = 0;
+        sc->total_bound = 0.0;
+        sc->exact = 0;
     }
 }
 
@@ -188,6 +211,10 @@ k_sel_update(const double* __restrict__ F, const double* __restrict__ H, uint64_
         sc->ticket = 0;
         sc->first_true = kNone;
         sc->first_panic = kNone;
+        sc->first_unsure = kNone;
+        sc->total_bound = 0.0;
+        sc->state_unsure = 0;
+        sc->exact = 1;
     }
 }
 
@@ -219,6 +246,285 @@ k_sel_scan(const double* __restrict__ F, const double* __restrict__ H, uint64_t 
     }
 }
 
+// ------------------------------------------------------------------------------- fast path ----
+// The exact kernels above cost one dependent FP64 add per element (~30 us per 4^6-element
+// entropy).  Most decisions are nowhere near a tie, so they are first attempted with a PARALLEL
+// evaluation whose distance from the reference's value is rigorously bounded:
+//   * the frequencies m_i are formed with the same IEEE operations, so they are identical;
+//   * each term -m*log2(m) differs from the reference's by <= 3 ulp (two <1-ulp log2s, one product);
+//   * a pairwise (tree) sum of D terms is within (ceil(log2 D)+3) u A of the real sum A' of the
+//     computed terms, the reference's sequential sum within (D-1) u A        (u = 2^-53, A = sum|term|);
+// so |e_fast - e_ref| <= (D + 64) * 1.2e-16 * A =: bound.  A decision is taken from the fast value
+// only when it holds for every value in [fast - bound, fast + bound]; otherwise the position is
+// reported as "unsure" and the exact kernel decides.  The reference's sum-to-one check
+// |t_ref - 1| <= D*EPS is certified from the tree sum t (|t - T| <= 16u, |t_ref - T| <= (D-1)u):
+// it cannot fail when |t - 1| <= 0.45*D*EPS; otherwise: unsure.  Selected sets, their order and all
+// reported numbers are therefore still the exact path's (the final state is always re-evaluated
+// exactly); only the work is reduced.
+constexpr int kFastThreads = 512;
+
+struct FastSum {
+    double e, t, a;  // entropy, total, sum |term|
+    int bad;         // a negative / NaN frequency was seen (reference yields NaN): cannot be bounded
+};
+
+template <class Elem>
+__device__ FastSum block_entropy_fast(uint64_t dim, Elem elem) {
+    __shared__ double s_part[3][kFastThreads / 32];
+    __shared__ int s_bad[kFastThreads / 32];
+    double e0 = 0.0, e1 = 0.0, t0 = 0.0, t1 = 0.0, a0 = 0.0, a1 = 0.0;
+    int bad = 0;
+    uint64_t i = threadIdx.x;
+    for (; i + kFastThreads < dim; i += 2 * kFastThreads) {
+        const double x0 = elem(i), x1 = elem(i + kFastThreads);
+        if (!(x0 == 0.0)) {
+            bad |= !(x0 > 0.0);
+            const double tm = __dmul_rn(-x0, log2(x0));
+            e0 += tm; a0 += fabs(tm); t0 += x0;
+        }
+        if (!(x1 == 0.0)) {
+            bad |= !(x1 > 0.0);
+            const double tm = __dmul_rn(-x1, log2(x1));
+            e1 += tm; a1 += fabs(tm); t1 += x1;
+        }
+    }
+    if (i < dim) {
+        const double x0 = elem(i);
+        if (!(x0 == 0.0)) {
+            bad |= !(x0 > 0.0);
+            const double tm = __dmul_rn(-x0, log2(x0));
+            e0 += tm; a0 += fabs(tm); t0 += x0;
+        }
+    }
+    double e = e0 + e1, t = t0 + t1, a = a0 + a1;
+    for (int o = 16; o; o >>= 1) {
+        e += __shfl_xor_sync(0xffffffffu, e, o);
+        t += __shfl_xor_sync(0xffffffffu, t, o);
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        s_part[0][w] = e; s_part[1][w] = t; s_part[2][w] = a; s_bad[w] = bad;
+    }
+    __syncthreads();
+    FastSum r{0.0, 0.0, 0.0, 0};
+    for (int q = 0; q < kFastThreads / 32; ++q) {
+        r.e += s_part[0][q]; r.t += s_part[1][q]; r.a += s_part[2][q]; r.bad |= s_bad[q];
+    }
+    __syncthreads();
+    return r;
+}
+
+// Each thread first sums dim/kFastThreads elements sequentially, then the partials are tree-summed:
+// |sum_fast - real sum| <= (dim/kFastThreads + 12) u A, the reference's sequential sum is within
+// (dim - 1) u A, and the per-term differences add 6 u A; 1.2e-16 > u = 2^-53 absorbs second-order terms.
+__device__ __forceinline__ double fast_slack(uint64_t dim) { return (double)(dim / kFastThreads) + 12.0; }
+__device__ __forceinline__ double fast_bound(uint64_t dim, double a, double extra) {
+    return ((double)dim + fast_slack(dim) + 16.0) * 1.2e-16 * (a + fabs(extra) + 1.0);
+}
+// reference check: |t_ref - 1| <= dim*EPS = 2 dim u.  |t_ref - T| <= (dim-1) u, |t - T| <= slack u (T ~ 1),
+// so the check cannot fail when |t - 1| <= (dim + 1 - slack) u; for tiny dim this is never certified
+// and the (then trivially cheap) exact kernel decides.
+__device__ __forceinline__ bool fast_total_ok(uint64_t dim, double t) {
+    const double lim = ((double)dim + 1.0 - fast_slack(dim) - 2.0) * 1.1102230246251565e-16;
+    return lim > 0.0 && fabs(t - 1.0) <= lim;
+}
+
+// fast increases_jsd for a window; one CTA per position.  first_true / first_unsure by atomicMin.
+__global__ void __launch_bounds__(kFastThreads)
+k_sel_scan_fast(const double* __restrict__ F, const double* __restrict__ H, uint64_t dim, const double* __restrict__ S,
+                const unsigned* __restrict__ members, SelScal* sc, const uint8_t* __restrict__ valid,
+                const uint8_t* __restrict__ is_member, const unsigned* __restrict__ order, unsigned pos0) {
+    const unsigned pos = pos0 + blockIdx.x;
+    const unsigned row = order[pos];
+    if (!valid[row] || is_member[row]) return;
+    const unsigned n = sc->n;
+    const double nd = (double)n;
+    const unsigned low_row = members[sc->lowest];
+    const double* fl = F + (size_t)low_row * dim;
+    const double* fc = F + (size_t)row * dim;
+    FastSum h = block_entropy_fast(dim, [&](uint64_t i) { return __ddiv_rn(__dadd_rn(__dsub_rn(S[i], fl[i]), fc[i]), nd); });
+    if (threadIdx.x == 0) {
+        const double mean_entropy = __ddiv_rn(__dadd_rn(__dsub_rn(sc->E, H[low_row]), H[row]), nd);
+        const double d = h.e - mean_entropy;
+        const double b = fast_bound(dim, h.a, mean_entropy);
+        const double thr = sc->total_jsd + kEps, tb = sc->total_bound + 4.0 * kEps;
+        if (h.bad || !fast_total_ok(dim, h.t) || !(d == d)) {
+            atomicMin(&sc->first_unsure, pos);
+        } else if (d - b > thr + tb) {
+            atomicMin(&sc->first_true, pos);
+        } else if (!(d + b < thr - tb)) {
+            atomicMin(&sc->first_unsure, pos);
+        }
+    }
+}
+
+// fast total_jsd + get_lowest_record_index: same shape as k_sel_update.  Leaves approximate
+// total_jsd (with total_bound) and mdelta, and lowest_index only if it is certain.
+__global__ void __launch_bounds__(kFastThreads)
+k_sel_update_fast(const double* __restrict__ F, const double* __restrict__ H, uint64_t dim,
+                  const double* __restrict__ S, const unsigned* __restrict__ members, double* __restrict__ mdelta,
+                  double* __restrict__ mbound, SelScal* sc) {
+    __shared__ unsigned s_last;
+    const unsigned j = blockIdx.x, n = sc->n;
+    const double nd = (double)n;
+    if (j == n) {
+        FastSum h = block_entropy_fast(dim, [&](uint64_t i) { return __ddiv_rn(S[i], nd); });
+        if (threadIdx.x == 0) {
+            const double me = __ddiv_rn(sc->E, nd);
+            sc->total_jsd = h.e - me;
+            sc->total_bound = fast_bound(dim, h.a, me);
+            if (h.bad || !fast_total_ok(dim, h.t)) atomicExch(&sc->state_unsure, 1u);
+        }
+    } else {
+        const unsigned row = members[j];
+        const double div = __dsub_rn(nd, 1.0);
+        const double* f = F + (size_t)row * dim;
+        FastSum h = block_entropy_fast(dim, [&](uint64_t i) {
+            double m = __ddiv_rn(__dsub_rn(S[i], f[i]), div);
+            return (m <= kEps) ? 0.0 : m;
+        });
+        if (threadIdx.x == 0) {
+            const double mean_entropy = __ddiv_rn(__dsub_rn(sc->E, H[row]), div);
+            mdelta[j] = h.e - mean_entropy;
+            mbound[j] = fast_bound(dim, h.a, mean_entropy);
+            if (h.bad || !fast_total_ok(dim, h.t)) atomicExch(&sc->state_unsure, 1u);
+        }
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(&sc->ticket, 1u) == n) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        volatile double* md = mdelta;
+        volatile double* mb = mbound;
+        const double total = *(volatile double*)&sc->total_jsd;
+        const double tb = *(volatile double*)&sc->total_bound;
+        // delta_j = total - jsd_j; the common error of `total` does not affect the ordering, so only
+        // the per-member bounds matter for the argmin
+        double mn = 1e300, mn_b = 0.0;
+        unsigned low = 0;
+        for (unsigned t = 0; t < n; ++t) {
+            const double d = total - md[t];
+            md[t] = d;
+            if (d < mn) {
+                mn = d;
+                mn_b = mb[t];
+                low = t;
+            }
+        }
+        unsigned unsure = 0;
+        for (unsigned t = 0; t < n; ++t) {
+            if (t == low) continue;
+            // certain only if member `low` is smaller than every other for all admissible errors
+            if (!(mn + mn_b + 2.0 * kEps < md[t] - mb[t])) unsure = 1;
+        }
+        if (!(mn + mn_b + tb < 1e6)) unsure = 1;  // the reference's `min_delta_jsd = 1e6` initial value
+        sc->lowest = low;
+        if (unsure) atomicExch(&sc->state_unsure, 1u);
+        sc->exact = 0;
+        sc->ticket = 0;
+        sc->first_true = kNone;
+        sc->first_panic = kNone;
+        sc->first_unsure = kNone;
+    }
+}
+
+// replace_lowest + total_jsd + get_lowest_record_index in ONE launch (fast path).  Every CTA forms
+// the updated sums S'[i] = clamp(S[i] - f_low[i]) + f_c[i] on the fly from the OLD buffers (same
+// operations as k_sel_replace_vec, so S' is bitwise the reference's); CTA n also stores S' and the
+// last CTA to finish stores the new member list / scalars into the other buffer set.
+__global__ void __launch_bounds__(kFastThreads)
+k_sel_replace_update_fast(const double* __restrict__ F, const double* __restrict__ H, uint64_t dim,
+                          const double* __restrict__ S_in, double* __restrict__ S_out,
+                          const unsigned* __restrict__ m_in, unsigned* __restrict__ m_out,
+                          uint8_t* __restrict__ is_member, double* __restrict__ mdelta, double* __restrict__ mbound,
+                          SelScal* sc, unsigned cand_row) {
+    __shared__ unsigned s_last;
+    const unsigned j = blockIdx.x, n = sc->n, low = sc->lowest;
+    const double nd = (double)n;
+    const unsigned low_row = m_in[low];
+    const double* fl = F + (size_t)low_row * dim;
+    const double* fc = F + (size_t)cand_row * dim;
+    const double E_new = __dadd_rn(__dsub_rn(sc->E, H[low_row]), H[cand_row]);  // records.rs:101,129
+    auto s_new = [&](uint64_t i) {
+        double s = __dsub_rn(S_in[i], fl[i]);
+        if (s <= kEps) s = 0.0;
+        return __dadd_rn(s, fc[i]);
+    };
+    if (j == n) {
+        FastSum h = block_entropy_fast(dim, [&](uint64_t i) {
+            const double s = s_new(i);
+            S_out[i] = s;
+            return __ddiv_rn(s, nd);
+        });
+        if (threadIdx.x == 0) {
+            const double me = __ddiv_rn(E_new, nd);
+            sc->total_jsd = h.e - me;
+            sc->total_bound = fast_bound(dim, h.a, me);
+            if (h.bad || !fast_total_ok(dim, h.t)) atomicExch(&sc->state_unsure, 1u);
+        }
+    } else {
+        // member j of the list after Vec::remove(low) + push(cand)
+        const unsigned row = j < low ? m_in[j] : (j + 1 < n ? m_in[j + 1] : cand_row);
+        const double div = __dsub_rn(nd, 1.0);
+        const double* f = F + (size_t)row * dim;
+        FastSum h = block_entropy_fast(dim, [&](uint64_t i) {
+            double m = __ddiv_rn(__dsub_rn(s_new(i), f[i]), div);
+            return (m <= kEps) ? 0.0 : m;
+        });
+        if (threadIdx.x == 0) {
+            const double mean_entropy = __ddiv_rn(__dsub_rn(E_new, H[row]), div);
+            mdelta[j] = h.e - mean_entropy;
+            mbound[j] = fast_bound(dim, h.a, mean_entropy);
+            if (h.bad || !fast_total_ok(dim, h.t)) atomicExch(&sc->state_unsure, 1u);
+        }
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(&sc->ticket, 1u) == n) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        for (unsigned t = 0; t < n; ++t) m_out[t] = t < low ? m_in[t] : (t + 1 < n ? m_in[t + 1] : cand_row);
+        is_member[low_row] = 0;
+        is_member[cand_row] = 1;
+        sc->E = E_new;
+        volatile double* md = mdelta;
+        volatile double* mb = mbound;
+        const double total = *(volatile double*)&sc->total_jsd;
+        const double tb = *(volatile double*)&sc->total_bound;
+        double mn = 1e300, mn_b = 0.0;
+        unsigned lo2 = 0;
+        for (unsigned t = 0; t < n; ++t) {
+            const double d = total - md[t];
+            md[t] = d;
+            if (d < mn) {
+                mn = d;
+                mn_b = mb[t];
+                lo2 = t;
+            }
+        }
+        unsigned unsure = 0;
+        for (unsigned t = 0; t < n; ++t) {
+            if (t == lo2) continue;
+            if (!(mn + mn_b + 2.0 * kEps < md[t] - mb[t])) unsure = 1;
+        }
+        if (!(mn + mn_b + tb < 1e6)) unsure = 1;
+        sc->lowest = lo2;
+        if (unsure) atomicExch(&sc->state_unsure, 1u);
+        sc->exact = 0;
+        sc->ticket = 0;
+        sc->first_true = kNone;
+        sc->first_panic = kNone;
+        sc->first_unsure = kNone;
+    }
+}
+
 __global__ void k_set_members(uint8_t* is_member, const unsigned* members, unsigned n, uint8_t v) {
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) is_member[members[i]] = v;
@@ -245,12 +551,35 @@ struct Selector {
     int reset_scan(SelState& s) {
         static_assert(offsetof(SelScal, first_panic) == offsetof(SelScal, first_true) + sizeof(unsigned), "layout");
         DVS_CUDA_TRY(cudaMemsetAsync((char*)s.sc.p + offsetof(SelScal, first_true), 0xFF, 2 * sizeof(unsigned), st));
+        DVS_CUDA_TRY(cudaMemsetAsync((char*)s.sc.p + offsetof(SelScal, first_unsure), 0xFF, sizeof(unsigned), st));
+        return DVS_OK;
+    }
+    int update_fast(SelState& s, unsigned n) {
+        k_sel_update_fast<<<n + 1, kFastThreads, 0, st>>>(f->freqs.p, f->entropy.p, dim, s.S(), s.members(),
+                                                          s.mdelta.p, s.mbound.p, s.sc.p);
+        DVS_LAUNCHED(ctx);
+        return DVS_OK;
+    }
+    int replace_fast(SelState& s, unsigned n, unsigned cand_row, uint8_t* is_member) {
+        k_sel_replace_update_fast<<<n + 1, kFastThreads, 0, st>>>(f->freqs.p, f->entropy.p, dim, s.S(), s.S_other(),
+                                                                  s.members(), s.members_other(), is_member,
+                                                                  s.mdelta.p, s.mbound.p, s.sc.p, cand_row);
+        DVS_LAUNCHED(ctx);
+        s.flip();
+        return DVS_OK;
+    }
+    // (first_true / first_unsure are re-armed by every update kernel and stay armed after an empty
+    // window; the caller resets them explicitly after an exact single-candidate scan)
+    int scan_fast(SelState& s, const uint8_t* is_member, const unsigned* d_order, unsigned pos0, unsigned count) {
+        k_sel_scan_fast<<<count, kFastThreads, 0, st>>>(f->freqs.p, f->entropy.p, dim, s.S(), s.members(), s.sc.p,
+                                                         f->valid.p, is_member, d_order, pos0);
+        DVS_LAUNCHED(ctx);
         return DVS_OK;
     }
     // one candidate row of another kfreqs object, no order / validity / membership filters
     int scan_raw(SelState& s, const double* candF, const double* candH, unsigned row, double* delta_out) {
         DVS_TRY(reset_scan(s));
-        k_sel_scan<<<1, kEntThreads, kEntSmemBytes, st>>>(f->freqs.p, f->entropy.p, dim, s.S.p, s.members.p, s.sc.p,
+        k_sel_scan<<<1, kEntThreads, kEntSmemBytes, st>>>(f->freqs.p, f->entropy.p, dim, s.S(), s.members(), s.sc.p,
                                                            candF, candH, nullptr, nullptr, nullptr, row, delta_out);
         DVS_LAUNCHED(ctx);
         return DVS_OK;
@@ -258,27 +587,27 @@ struct Selector {
 
     // SummedRecords::new over `members` (+ optional pushed row): sums, then total_jsd + member deltas
     int build(SelState& s, const unsigned* d_members, unsigned n, int extra_row) {
-        k_sel_sum<<<vec_grid(), 256, 0, st>>>(f->freqs.p, f->entropy.p, dim, d_members, n, extra_row, s.S.p,
-                                              s.members.p, s.sc.p);
+        k_sel_sum<<<vec_grid(), 256, 0, st>>>(f->freqs.p, f->entropy.p, dim, d_members, n, extra_row, s.S(),
+                                              s.members(), s.sc.p);
         DVS_LAUNCHED(ctx);
         return update(s, n + (extra_row >= 0 ? 1u : 0u));
     }
     int update(SelState& s, unsigned n) {
-        k_sel_update<<<n + 1, kEntThreads, kEntSmemBytes, st>>>(f->freqs.p, f->entropy.p, dim, s.S.p, s.members.p,
+        k_sel_update<<<n + 1, kEntThreads, kEntSmemBytes, st>>>(f->freqs.p, f->entropy.p, dim, s.S(), s.members(),
                                                                  s.mdelta.p, s.sc.p);
         DVS_LAUNCHED(ctx);
         return DVS_OK;
     }
     int replace(SelState& s, unsigned n, unsigned cand_row, uint8_t* is_member) {
-        k_sel_replace_vec<<<vec_grid(), 256, 0, st>>>(f->freqs.p, f->entropy.p, dim, s.members.p, is_member,
-                                                      s.sc.p, cand_row, s.S.p);
+        k_sel_replace_vec<<<vec_grid(), 256, 0, st>>>(f->freqs.p, f->entropy.p, dim, s.members(), is_member,
+                                                      s.sc.p, cand_row, s.S());
         DVS_LAUNCHED(ctx);
         return update(s, n);
     }
     int scan(SelState& s, const dvs_kfreqs* q, const uint8_t* is_member, const unsigned* d_order, unsigned pos0,
              unsigned count, double* delta_out) {
         DVS_TRY(reset_scan(s));  // re-arm the min-index reduction
-        k_sel_scan<<<count, kEntThreads, kEntSmemBytes, st>>>(f->freqs.p, f->entropy.p, dim, s.S.p, s.members.p,
+        k_sel_scan<<<count, kEntThreads, kEntSmemBytes, st>>>(f->freqs.p, f->entropy.p, dim, s.S(), s.members(),
                                                                s.sc.p, q->freqs.p, q->entropy.p, q->valid.p,
                                                                is_member, d_order, pos0, delta_out);
         DVS_LAUNCHED(ctx);
@@ -383,33 +712,82 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
     unsigned cursor = min_size;
     unsigned accepts = 0;
     unsigned window = 64;  // adaptive: grows while windows come back empty, shrinks after a hit
+    // DVS_SELECT_EXACT_ONLY=1 disables the bounded-error fast path (tests compare both)
+    const char* exact_env = getenv("DVS_SELECT_EXACT_ONLY");
+    const bool use_fast = !(exact_env && exact_env[0] == '1');
+    unsigned exact_evals = 0;
     while (cursor < num) {
         const unsigned count = std::min(window, num - cursor);
-        DVS_TRY(sel.scan(*cur, f, is_member.p, d_order.p, cursor, count, nullptr));
-        DVS_TRY(sel.read(*cur));
-        const SelScal h = *sel.h_sc;
-        if (h.panic) return panic_error(h);
-        if (h.first_panic != kNone && h.first_panic <= h.first_true) {
-            set_error("cannot calculate entropy as frequency vector total !=1.0 (candidate at position %u)",
-                      h.first_panic);
-            return DVS_ERR_VALUE;
+        SelScal h;
+        unsigned pos = kNone;
+        if (use_fast) {
+            DVS_TRY(sel.scan_fast(*cur, is_member.p, d_order.p, cursor, count));
+            DVS_TRY(sel.read(*cur));
+            h = *sel.h_sc;
+            if (h.panic) return panic_error(h);
+            if (h.state_unsure) {
+                // the last fast update could not certify lowest_index / a sum check: redo it exactly and
+                // re-score the window against the now certain state
+                DVS_TRY(sel.update(*cur, n));
+                ++exact_evals;
+                continue;
+            }
+            if (h.first_unsure < h.first_true) {
+                // an undecided candidate comes before the first certain acceptance: decide it exactly
+                const unsigned pu = h.first_unsure;
+                if (!h.exact) DVS_TRY(sel.update(*cur, n));
+                DVS_TRY(sel.scan(*cur, f, is_member.p, d_order.p, pu, 1, nullptr));
+                DVS_TRY(sel.read(*cur));
+                h = *sel.h_sc;
+                ++exact_evals;
+                if (h.panic) return panic_error(h);
+                if (h.first_panic == pu) {
+                    set_error("cannot calculate entropy as frequency vector total !=1.0 (candidate at position %u)", pu);
+                    return DVS_ERR_VALUE;
+                }
+                if (h.first_true != pu) {  // rejected by the exact evaluation: carry on after it
+                    DVS_TRY(sel.reset_scan(*cur));
+                    cursor = pu + 1;
+                    continue;
+                }
+                pos = pu;
+            } else if (h.first_true != kNone) {
+                pos = h.first_true;
+            }
+        } else {
+            DVS_TRY(sel.scan(*cur, f, is_member.p, d_order.p, cursor, count, nullptr));
+            DVS_TRY(sel.read(*cur));
+            h = *sel.h_sc;
+            if (h.panic) return panic_error(h);
+            if (h.first_panic != kNone && h.first_panic <= h.first_true) {
+                set_error("cannot calculate entropy as frequency vector total !=1.0 (candidate at position %u)",
+                          h.first_panic);
+                return DVS_ERR_VALUE;
+            }
+            pos = h.first_true;
         }
-        if (h.first_true == kNone) {
+        if (pos == kNone) {
             cursor += count;
             window = std::min(window * 2, window_max);
             continue;
         }
-        const unsigned pos = h.first_true;
         const unsigned row = order[pos];
         window = std::max(64u, std::min(window_max, 2 * (pos - cursor + 1)));
         cursor = pos + 1;
-        if (!grow_mode || n == max_size) {
-            DVS_TRY(sel.replace(*cur, n, row, is_member.p));  // replace_lowest, records.rs:111-118
+        if (!grow_mode || n == max_size) {  // replace_lowest, records.rs:111-118
+            DVS_TRY(use_fast ? sel.replace_fast(*cur, n, row, is_member.p) : sel.replace(*cur, n, row, is_member.p));
             ++accepts;
             continue;
         }
-        // records.rs:434-451: nw = clone(); nw.push(rec); keep whichever has the larger statistic
-        DVS_TRY(sel.build(*alt, cur->members.p, n, (int)row));
+        // records.rs:434-451: nw = clone(); nw.push(rec); keep whichever has the larger statistic.
+        // The statistics are compared exactly, so both states are evaluated by the exact kernel.
+        if (!h.exact) {
+            DVS_TRY(sel.update(*cur, n));
+            DVS_TRY(sel.read(*cur));
+            h = *sel.h_sc;
+            if (h.panic) return panic_error(h);
+        }
+        DVS_TRY(sel.build(*alt, cur->members(), n, (int)row));
         DVS_TRY(sel.read(*alt));
         const SelScal hb = *sel.h_sc;
         if (hb.panic) return panic_error(hb);
@@ -422,12 +800,17 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
             uint8_t one = 1;
             DVS_CUDA_TRY(cudaMemcpyAsync(is_member.p + row, &one, 1, cudaMemcpyHostToDevice, st));
             DVS_CUDA_TRY(cudaStreamSynchronize(st));
+        } else {
+            DVS_TRY(sel.reset_scan(*cur));  // candidate discarded: re-arm the min-index reduction of `cur`
         }
     }
     DVS_TRY(sel.read(*cur));
+    if (!sel.h_sc->exact || sel.h_sc->state_unsure) DVS_TRY(sel.update(*cur, n));  // reported numbers are exact
+    ctx->last_exact_evals = exact_evals;
+    DVS_TRY(sel.read(*cur));
     const SelScal h = *sel.h_sc;
     if (h.panic) return panic_error(h);
-    if (sel_idx) DVS_CUDA_TRY(cudaMemcpyAsync(sel_idx, cur->members.p, n * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    if (sel_idx) DVS_CUDA_TRY(cudaMemcpyAsync(sel_idx, cur->members(), n * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     if (sel_delta) DVS_CUDA_TRY(cudaMemcpyAsync(sel_delta, cur->mdelta.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
     DVS_CUDA_TRY(cudaStreamSynchronize(st));
     if (stats5) {
@@ -443,6 +826,7 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
 }
 
 uint32_t dvs_select_last_accepts(dvs_ctx* ctx) { return ctx->last_accepts; }
+uint32_t dvs_select_last_exact_evals(dvs_ctx* ctx) { return ctx->last_exact_evals; }
 
 int dvs_summed_create(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* members, uint32_t n, dvs_summed** out) {
     if (!ctx || !f || !out || (!members && n)) {
@@ -522,7 +906,7 @@ int dvs_summed_result(dvs_ctx* ctx, dvs_summed* s, uint32_t* sel_idx, double* se
     DVS_TRY(sel.read(s->st));
     const SelScal h = *sel.h_sc;
     if (sel_idx)
-        DVS_CUDA_TRY(cudaMemcpyAsync(sel_idx, s->st.members.p, s->n * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+        DVS_CUDA_TRY(cudaMemcpyAsync(sel_idx, s->st.members(), s->n * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
     if (sel_delta)
         DVS_CUDA_TRY(cudaMemcpyAsync(sel_delta, s->st.mdelta.p, s->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     DVS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));

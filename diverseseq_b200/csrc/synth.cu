@@ -56,8 +56,10 @@ __host__ __device__ inline void syn_table(uint64_t seed, uint32_t fam, uint32_t*
         uint64_t w[4], tot = 0;
         for (uint32_t j = 0; j < 4; ++j) {
             uint64_t h = syn_hash(seed, 4, fam, c * 4 + j);
-            uint64_t v = (h & 255) + 24;  // 24..279
-            w[j] = v * v;                 // squared: spread between bases up to ~135x
+            // sum of two uniforms ~ Gamma(2)-shaped weight => rows are Dirichlet(2,2,2,2)-like
+            // (SURVEY.md §8d), i.e. conditional base probabilities mostly within 0.08..0.5 as in
+            // real microbial genomes
+            w[j] = (h & 255) + ((h >> 8) & 255) + 2;
             tot += w[j];
         }
         uint64_t acc = 0;

@@ -130,6 +130,10 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
                uint32_t* size_out);
 /* number of candidates that changed the set during the last dvs_select on this ctx */
 uint32_t dvs_select_last_accepts(dvs_ctx* ctx);
+/* number of exact re-evaluations the bounded-error fast path had to request during the last
+ * dvs_select (0 when every decision was far from a tie; environment DVS_SELECT_EXACT_ONLY=1
+ * disables the fast path altogether) */
+uint32_t dvs_select_last_exact_evals(dvs_ctx* ctx);
 
 /* SummedRecords::new over the listed rows + delta_jsd queries: make_summed_records and
  * SummedRecordsWrapper (src/records.rs:509-524, src/records_py.rs:90-125) */

@@ -204,6 +204,25 @@ def test_select_reference_tiny_goldens(lib, ctx, orc):
         _check_select(lib, ctx, orc, seqs, 1, np.array(perm, dtype=np.uint32), lib.MODE_MAX_COV, 3, 4)
 
 
+def test_select_fast_path_equals_exact_only(lib, ctx, orc, monkeypatch):
+    """the bounded-error fast path must take exactly the decisions of the exact-only loop"""
+    flat, off = lib.synth_host(99, 1500, 12, 6000)
+    kf = lib.KFreqs.count(ctx, lib.SeqSet.upload(ctx, flat, off), 5)
+    order = np.random.default_rng(3).permutation(1500).astype(np.uint32)
+    for mode, lo, hi in ((lib.MODE_NMOST, 40, 40), (lib.MODE_MAX_STDEV, 10, 30), (lib.MODE_MAX_COV, 10, 60)):
+        monkeypatch.setenv("DVS_SELECT_EXACT_ONLY", "1")
+        i0, d0, s0 = kf.select(order, mode, lo, hi)
+        assert ctx._lib.dvs_select_last_exact_evals(ctx.handle) == 0
+        monkeypatch.setenv("DVS_SELECT_EXACT_ONLY", "0")
+        i1, d1, s1 = kf.select(order, mode, lo, hi)
+        assert i0.tolist() == i1.tolist() and np.array_equal(d0, d1) and np.array_equal(s0, s1)
+        assert ctx._lib.dvs_select_last_exact_evals(ctx.handle) <= 5  # decisions are far from ties here
+    _, of, oe, ov = orc.count_batch(flat, off, 5)
+    exp = orc.select_rows(of, oe, order, "nmost", 40, valid=ov)
+    i1, d1, s1 = kf.select(order, lib.MODE_NMOST, 40)
+    assert i1.tolist() == exp.ids.tolist() and np.array_equal(d1, exp.delta_jsd)
+
+
 def test_select_errors(lib, ctx):
     seqs = [np.array(s, dtype=np.uint8) for s in ([0, 0, 1, 1], [1, 1, 1, 3], [4, 4], [4])]
     kf = lib.KFreqs.count(ctx, lib.SeqSet.from_seqs(ctx, seqs), 1)
