@@ -197,13 +197,33 @@ def run_reference(a):
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")} | {"value": v},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
 # ------------------------------------------------------------------------ B200 leg ----
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: everything else any library prints to fd 1 (NCCL's version
+    banner, torchrun notices) is sent to stderr; emit() writes the line to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     a = parse_args()
+    claim_stdout()
     if a.impl == "reference":
         return run_reference(a)
 
@@ -343,7 +363,7 @@ def main():
                           "nmost_accepts": accepts, "total_gbp": total_bases / 1e9,
                           "selected_head": idx[:8].tolist(), "total_jsd": float(stats[0]),
                           "host_wall_ms_last_step": phase.get("host_wall_ms")}}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -426,9 +426,10 @@ int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dv
     }
     DVS_CUDA_TRY(dvs::enter(ctx));
     size_t free_b = 0, total_b = 0;
-    DVS_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
     const double need = (double)s->nrec * (double)dim * 12.0;
-    if (need > 0.9 * (double)free_b) {
+    // cudaMemGetInfo costs milliseconds and pooled blocks count as "used": only ask when it can matter
+    if (need > 8e9) DVS_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    if (need > 8e9 && need > 0.9 * (double)free_b) {
         set_error("dvs_count_kmers: dense rows need %.1f GB (nrec=%u, dim=%llu) but only %.1f GB are free", need / 1e9,
                   s->nrec, (unsigned long long)dim, free_b / 1e9);
         return DVS_ERR_ARG;

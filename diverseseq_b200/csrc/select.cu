@@ -41,7 +41,14 @@ struct SelScal {
     unsigned first_unsure;   // scan result: first position the fast scan could not decide
     unsigned state_unsure;   // fast update could not certify lowest_index / the sum checks
     unsigned exact;          // 1 when total_jsd / mdelta / lowest come from the exact kernel
-    unsigned pad_;
+    // ---- device-driven rounds (k_sel_scan_dev / k_sel_round_dev) ----
+    unsigned cursor;         // next position to examine
+    unsigned window;         // candidates scored per round
+    unsigned window_max;
+    unsigned num;            // number of positions
+    unsigned halt;           // 1: the host must resolve an undecided candidate / state exactly
+    unsigned accepts;        // candidates that replaced the lowest record so far
+    unsigned which;          // which copy of the double-buffered S / member list is current
 };
 
 struct SelState {
@@ -126,17 +133,34 @@ __global__ void k_sel_replace_vec(const double* __restrict__ F, const double* __
         s_last = (atomicAdd(&sc->ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
     }
     __syncthreads();
-    if (s_last && threadIdx.x == 0) {
+    if (s_last) {  // block-uniform
         const unsigned n = sc->n;
-        double e = __dsub_rn(sc->E, H[low_row]);
-        sc->E = __dadd_rn(e, H[cand_row]);
-        for (unsigned j = low; j + 1 < n; ++j) members[j] = members[j + 1];
-        members[n - 1] = cand_row;
-        if (is_member) {
-            is_member[low_row] = 0;
-            is_member[cand_row] = 1;
+        // Vec::remove(low) + push(cand): every thread moves a strided share, reads before writes
+        unsigned keep[8];
+        const unsigned per = (n + blockDim.x - 1) / blockDim.x;
+        if (per <= 8) {
+            for (unsigned q = 0; q < per; ++q) {
+                const unsigned j = threadIdx.x + q * blockDim.x;
+                keep[q] = (j >= low && j + 1 < n) ? members[j + 1] : 0u;
+            }
+            __syncthreads();
+            for (unsigned q = 0; q < per; ++q) {
+                const unsigned j = threadIdx.x + q * blockDim.x;
+                if (j >= low && j + 1 < n) members[j] = keep[q];
+            }
+        } else if (threadIdx.x == 0) {
+            for (unsigned j = low; j + 1 < n; ++j) members[j] = members[j + 1];
         }
-        sc->ticket = 0;
+        if (threadIdx.x == 0) {
+            double e = __dsub_rn(sc->E, H[low_row]);
+            sc->E = __dadd_rn(e, H[cand_row]);
+            members[n - 1] = cand_row;
+            if (is_member) {
+                is_member[low_row] = 0;
+                is_member[cand_row] = 1;
+            }
+            sc->ticket = 0;
+        }
     }
 }
 
@@ -181,40 +205,54 @@ k_sel_update(const double* __restrict__ F, const double* __restrict__ H, uint64_
         s_last = (atomicAdd(&sc->ticket, 1u) == n) ? 1u : 0u;
     }
     __syncthreads();
-    if (s_last && threadIdx.x == 0) {
+    if (s_last) {  // block-uniform: the last CTA finishes get_lowest_record_index + the statistics
         __threadfence();
-        volatile double* md = mdelta;
-        const double total_jsd = *(volatile double*)&sc->total_jsd;
-        double mn = 1e6;
-        unsigned low = 0;
-        double sum = 0.0;
-        for (unsigned t = 0; t < n; ++t) {
-            const double d = __dsub_rn(total_jsd, md[t]);
-            md[t] = d;
-            if (d < mn) {
-                mn = d;
-                low = t;
+        // the sums below are sequential (reference order); stage the n values in shared memory first so
+        // the single summing thread does not pay one L2 round trip per member
+        constexpr unsigned kStage = (unsigned)(kEntSmemBytes / sizeof(double));
+        const bool staged = n <= kStage;
+        if (staged) {
+            for (unsigned t = threadIdx.x; t < n; t += blockDim.x) ent_smem[t] = __ldcg(&mdelta[t]);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            volatile double* mdv = mdelta;
+            const double total_jsd = __ldcg(&sc->total_jsd);
+            double mn = 1e6;
+            unsigned low = 0;
+            double sum = 0.0;
+            for (unsigned t = 0; t < n; ++t) {
+                const double d = __dsub_rn(total_jsd, staged ? ent_smem[t] : mdv[t]);
+                if (staged) ent_smem[t] = d; else mdv[t] = d;
+                if (d < mn) {
+                    mn = d;
+                    low = t;
+                }
+                sum = __dadd_rn(sum, d);
             }
-            sum = __dadd_rn(sum, d);
+            const double mean = __ddiv_rn(sum, nd);
+            double ss = 0.0;
+            for (unsigned t = 0; t < n; ++t) {
+                const double d = __dsub_rn(staged ? ent_smem[t] : mdv[t], mean);
+                ss = __dadd_rn(ss, __dmul_rn(d, d));
+            }
+            const double sd = __dsqrt_rn(__ddiv_rn(ss, __dsub_rn(nd, 1.0)));
+            sc->lowest = low;
+            sc->mean = mean;
+            sc->stdv = sd;
+            sc->cov = __ddiv_rn(sd, mean);
+            sc->ticket = 0;
+            sc->first_true = kNone;
+            sc->first_panic = kNone;
+            sc->first_unsure = kNone;
+            sc->total_bound = 0.0;
+            sc->state_unsure = 0;
+            sc->exact = 1;
         }
-        const double mean = __ddiv_rn(sum, nd);
-        double ss = 0.0;
-        for (unsigned t = 0; t < n; ++t) {
-            const double d = __dsub_rn(md[t], mean);
-            ss = __dadd_rn(ss, __dmul_rn(d, d));
+        if (staged) {
+            __syncthreads();
+            for (unsigned t = threadIdx.x; t < n; t += blockDim.x) mdelta[t] = ent_smem[t];
         }
-        const double sd = __dsqrt_rn(__ddiv_rn(ss, __dsub_rn(nd, 1.0)));
-        sc->lowest = low;
-        sc->mean = mean;
-        sc->stdv = sd;
-        sc->cov = __ddiv_rn(sd, mean);
-        sc->ticket = 0;
-        sc->first_true = kNone;
-        sc->first_panic = kNone;
-        sc->first_unsure = kNone;
-        sc->total_bound = 0.0;
-        sc->state_unsure = 0;
-        sc->exact = 1;
     }
 }
 
@@ -331,12 +369,63 @@ __device__ __forceinline__ bool fast_total_ok(uint64_t dim, double t) {
     return lim > 0.0 && fabs(t - 1.0) <= lim;
 }
 
-// fast increases_jsd for a window; one CTA per position.  first_true / first_unsure by atomicMin.
-__global__ void __launch_bounds__(kFastThreads)
-k_sel_scan_fast(const double* __restrict__ F, const double* __restrict__ H, uint64_t dim, const double* __restrict__ S,
-                const unsigned* __restrict__ members, SelScal* sc, const uint8_t* __restrict__ valid,
-                const uint8_t* __restrict__ is_member, const unsigned* __restrict__ order, unsigned pos0) {
-    const unsigned pos = pos0 + blockIdx.x;
+// Block-cooperative end of a fast update (run by every thread of the LAST CTA to finish):
+// delta_j = total - jsd_j, argmin (lowest index wins ties) and the certainty test
+// "member `low` is smaller than every other member for all admissible errors".  Returns 1 when the
+// argmin could not be certified.  (A single thread walking n global values costs n L2 latencies.)
+__device__ __forceinline__ unsigned finalize_fast_block(double* mdelta, const double* mbound, unsigned n, double total,
+                                                        double total_bound, unsigned* low_out) {
+    __shared__ double s_mn[kFastThreads / 32], s_mb[kFastThreads / 32];
+    __shared__ unsigned s_ix[kFastThreads / 32];
+    __shared__ double s_best, s_bestb;
+    __shared__ unsigned s_besti;
+    double mn = 1e300, mb = 0.0;
+    unsigned ix = kNone;
+    for (unsigned t = threadIdx.x; t < n; t += blockDim.x) {
+        const double d = total - __ldcg(&mdelta[t]);
+        mdelta[t] = d;
+        if (d < mn || (d == mn && t < ix)) {
+            mn = d;
+            mb = __ldcg(&mbound[t]);
+            ix = t;
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        const double omn = __shfl_xor_sync(0xffffffffu, mn, o), omb = __shfl_xor_sync(0xffffffffu, mb, o);
+        const unsigned oix = __shfl_xor_sync(0xffffffffu, ix, o);
+        if (omn < mn || (omn == mn && oix < ix)) {
+            mn = omn; mb = omb; ix = oix;
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_mn[threadIdx.x >> 5] = mn; s_mb[threadIdx.x >> 5] = mb; s_ix[threadIdx.x >> 5] = ix;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (unsigned w = 1; w < blockDim.x / 32; ++w)
+            if (s_mn[w] < mn || (s_mn[w] == mn && s_ix[w] < ix)) {
+                mn = s_mn[w]; mb = s_mb[w]; ix = s_ix[w];
+            }
+        s_best = mn; s_bestb = mb; s_besti = (ix == kNone) ? 0u : ix;
+    }
+    __syncthreads();
+    mn = s_best; mb = s_bestb;
+    const unsigned low = s_besti;
+    int unsure = 0;
+    for (unsigned t = threadIdx.x; t < n; t += blockDim.x)
+        if (t != low && !(mn + mb + 2.0 * kEps < mdelta[t] - __ldcg(&mbound[t]))) unsure = 1;
+    if (!(mn + mb + total_bound < 1e6)) unsure = 1;  // the reference's `min_delta_jsd = 1e6` initial value
+    unsure = __syncthreads_or(unsure);
+    *low_out = low;
+    return (unsigned)unsure;
+}
+
+// fast increases_jsd of the candidate at position `pos`; first_true / first_unsure by atomicMin
+__device__ __forceinline__ void scan_fast_body(const double* __restrict__ F, const double* __restrict__ H, uint64_t dim,
+                                               const double* __restrict__ S, const unsigned* __restrict__ members,
+                                               SelScal* sc, const uint8_t* __restrict__ valid,
+                                               const uint8_t* __restrict__ is_member,
+                                               const unsigned* __restrict__ order, unsigned pos) {
     const unsigned row = order[pos];
     if (!valid[row] || is_member[row]) return;
     const unsigned n = sc->n;
@@ -358,6 +447,30 @@ k_sel_scan_fast(const double* __restrict__ F, const double* __restrict__ H, uint
             atomicMin(&sc->first_unsure, pos);
         }
     }
+}
+
+// host-driven window: one CTA per position pos0 + blockIdx.x
+__global__ void __launch_bounds__(kFastThreads)
+k_sel_scan_fast(const double* __restrict__ F, const double* __restrict__ H, uint64_t dim, const double* __restrict__ S,
+                const unsigned* __restrict__ members, SelScal* sc, const uint8_t* __restrict__ valid,
+                const uint8_t* __restrict__ is_member, const unsigned* __restrict__ order, unsigned pos0) {
+    scan_fast_body(F, H, dim, S, members, sc, valid, is_member, order, pos0 + blockIdx.x);
+}
+
+// device-driven window: cursor / window / current buffer come from the scalar block, so the host can
+// enqueue many rounds back to back without reading anything back
+__global__ void __launch_bounds__(kFastThreads)
+k_sel_scan_dev(const double* __restrict__ F, const double* __restrict__ H, uint64_t dim, const double* __restrict__ S0,
+               const double* __restrict__ S1, const unsigned* __restrict__ M0, const unsigned* __restrict__ M1,
+               SelScal* sc, const uint8_t* __restrict__ valid, const uint8_t* __restrict__ is_member,
+               const unsigned* __restrict__ order) {
+    if (sc->halt) return;
+    const unsigned cursor = sc->cursor, num = sc->num;
+    if (cursor >= num) return;
+    const unsigned count = min(sc->window, num - cursor);
+    if (blockIdx.x >= count) return;
+    const unsigned w = sc->which;
+    scan_fast_body(F, H, dim, w ? S1 : S0, w ? M1 : M0, sc, valid, is_member, order, cursor + blockIdx.x);
 }
 
 // fast total_jsd + get_lowest_record_index: same shape as k_sel_update.  Leaves approximate
@@ -397,39 +510,20 @@ k_sel_update_fast(const double* __restrict__ F, const double* __restrict__ H, ui
         s_last = (atomicAdd(&sc->ticket, 1u) == n) ? 1u : 0u;
     }
     __syncthreads();
-    if (s_last && threadIdx.x == 0) {
+    if (s_last) {  // block-uniform
         __threadfence();
-        volatile double* md = mdelta;
-        volatile double* mb = mbound;
-        const double total = *(volatile double*)&sc->total_jsd;
-        const double tb = *(volatile double*)&sc->total_bound;
-        // delta_j = total - jsd_j; the common error of `total` does not affect the ordering, so only
-        // the per-member bounds matter for the argmin
-        double mn = 1e300, mn_b = 0.0;
+        const double total = __ldcg(&sc->total_jsd), tb = __ldcg(&sc->total_bound);
         unsigned low = 0;
-        for (unsigned t = 0; t < n; ++t) {
-            const double d = total - md[t];
-            md[t] = d;
-            if (d < mn) {
-                mn = d;
-                mn_b = mb[t];
-                low = t;
-            }
+        const unsigned unsure = finalize_fast_block(mdelta, mbound, n, total, tb, &low);
+        if (threadIdx.x == 0) {
+            sc->lowest = low;
+            if (unsure) atomicExch(&sc->state_unsure, 1u);
+            sc->exact = 0;
+            sc->ticket = 0;
+            sc->first_true = kNone;
+            sc->first_panic = kNone;
+            sc->first_unsure = kNone;
         }
-        unsigned unsure = 0;
-        for (unsigned t = 0; t < n; ++t) {
-            if (t == low) continue;
-            // certain only if member `low` is smaller than every other for all admissible errors
-            if (!(mn + mn_b + 2.0 * kEps < md[t] - mb[t])) unsure = 1;
-        }
-        if (!(mn + mn_b + tb < 1e6)) unsure = 1;  // the reference's `min_delta_jsd = 1e6` initial value
-        sc->lowest = low;
-        if (unsure) atomicExch(&sc->state_unsure, 1u);
-        sc->exact = 0;
-        sc->ticket = 0;
-        sc->first_true = kNone;
-        sc->first_panic = kNone;
-        sc->first_unsure = kNone;
     }
 }
 
@@ -437,12 +531,12 @@ k_sel_update_fast(const double* __restrict__ F, const double* __restrict__ H, ui
 // the updated sums S'[i] = clamp(S[i] - f_low[i]) + f_c[i] on the fly from the OLD buffers (same
 // operations as k_sel_replace_vec, so S' is bitwise the reference's); CTA n also stores S' and the
 // last CTA to finish stores the new member list / scalars into the other buffer set.
-__global__ void __launch_bounds__(kFastThreads)
-k_sel_replace_update_fast(const double* __restrict__ F, const double* __restrict__ H, uint64_t dim,
-                          const double* __restrict__ S_in, double* __restrict__ S_out,
-                          const unsigned* __restrict__ m_in, unsigned* __restrict__ m_out,
-                          uint8_t* __restrict__ is_member, double* __restrict__ mdelta, double* __restrict__ mbound,
-                          SelScal* sc, unsigned cand_row) {
+// dev_pos != kNone: device-driven round; the last CTA also advances cursor / window / accepts / which.
+__device__ __forceinline__ void replace_update_fast_body(
+    const double* __restrict__ F, const double* __restrict__ H, uint64_t dim, const double* __restrict__ S_in,
+    double* __restrict__ S_out, const unsigned* __restrict__ m_in, unsigned* __restrict__ m_out,
+    uint8_t* __restrict__ is_member, double* __restrict__ mdelta, double* __restrict__ mbound, SelScal* sc,
+    unsigned cand_row, unsigned dev_pos, unsigned dev_cursor) {
     __shared__ unsigned s_last;
     const unsigned j = blockIdx.x, n = sc->n, low = sc->lowest;
     const double nd = (double)n;
@@ -488,41 +582,89 @@ k_sel_replace_update_fast(const double* __restrict__ F, const double* __restrict
         s_last = (atomicAdd(&sc->ticket, 1u) == n) ? 1u : 0u;
     }
     __syncthreads();
-    if (s_last && threadIdx.x == 0) {
+    if (s_last) {  // block-uniform: the whole last CTA finishes the round
         __threadfence();
-        for (unsigned t = 0; t < n; ++t) m_out[t] = t < low ? m_in[t] : (t + 1 < n ? m_in[t + 1] : cand_row);
-        is_member[low_row] = 0;
-        is_member[cand_row] = 1;
-        sc->E = E_new;
-        volatile double* md = mdelta;
-        volatile double* mb = mbound;
-        const double total = *(volatile double*)&sc->total_jsd;
-        const double tb = *(volatile double*)&sc->total_bound;
-        double mn = 1e300, mn_b = 0.0;
+        for (unsigned t = threadIdx.x; t < n; t += blockDim.x)
+            m_out[t] = t < low ? m_in[t] : (t + 1 < n ? m_in[t + 1] : cand_row);
+        const double total = __ldcg(&sc->total_jsd), tb = __ldcg(&sc->total_bound);
         unsigned lo2 = 0;
-        for (unsigned t = 0; t < n; ++t) {
-            const double d = total - md[t];
-            md[t] = d;
-            if (d < mn) {
-                mn = d;
-                mn_b = mb[t];
-                lo2 = t;
+        const unsigned unsure = finalize_fast_block(mdelta, mbound, n, total, tb, &lo2);
+        if (threadIdx.x == 0) {
+            is_member[low_row] = 0;
+            is_member[cand_row] = 1;
+            sc->E = E_new;
+            sc->lowest = lo2;
+            if (unsure) atomicExch(&sc->state_unsure, 1u);
+            sc->exact = 0;
+            sc->ticket = 0;
+            sc->first_true = kNone;
+            sc->first_panic = kNone;
+            sc->first_unsure = kNone;
+            if (dev_pos != kNone) {
+                sc->window = max(64u, min(sc->window_max, 2u * (dev_pos - dev_cursor + 1u)));
+                sc->cursor = dev_pos + 1u;
+                sc->accepts += 1u;
+                sc->which ^= 1u;
             }
         }
-        unsigned unsure = 0;
-        for (unsigned t = 0; t < n; ++t) {
-            if (t == lo2) continue;
-            if (!(mn + mn_b + 2.0 * kEps < md[t] - mb[t])) unsure = 1;
-        }
-        if (!(mn + mn_b + tb < 1e6)) unsure = 1;
-        sc->lowest = lo2;
-        if (unsure) atomicExch(&sc->state_unsure, 1u);
-        sc->exact = 0;
-        sc->ticket = 0;
-        sc->first_true = kNone;
-        sc->first_panic = kNone;
-        sc->first_unsure = kNone;
     }
+}
+
+__global__ void __launch_bounds__(kFastThreads)
+k_sel_replace_update_fast(const double* __restrict__ F, const double* __restrict__ H, uint64_t dim,
+                          const double* __restrict__ S_in, double* __restrict__ S_out,
+                          const unsigned* __restrict__ m_in, unsigned* __restrict__ m_out,
+                          uint8_t* __restrict__ is_member, double* __restrict__ mdelta, double* __restrict__ mbound,
+                          SelScal* sc, unsigned cand_row) {
+    replace_update_fast_body(F, H, dim, S_in, S_out, m_in, m_out, is_member, mdelta, mbound, sc, cand_row, kNone, 0u);
+}
+
+// One device-driven round after k_sel_scan_dev: every CTA takes the same decision from the scalar
+// block (only the last CTA to finish modifies it): accept the first certain candidate (fused
+// replace + update), advance past an empty window, or halt for the host when the first
+// interesting candidate / the state could not be decided within the error bound.
+__global__ void __launch_bounds__(kFastThreads)
+k_sel_round_dev(const double* __restrict__ F, const double* __restrict__ H, uint64_t dim, double* __restrict__ S0,
+                double* __restrict__ S1, unsigned* __restrict__ M0, unsigned* __restrict__ M1,
+                uint8_t* __restrict__ is_member, double* __restrict__ mdelta, double* __restrict__ mbound, SelScal* sc,
+                const unsigned* __restrict__ order) {
+    __shared__ unsigned s_last2;
+    if (sc->halt) return;
+    const unsigned cursor = sc->cursor, num = sc->num;
+    if (cursor >= num) return;
+    const unsigned window = sc->window, count = min(window, num - cursor);
+    const unsigned ft = sc->first_true, fu = sc->first_unsure, su = sc->state_unsure, n = sc->n;
+    if (!su && !(fu < ft) && ft != kNone) {
+        const unsigned w = sc->which;
+        replace_update_fast_body(F, H, dim, w ? S1 : S0, w ? S0 : S1, w ? M1 : M0, w ? M0 : M1, is_member, mdelta,
+                                 mbound, sc, order[ft], ft, cursor);
+        return;
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last2 = (atomicAdd(&sc->ticket, 1u) == n) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last2 && threadIdx.x == 0) {
+        sc->ticket = 0;
+        if (su || fu < ft) {
+            sc->halt = 1u;
+        } else {  // empty window
+            sc->cursor = cursor + count;
+            sc->window = min(window * 2u, sc->window_max);
+        }
+    }
+}
+
+__global__ void k_sel_set_dev(SelScal* sc, unsigned cursor, unsigned window, unsigned window_max, unsigned num,
+                              unsigned accepts, unsigned which) {
+    sc->cursor = cursor;
+    sc->window = window;
+    sc->window_max = window_max;
+    sc->num = num;
+    sc->accepts = accepts;
+    sc->which = which;
+    sc->halt = 0;
 }
 
 __global__ void k_set_members(uint8_t* is_member, const unsigned* members, unsigned n, uint8_t v) {
@@ -716,7 +858,40 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
     const char* exact_env = getenv("DVS_SELECT_EXACT_ONLY");
     const bool use_fast = !(exact_env && exact_env[0] == '1');
     unsigned exact_evals = 0;
+    const unsigned window_max_dev = std::max(64u, (unsigned)ctx->sm_count * 4u);  // grid of a device-driven scan
+    const char* dev_env = getenv("DVS_SELECT_HOST_LOOP");
+    const bool use_dev = use_fast && !(dev_env && dev_env[0] == '1');
+    constexpr int kRoundsPerBatch = 32;
     while (cursor < num) {
+        if (use_dev && (!grow_mode || n == max_size)) {
+            // Device-driven rounds: scan + decide + replace/update are enqueued kRoundsPerBatch times
+            // without any read-back; the kernels carry cursor / window / accepts in the scalar block
+            // and stop doing work once they halt (undecided within the error bound) or finish.
+            k_sel_set_dev<<<1, 1, 0, st>>>(cur->sc.p, cursor, std::min(window, window_max_dev), window_max_dev, num,
+                                           accepts, (unsigned)cur->which);
+            DVS_LAUNCHED(ctx);
+            for (int r = 0; r < kRoundsPerBatch; ++r) {
+                k_sel_scan_dev<<<window_max_dev, kFastThreads, 0, st>>>(
+                    f->freqs.p, f->entropy.p, dim, cur->Sbuf[0].p, cur->Sbuf[1].p, cur->membuf[0].p, cur->membuf[1].p,
+                    cur->sc.p, f->valid.p, is_member.p, d_order.p);
+                DVS_LAUNCHED(ctx);
+                k_sel_round_dev<<<n + 1, kFastThreads, 0, st>>>(
+                    f->freqs.p, f->entropy.p, dim, cur->Sbuf[0].p, cur->Sbuf[1].p, cur->membuf[0].p, cur->membuf[1].p,
+                    is_member.p, cur->mdelta.p, cur->mbound.p, cur->sc.p, d_order.p);
+                DVS_LAUNCHED(ctx);
+            }
+            DVS_TRY(sel.read(*cur));
+            const SelScal hd = *sel.h_sc;
+            if (hd.panic) return panic_error(hd);
+            cursor = hd.cursor;
+            window = hd.window;
+            accepts = hd.accepts;
+            cur->which = (int)hd.which;
+            if (!hd.halt) continue;  // finished, or simply out of enqueued rounds
+            // halted: one host-driven iteration below resolves the undecided state / candidate exactly
+            DVS_TRY(sel.reset_scan(*cur));
+            if (cursor >= num) break;
+        }
         const unsigned count = std::min(window, num - cursor);
         SelScal h;
         unsigned pos = kNone;

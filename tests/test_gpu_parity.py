@@ -214,9 +214,11 @@ def test_select_fast_path_equals_exact_only(lib, ctx, orc, monkeypatch):
         i0, d0, s0 = kf.select(order, mode, lo, hi)
         assert ctx._lib.dvs_select_last_exact_evals(ctx.handle) == 0
         monkeypatch.setenv("DVS_SELECT_EXACT_ONLY", "0")
-        i1, d1, s1 = kf.select(order, mode, lo, hi)
-        assert i0.tolist() == i1.tolist() and np.array_equal(d0, d1) and np.array_equal(s0, s1)
-        assert ctx._lib.dvs_select_last_exact_evals(ctx.handle) <= 5  # decisions are far from ties here
+        for host_loop in ("1", "0"):  # host-driven fast rounds, then device-driven rounds
+            monkeypatch.setenv("DVS_SELECT_HOST_LOOP", host_loop)
+            i1, d1, s1 = kf.select(order, mode, lo, hi)
+            assert i0.tolist() == i1.tolist() and np.array_equal(d0, d1) and np.array_equal(s0, s1)
+            assert ctx._lib.dvs_select_last_exact_evals(ctx.handle) <= 5  # decisions are far from ties here
     _, of, oe, ov = orc.count_batch(flat, off, 5)
     exp = orc.select_rows(of, oe, order, "nmost", 40, valid=ov)
     i1, d1, s1 = kf.select(order, lib.MODE_NMOST, 40)
