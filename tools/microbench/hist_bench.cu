@@ -28,13 +28,13 @@ __device__ __forceinline__ uint32_t pack16(uint4 v) { return (pack4(v.x) << 24) 
 template <int MODE, int K, int COPIES>
 __global__ void k_hist(const uint8_t* __restrict__ seq, size_t n, uint32_t* __restrict__ out, size_t chunk) {
     extern __shared__ uint32_t hist[];
-    constexpr uint32_t KK = (MODE == 2) ? K + 1 : (MODE == 5 ? K + 2 : K);
+    constexpr uint32_t KK = (MODE == 2 || MODE == 6) ? K + 1 : (MODE == 5 ? K + 2 : K);
     constexpr uint32_t BINS = 1u << (2 * KK);
     constexpr uint32_t WORDS = (MODE == 5) ? BINS / 2 : BINS;
     constexpr uint32_t mask = BINS - 1u;
     uint32_t sink = 0;
     for (size_t c0 = (size_t)blockIdx.x * chunk; c0 < n; c0 += (size_t)gridDim.x * chunk) {
-        if (MODE == 0 || MODE == 2 || MODE == 4 || MODE == 5) {
+        if (MODE == 0 || MODE == 2 || MODE == 4 || MODE == 5 || MODE == 6) {
             for (uint32_t i = threadIdx.x; i < WORDS * COPIES; i += blockDim.x) hist[i] = 0;
             __syncthreads();
         }
@@ -64,12 +64,22 @@ __global__ void k_hist(const uint8_t* __restrict__ seq, size_t n, uint32_t* __re
                         atomicAdd(&hist[idx >> 1], 1u << (16 * (idx & 1)));
                     }
                 }
+            } else if (MODE == 6) {
+                // lane-group replication: lanes [g*32/COPIES, (g+1)*32/COPIES) use replica g, which owns the
+                // banks [g*32/COPIES, ...): address = (idx / BPG) * 32 + idx % BPG + g * BPG, BPG = 32/COPIES
+                constexpr uint32_t BPG = 32 / COPIES;
+                const uint32_t goff = ((threadIdx.x & 31) / BPG) * BPG;
+#pragma unroll
+                for (int j = 1; j < 16; j += 2) {
+                    uint32_t idx = __funnelshift_r(pc, pp, 2 * (15 - j)) & mask;
+                    atomicAdd(&hist[(idx / BPG) * 32 + (idx % BPG) + goff], 1u);
+                }
             } else if (MODE == 3) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) atomicAdd(&out[__funnelshift_r(pc, pp, 2 * (15 - j)) & mask], 1u);
             }
         }
-        if (MODE == 0 || MODE == 2 || MODE == 4 || MODE == 5) {
+        if (MODE == 0 || MODE == 2 || MODE == 4 || MODE == 5 || MODE == 6) {
             __syncthreads();
             for (uint32_t i = threadIdx.x; i < WORDS * COPIES; i += blockDim.x) { uint32_t c = hist[i]; if (c) atomicAdd(&out[i % WORDS], c); }
             __syncthreads();
@@ -116,7 +126,7 @@ template <class F> float time_ms(F f, int reps = 5) {
 
 template <int MODE, int K, int COPIES>
 void run_hist(const char* name, const uint8_t* seq, size_t n, uint32_t* out, int threads, int ctas_per_sm, int sms) {
-    constexpr uint32_t KK = (MODE == 2) ? K + 1 : (MODE == 5 ? K + 2 : K);
+    constexpr uint32_t KK = (MODE == 2 || MODE == 6) ? K + 1 : (MODE == 5 ? K + 2 : K);
     size_t smem = (MODE == 1 || MODE == 3) ? 0 : (size_t)(MODE == 5 ? (1u << (2 * KK)) / 2 : (1u << (2 * KK))) * 4 * COPIES;
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_hist<MODE, K, COPIES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = sms * ctas_per_sm;
@@ -151,6 +161,12 @@ int main() {
         run_hist<2, 6, 1>("(k+1)-mers stride 2 (half the atomics)", seq, n, out, 512, 3, sms);
         run_hist<2, 6, 1>("(k+1)-mers stride 2 (half the atomics)", seq, n, out, 1024, 2, sms);
         run_hist<5, 6, 1>("(k+2)-mers stride 3, u16-packed", seq, n, out, 1024, 1, sms);
+        run_hist<6, 6, 1>("stride 2, lane-group replicas x1 (=MODE 2 layout)", seq, n, out, 1024, 1, sms);
+        run_hist<6, 6, 2>("stride 2, lane-group replicas x2 (16 banks each)", seq, n, out, 1024, 1, sms);
+        run_hist<6, 5, 1>("stride 2, replicas x1, k=5", seq, n, out, 1024, 2, sms);
+        run_hist<6, 5, 2>("stride 2, replicas x2, k=5", seq, n, out, 1024, 2, sms);
+        run_hist<6, 5, 4>("stride 2, replicas x4, k=5 (8 banks each)", seq, n, out, 1024, 2, sms);
+        run_hist<6, 5, 8>("stride 2, replicas x8, k=5 (4 banks each)", seq, n, out, 1024, 1, sms);
         run_hist<3, 8, 1>("global RED, 256 KB table", seq, n, out, 512, 4, sms);
         run_hist<3, 10, 1>("global RED, 4 MB table", seq, n, out, 512, 4, sms);
         run_hist<3, 12, 1>("global RED, 64 MB table", seq, n, out, 512, 4, sms);
