@@ -46,6 +46,9 @@ def parse_args():
     ap.add_argument("--nfam", type=int, default=64)
     ap.add_argument("--k", type=int, default=6)
     ap.add_argument("--n", type=int, default=100)
+    ap.add_argument("--multi", default="chunked", choices=["chunked", "union"],
+                    help="N>1 selection: 'chunked' = the reference's -np N semantics (select per GPU, merge with "
+                         "final_nmost); 'union' = single-pass selection over all records on every GPU")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of one CPU sample")
@@ -58,7 +61,10 @@ def workload_config(a, world):
                     f"(~{a.mean_len / 1e6:g} Mbp each, {a.nfam} Markov families, invalid runs 1e-4) per GPU "
                     "[BASELINE.json configs[1]]",
         "nrec_per_gpu": a.nrec, "mean_len": a.mean_len, "k": a.k, "n": a.n, "seed": SEED,
-        "parallelism": f"records sharded x{world}, rows all-gathered, selection replicated" if world > 1 else "1 GPU",
+        "parallelism": ("1 GPU" if world == 1 else
+                        f"records sharded x{world}; nmost per GPU then final_nmost merge of the {world}x{a.n} winners "
+                        "(reference -np semantics, records.py:206-251)" if a.multi == "chunked" else
+                        f"records sharded x{world}, rows all-gathered, single-pass selection replicated"),
         "l2": "inputs (~42 GB/GPU) are far larger than the 126 MB L2, no flush needed",
     }
 
@@ -248,6 +254,7 @@ def main():
     bases = seqset.total_bases
     total_bases = shard.sum_over_ranks(bases, device)
     order = shard.global_order(SEED, a.nrec * world)
+    local_order = shard.global_order(SEED + rank, a.nrec)
 
     def barrier():
         if world > 1:
@@ -262,9 +269,13 @@ def main():
         t1 = time.perf_counter()
         phase["count_ms"] = ctx.phase_ms(_lib.PHASE_COUNT_KERNEL)
         phase["freq_entropy_ms"] = ctx.phase_ms(_lib.PHASE_FREQ_ENTROPY)
-        allf = shard.all_gather_kfreqs(ctx, kf, device) if world > 1 else kf
-        t2 = time.perf_counter()
-        idx, delta, stats = allf.select(order, _lib.MODE_NMOST, a.n)
+        if world > 1 and a.multi == "chunked":
+            t2 = t1
+            idx, delta, stats = shard.chunked_select(ctx, kf, local_order, _lib.MODE_NMOST, a.n, a.n, device)
+        else:
+            allf = shard.all_gather_kfreqs(ctx, kf, device) if world > 1 else kf
+            t2 = time.perf_counter()
+            idx, delta, stats = allf.select(order, _lib.MODE_NMOST, a.n)
         t3 = time.perf_counter()
         phase["select_ms"] = ctx.phase_ms(_lib.PHASE_SELECT)
         phase["host_wall_ms"] = {"count_call": (t1 - t0) * 1e3, "gather": (t2 - t1) * 1e3, "select_call": (t3 - t2) * 1e3}
@@ -311,8 +322,16 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = algo_bytes / (kc_ms * 1e-3) / 1e9
+    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture
+    try:
+        tr = json.loads((ROOT / "profiles" / "r1_k_count_traffic.json").read_text())
+        wl = tr["workload"]
+        if (wl["nrec"], wl["mean_len"], wl["k"]) == (a.nrec, a.mean_len, a.k):
+            traffic = tr["traffic_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "k_count", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None,
+                "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
                 "kernel_ms": kc_ms, "algorithmic_bytes_per_launch": algo_bytes}
 

@@ -10,9 +10,9 @@ distance.py:218,326-327; cluster.py:328,377) work unchanged:
     make_zarr_store / ZarrStoreWrapper (in-memory variant), get_seqids_from_store
 
 There is no CPU fallback: every numeric result comes from the CUDA library and a missing
-library / GPU raises.  Storage (.dvseqsz Zarr directories) is outside this round's scope
-(SURVEY.md §8f-1); the in-memory store the reference's tests use as their fake backend
-(src/zarr_io.rs:67) is provided so those tests can be restated against this module.
+library / GPU raises.  `make_zarr_store()` gives the in-memory store the reference's tests use as
+their fake backend (src/zarr_io.rs:67); `make_zarr_store(path)` opens a `.dvseqsz` directory
+(diverseseq_b200/dvseqsz.py).
 """
 from __future__ import annotations
 
@@ -120,12 +120,18 @@ class ZarrStoreWrapper:
         return [LazySeq(s, self, num_states) for s in self.get_seqids()]
 
 
-def make_zarr_store(path: str | None = None, mode: str = "r") -> ZarrStoreWrapper:
-    return ZarrStoreWrapper(path, mode)
+def make_zarr_store(path: str | None = None, mode: str = "r"):
+    """src/lib.rs:23-27: no path -> in-memory store, else the `.dvseqsz` directory store"""
+    if path is None:
+        return ZarrStoreWrapper(None, mode)
+    from .dvseqsz import DvseqszStore
+    return DvseqszStore(path, mode)
 
 
 def get_seqids_from_store(path: str) -> list[str]:
-    return ZarrStoreWrapper(path, "r").get_seqids()
+    """src/lib.rs:29-34"""
+    from .dvseqsz import DvseqszStore
+    return DvseqszStore(path, "r").get_seqids()
 
 
 # ------------------------------------------------------------------------------ results ----
@@ -200,7 +206,11 @@ def _select_from_store(store, seqids, k, num_states, mode, min_size, max_size) -
     ctx = _lib.default_context()
     seqids = list(store.unique_seqids if seqids is None else seqids)
     names, order = _rows_and_order(seqids)
-    seqset = _lib.SeqSet.from_seqs(ctx, [_read_array(store, n) for n in names])
+    if hasattr(store, "read_into"):  # on-disk .dvseqsz: threaded zstd decode into a pinned staging buffer
+        from .dvseqsz import load_seqset
+        seqset, _ = load_seqset(ctx, store, names)
+    else:
+        seqset = _lib.SeqSet.from_seqs(ctx, [_read_array(store, n) for n in names])
     if k == 0:
         raise ValueError("k cannot be 0")
     if len(seqids) < min_size:  # before any counting, like records.rs:323-325

@@ -45,6 +45,7 @@ SIGNATURES = {
     "dvs_kfreqs_from_rows": (_i32, [_vp, _vp, _vp, _u32, _u64, C.POINTER(_vp)]),
     "dvs_kfreqs_device_ptrs": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "dvs_kfreqs_from_device": (_i32, [_vp, _vp, _vp, _vp, _u32, _u64, C.POINTER(_vp)]),
+    "dvs_kfreqs_take_rows": (_i32, [_vp, _vp, _vp, _u32, C.POINTER(_vp)]),
     "dvs_kfreqs_nrec": (_u32, [_vp]),
     "dvs_kfreqs_dim": (_u64, [_vp]),
     "dvs_kfreqs_download": (_i32, [_vp, _vp, _u32, _u32, _vp, _vp, _vp, _vp]),
@@ -286,12 +287,22 @@ class KFreqs(_Handle):
         return cls(ctx, h)
 
     @classmethod
-    def from_device(cls, ctx: Context, rows_ptr: int, ent_ptr: int, valid_ptr: int, nrec: int, dim: int) -> "KFreqs":
-        """device-to-device copy from gathered device buffers (raw pointers on ctx's GPU)"""
+    def from_device(cls, ctx: Context, rows_ptr: int, ent_ptr: int | None, valid_ptr: int | None, nrec: int,
+                    dim: int) -> "KFreqs":
+        """device-to-device copy from gathered device buffers (raw pointers on ctx's GPU); ent_ptr None
+        recomputes the entropies from the rows (KmerSeq::new), valid_ptr None marks every row valid"""
         h = _vp()
-        check(ctx._lib.dvs_kfreqs_from_device(ctx.handle, _vp(rows_ptr), _vp(ent_ptr), _vp(valid_ptr), nrec, dim,
-                                              C.byref(h)))
+        check(ctx._lib.dvs_kfreqs_from_device(ctx.handle, _vp(rows_ptr), _vp(ent_ptr) if ent_ptr else None,
+                                              _vp(valid_ptr) if valid_ptr else None, nrec, dim, C.byref(h)))
         return cls(ctx, h)
+
+    def take_rows(self, rows) -> "KFreqs":
+        """device gather of the given rows into a new KFreqs (the records of a selection result)"""
+        rows = np.ascontiguousarray(rows, dtype=np.uint32)
+        h = _vp()
+        check(self.ctx._lib.dvs_kfreqs_take_rows(self.ctx.handle, self.handle, ptr(rows) if rows.size else None,
+                                                 rows.size, C.byref(h)))
+        return KFreqs(self.ctx, h)
 
     def device_ptrs(self) -> tuple[int, int, int]:
         a, b, c = _vp(), _vp(), _vp()

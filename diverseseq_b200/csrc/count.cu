@@ -135,15 +135,15 @@ __device__ __forceinline__ uint32_t pack16p(uint4 v) {
 // `idx` at slot `idx ^ (idx >> 5)` (a bijection) folds the next 2.5 bases into the bank bits.
 __device__ __forceinline__ uint32_t scr_word(uint32_t idx) { return idx ^ (idx >> 5); }
 
-template <int MODE, bool SCR>
-__global__ void __launch_bounds__(kCountThreads)
+template <int MODE, bool SCR, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 k_count(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offsets, const CountWork* __restrict__ work,
         uint32_t nwork, uint32_t* __restrict__ next_item, int k, uint64_t dim, uint32_t part_bins,
         uint32_t* __restrict__ counts) {
     extern __shared__ uint32_t hist[];
     __shared__ uint32_t s_item;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int kWarps = kCountThreads / 32;
+    constexpr int kWarps = THREADS / 32;
     constexpr uint32_t kFull = 0xffffffffu;
     const int kk = (MODE == MODE_SUPER) ? k + 1 : k;                       // bases per histogrammed word
     const uint32_t mask = (kk >= 16) ? 0xFFFFFFFFu : ((1u << (2 * kk)) - 1u);
@@ -163,7 +163,7 @@ k_count(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offsets, 
         const uint32_t part_base = (MODE == MODE_SMEM_PARTS) ? w.part * part_bins : 0u;
         uint32_t* grow = counts + (size_t)w.rec * dim;
         if (MODE != MODE_GLOBAL) {
-            for (uint32_t i = tid; i < hist_words; i += kCountThreads) hist[i] = 0;
+            for (uint32_t i = tid; i < hist_words; i += THREADS) hist[i] = 0;
             __syncthreads();
         }
         // idx4 = 4 * bin: one k-mer (MODE 0/1/2) or one (k+1)-mer (MODE 3)
@@ -279,7 +279,7 @@ k_count(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offsets, 
         if (MODE != MODE_GLOBAL) {
             __syncthreads();
             if (MODE == MODE_SUPER) {
-                for (uint32_t x = tid; x < (uint32_t)dim; x += kCountThreads) {
+                for (uint32_t x = tid; x < (uint32_t)dim; x += THREADS) {
                     uint32_t c = side[x];
 #pragma unroll
                     for (uint32_t b = 0; b < 4; ++b) {  // x is the prefix k-mer
@@ -294,7 +294,7 @@ k_count(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offsets, 
                     if (c) atomicAdd(&grow[x], c);
                 }
             } else {
-                for (uint32_t i = tid; i < part_bins; i += kCountThreads) {
+                for (uint32_t i = tid; i < part_bins; i += THREADS) {
                     uint32_t c = hist[SCR ? scr_word(i) : i];
                     if (c && (uint64_t)part_base + i < dim) atomicAdd(&grow[part_base + i], c);
                 }
@@ -358,6 +358,23 @@ k_rows_entropy(const double* __restrict__ freqs, uint64_t dim, double* __restric
         bool bad = entropy_total_bad(h.t, dim);
         err[r] = bad ? 1 : 0;
         err_total[r] = h.t;
+    }
+}
+
+// device gather of whole rows (+ their scalars): one CTA per output row
+__global__ void k_take_rows(const double* __restrict__ F, const double* __restrict__ H, const uint8_t* __restrict__ V,
+                            const uint8_t* __restrict__ E, const double* __restrict__ ET, uint64_t dim,
+                            const uint32_t* __restrict__ rows, double* __restrict__ Fo, double* __restrict__ Ho,
+                            uint8_t* __restrict__ Vo, uint8_t* __restrict__ Eo, double* __restrict__ ETo) {
+    const uint32_t i = blockIdx.x, r = rows[i];
+    const double* src = F + (size_t)r * dim;
+    double* dst = Fo + (size_t)i * dim;
+    for (uint64_t c = threadIdx.x; c < dim; c += blockDim.x) dst[c] = src[c];
+    if (threadIdx.x == 0) {
+        Ho[i] = H[r];
+        Vo[i] = V[r];
+        Eo[i] = E[r];
+        ETo[i] = ET[r];
     }
 }
 
@@ -486,12 +503,16 @@ int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dv
     int ctas_per_sm = 4;
     if (smem) ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (ctx->smem_optin + 1024) / (hist_bytes + 1024)));
     const uint32_t grid = (uint32_t)(ctx->sm_count * ctas_per_sm);
+    const int threads4 = (mode == MODE_SMEM_PARTS) ? 1024 : kCountThreads;
     uint64_t chunk = 1 << 20;
     {
-        // aim for >= 8 items per CTA, chunks between 64 KB and 1 MB, multiples of the 8 KB stripe
+        // aim for >= 8 items per CTA, multiples of the 8 KB stripe.  Every item pays a zero + flush of its
+        // table, so big tables (k >= 7) take up to 2-8 MB per item, small ones 64 KB .. 1 MB
+        const uint64_t flush_bins = (mode == MODE_SUPER) ? dim : part_bins;  // global atomics per item
+        const uint64_t max_chunk = flush_bins >= 32768 ? (8u << 20) : (flush_bins >= 16384 ? (2u << 20) : (1u << 20));
         uint64_t want_items = (uint64_t)grid * 8;
         uint64_t c = (s->total + want_items - 1) / std::max<uint64_t>(want_items, 1);
-        c = std::max<uint64_t>(64 << 10, std::min<uint64_t>(c, 1 << 20));
+        c = std::max<uint64_t>(64 << 10, std::min<uint64_t>(c, max_chunk));
         chunk = (c + 8191) / 8192 * 8192;
     }
     std::vector<CountWork> work;
@@ -517,8 +538,8 @@ int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dv
         auto launch4 = [&](auto kern) -> cudaError_t {
             cudaError_t e = set_smem(kern);
             if (e != cudaSuccess) return e;
-            kern<<<g, kCountThreads, hist_bytes, st>>>(s->data(), s->offsets.p, d_work.p, (uint32_t)work.size(),
-                                                       d_next.p, k, dim, part_bins, f->counts.p);
+            kern<<<g, threads4, hist_bytes, st>>>(s->data(), s->offsets.p, d_work.p, (uint32_t)work.size(),
+                                                  d_next.p, k, dim, part_bins, f->counts.p);
             ctx->launches++;
             return cudaGetLastError();
         };
@@ -536,13 +557,13 @@ int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dv
         if (!ns4)
             e = smem ? launch_generic(k_count_generic<true>) : launch_generic(k_count_generic<false>);
         else if (mode == MODE_SUPER)
-            e = scramble ? launch4(k_count<MODE_SUPER, true>) : launch4(k_count<MODE_SUPER, false>);
+            e = scramble ? launch4(k_count<MODE_SUPER, true, 512>) : launch4(k_count<MODE_SUPER, false, 512>);
         else if (mode == MODE_SMEM)
-            e = scramble ? launch4(k_count<MODE_SMEM, true>) : launch4(k_count<MODE_SMEM, false>);
-        else if (mode == MODE_SMEM_PARTS)
-            e = scramble ? launch4(k_count<MODE_SMEM_PARTS, true>) : launch4(k_count<MODE_SMEM_PARTS, false>);
+            e = scramble ? launch4(k_count<MODE_SMEM, true, 512>) : launch4(k_count<MODE_SMEM, false, 512>);
+        else if (mode == MODE_SMEM_PARTS)  // one 128 KB CTA per SM: 1024 threads keep 32 warps resident
+            e = scramble ? launch4(k_count<MODE_SMEM_PARTS, true, 1024>) : launch4(k_count<MODE_SMEM_PARTS, false, 1024>);
         else
-            e = launch4(k_count<MODE_GLOBAL, false>);
+            e = launch4(k_count<MODE_GLOBAL, false, 512>);
         pt.stop();
         if (e != cudaSuccess) {
             set_error("k_count launch failed: %s", cudaGetErrorString(e));
@@ -606,7 +627,7 @@ int dvs_kfreqs_device_ptrs(const dvs_kfreqs* f, void** freqs, void** entropies, 
 
 int dvs_kfreqs_from_device(dvs_ctx* ctx, const void* d_rows, const void* d_entropies, const void* d_valid,
                            uint32_t nrec, uint64_t dim, dvs_kfreqs** out) {
-    if (!ctx || !d_rows || !d_entropies || !d_valid || !out || dim == 0) {
+    if (!ctx || !d_rows || !out || dim == 0) {
         set_error("dvs_kfreqs_from_device: bad argument");
         return DVS_ERR_ARG;
     }
@@ -616,11 +637,20 @@ int dvs_kfreqs_from_device(dvs_ctx* ctx, const void* d_rows, const void* d_entro
     cudaError_t e = cudaSuccess;
     if (nrec) {
         e = cudaMemcpyAsync(f->freqs.p, d_rows, (size_t)nrec * dim * sizeof(double), cudaMemcpyDeviceToDevice, st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(f->entropy.p, d_entropies, nrec * sizeof(double), cudaMemcpyDeviceToDevice, st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(f->valid.p, d_valid, nrec, cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess && d_entropies)
+            e = cudaMemcpyAsync(f->entropy.p, d_entropies, nrec * sizeof(double), cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess)
+            e = d_valid ? cudaMemcpyAsync(f->valid.p, d_valid, nrec, cudaMemcpyDeviceToDevice, st)
+                        : cudaMemsetAsync(f->valid.p, 1, nrec, st);
         if (e == cudaSuccess) e = cudaMemsetAsync(f->err.p, 0, nrec, st);
         if (e == cudaSuccess) e = cudaMemsetAsync(f->err_total.p, 0, nrec * sizeof(double), st);
         if (e == cudaSuccess) e = cudaMemsetAsync(f->totals.p, 0, nrec * sizeof(uint64_t), st);
+        if (e == cudaSuccess && !d_entropies) {
+            k_rows_entropy<<<nrec, kEntThreads, kEntSmemBytes, st>>>(f->freqs.p, dim, f->entropy.p, f->err.p,
+                                                                     f->err_total.p, 1);
+            ctx->launches++;
+            e = cudaGetLastError();
+        }
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     }
     if (e != cudaSuccess) {
@@ -629,6 +659,47 @@ int dvs_kfreqs_from_device(dvs_ctx* ctx, const void* d_rows, const void* d_entro
         return DVS_ERR_CUDA;
     }
     *out = f;
+    return DVS_OK;
+}
+
+int dvs_kfreqs_take_rows(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* rows, uint32_t n, dvs_kfreqs** out) {
+    if (!ctx || !f || !out || (!rows && n)) {
+        set_error("dvs_kfreqs_take_rows: bad argument");
+        return DVS_ERR_ARG;
+    }
+    for (uint32_t i = 0; i < n; ++i)
+        if (rows[i] >= f->nrec) {
+            set_error("dvs_kfreqs_take_rows: row %u out of range", rows[i]);
+            return DVS_ERR_ARG;
+        }
+    dvs_kfreqs* g = nullptr;
+    DVS_TRY(kfreqs_alloc(ctx, n, f->dim, false, &g));
+    g->k = f->k;
+    g->num_states = f->num_states;
+    cudaStream_t st = ctx->stream;
+    cudaError_t e = cudaSuccess;
+    DevBuf<uint32_t> d_rows;
+    if (n) {
+        if (d_rows.alloc(n) != DVS_OK) {
+            dvs_kfreqs_free(g);
+            return DVS_ERR_CUDA;
+        }
+        e = cudaMemcpyAsync(d_rows.p, rows, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) {
+            k_take_rows<<<n, 256, 0, st>>>(f->freqs.p, f->entropy.p, f->valid.p, f->err.p, f->err_total.p, f->dim,
+                                           d_rows.p, g->freqs.p, g->entropy.p, g->valid.p, g->err.p, g->err_total.p);
+            ctx->launches++;
+            e = cudaGetLastError();
+        }
+    }
+    if (e == cudaSuccess) e = cudaMemsetAsync(g->totals.p, 0, (size_t)std::max<uint32_t>(n, 1) * sizeof(uint64_t), st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        set_error("dvs_kfreqs_take_rows failed: %s", cudaGetErrorString(e));
+        dvs_kfreqs_free(g);
+        return DVS_ERR_CUDA;
+    }
+    *out = g;
     return DVS_OK;
 }
 

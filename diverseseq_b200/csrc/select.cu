@@ -41,6 +41,9 @@ struct SelScal {
     unsigned first_unsure;   // scan result: first position the fast scan could not decide
     unsigned state_unsure;   // fast update could not certify lowest_index / the sum checks
     unsigned exact;          // 1 when total_jsd / mdelta / lowest come from the exact kernel
+    unsigned pad0_;
+    double std_bound;        // fast path: |stdv - reference std_delta_jsd| <= std_bound  (0 when exact)
+    double cov_bound;        // fast path: same for cov (infinite when the mean is too close to 0)
     // ---- device-driven rounds (k_sel_scan_dev / k_sel_round_dev) ----
     unsigned cursor;         // next position to examine
     unsigned window;         // candidates scored per round
@@ -246,6 +249,8 @@ k_sel_update(const double* __restrict__ F, const double* __restrict__ H, uint64_
             sc->first_panic = kNone;
             sc->first_unsure = kNone;
             sc->total_bound = 0.0;
+            sc->std_bound = 0.0;
+            sc->cov_bound = 0.0;
             sc->state_unsure = 0;
             sc->exact = 1;
         }
@@ -420,6 +425,78 @@ __device__ __forceinline__ unsigned finalize_fast_block(double* mdelta, const do
     return (unsigned)unsure;
 }
 
+// block-wide sum / max of one double per thread (all threads get the result)
+__device__ __forceinline__ double block_sum_fast(double v) {
+    __shared__ double s_red[kFastThreads / 32];
+    __shared__ double s_out;
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (unsigned w = 0; w < blockDim.x / 32; ++w) t += s_red[w];
+        s_out = t;
+    }
+    __syncthreads();
+    const double r = s_out;
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ double block_max_fast(double v) {
+    __shared__ double s_red[kFastThreads / 32];
+    __shared__ double s_out;
+    for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = s_red[0];
+        for (unsigned w = 1; w < blockDim.x / 32; ++w) t = fmax(t, s_red[w]);
+        s_out = t;
+    }
+    __syncthreads();
+    const double r = s_out;
+    __syncthreads();
+    return r;
+}
+
+// mean / std / cov of the (approximate) member deltas with rigorous distance bounds to the values
+// the reference computes (src/records.rs:153-172).  delta_j is within mbound_j (+ the common
+// total_bound, which cancels in the deviations) of the reference's; std is 1-Lipschitz in the
+// deviations scaled by 1/sqrt(n-1), the sequential sums add <= (n+8) u relative error.
+__device__ __forceinline__ void stats_fast_block(const double* mdelta, const double* mbound, unsigned n,
+                                                 double total_bound, SelScal* sc) {
+    double sd = 0.0, bmx = 0.0, amx = 0.0;
+    for (unsigned t = threadIdx.x; t < n; t += blockDim.x) {
+        const double d = mdelta[t];
+        sd += d;
+        bmx = fmax(bmx, __ldcg(&mbound[t]));
+        amx = fmax(amx, fabs(d));
+    }
+    const double nd = (double)n;
+    const double mean = block_sum_fast(sd) / nd;
+    bmx = block_max_fast(bmx);
+    amx = block_max_fast(amx);
+    double ss = 0.0;
+    for (unsigned t = threadIdx.x; t < n; t += blockDim.x) {
+        const double d = mdelta[t] - mean;
+        ss += d * d;
+    }
+    const double sdev = sqrt(block_sum_fast(ss) / (nd - 1.0));
+    if (threadIdx.x == 0) {
+        const double u = 1.2e-16, scale = amx + fabs(mean);
+        const double b_mean = bmx + total_bound + (nd + 8.0) * u * scale;
+        const double b_std = 1.5 * (bmx + 4.0 * u * scale) + (nd + 8.0) * u * sdev;
+        const double cov = sdev / mean;
+        double b_cov = 1e300;
+        if (fabs(mean) > 2.0 * b_mean) b_cov = (b_std + fabs(cov) * b_mean) / (fabs(mean) - b_mean) + 8.0 * u * fabs(cov);
+        sc->mean = mean;
+        sc->stdv = sdev;
+        sc->cov = cov;
+        sc->std_bound = b_std;
+        sc->cov_bound = b_cov;
+    }
+}
+
 // fast increases_jsd of the candidate at position `pos`; first_true / first_unsure by atomicMin
 __device__ __forceinline__ void scan_fast_body(const double* __restrict__ F, const double* __restrict__ H, uint64_t dim,
                                                const double* __restrict__ S, const unsigned* __restrict__ members,
@@ -515,6 +592,7 @@ k_sel_update_fast(const double* __restrict__ F, const double* __restrict__ H, ui
         const double total = __ldcg(&sc->total_jsd), tb = __ldcg(&sc->total_bound);
         unsigned low = 0;
         const unsigned unsure = finalize_fast_block(mdelta, mbound, n, total, tb, &low);
+        stats_fast_block(mdelta, mbound, n, tb, sc);
         if (threadIdx.x == 0) {
             sc->lowest = low;
             if (unsure) atomicExch(&sc->state_unsure, 1u);
@@ -589,6 +667,7 @@ __device__ __forceinline__ void replace_update_fast_body(
         const double total = __ldcg(&sc->total_jsd), tb = __ldcg(&sc->total_bound);
         unsigned lo2 = 0;
         const unsigned unsure = finalize_fast_block(mdelta, mbound, n, total, tb, &lo2);
+        if (dev_pos == kNone) stats_fast_block(mdelta, mbound, n, tb, sc);  // only max-mode callers read them
         if (threadIdx.x == 0) {
             is_member[low_row] = 0;
             is_member[cand_row] = 1;
@@ -733,6 +812,13 @@ struct Selector {
                                               s.members(), s.sc.p);
         DVS_LAUNCHED(ctx);
         return update(s, n + (extra_row >= 0 ? 1u : 0u));
+    }
+    // fast SummedRecords::new (+ optional pushed row): exact sums, bounded-error total / deltas / stats
+    int build_fast(SelState& s, const unsigned* d_members, unsigned n, int extra_row) {
+        k_sel_sum<<<vec_grid(), 256, 0, st>>>(f->freqs.p, f->entropy.p, dim, d_members, n, extra_row, s.S(),
+                                              s.members(), s.sc.p);
+        DVS_LAUNCHED(ctx);
+        return update_fast(s, n + (extra_row >= 0 ? 1u : 0u));
     }
     int update(SelState& s, unsigned n) {
         k_sel_update<<<n + 1, kEntThreads, kEntSmemBytes, st>>>(f->freqs.p, f->entropy.p, dim, s.S(), s.members(),
@@ -955,7 +1041,36 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
             continue;
         }
         // records.rs:434-451: nw = clone(); nw.push(rec); keep whichever has the larger statistic.
-        // The statistics are compared exactly, so both states are evaluated by the exact kernel.
+        // First try with the bounded-error kernels: the comparison is decided from them only when it
+        // holds for every admissible error; otherwise both states are evaluated by the exact kernel.
+        const bool use_cov = (mode == DVS_MODE_MAX_COV);
+        int decided = -1;  // -1 undecided, 0 discard candidate, 1 adopt the grown set
+        if (use_fast && !h.state_unsure) {
+            DVS_TRY(sel.build_fast(*alt, cur->members(), n, (int)row));
+            DVS_TRY(sel.read(*alt));
+            const SelScal hf = *sel.h_sc;
+            if (hf.panic) return panic_error(hf);
+            if (!hf.state_unsure) {
+                const double sa_f = use_cov ? h.cov : h.stdv, ba = h.exact ? 0.0 : (use_cov ? h.cov_bound : h.std_bound);
+                const double sb_f = use_cov ? hf.cov : hf.stdv, bb = use_cov ? hf.cov_bound : hf.std_bound;
+                if (sb_f - bb > sa_f + ba) decided = 1;
+                else if (sb_f + bb < sa_f - ba) decided = 0;
+            }
+        }
+        if (decided == 1) {
+            std::swap(cur, alt);
+            ++n;
+            ++accepts;
+            uint8_t one = 1;
+            DVS_CUDA_TRY(cudaMemcpyAsync(is_member.p + row, &one, 1, cudaMemcpyHostToDevice, st));
+            DVS_CUDA_TRY(cudaStreamSynchronize(st));
+            continue;
+        }
+        if (decided == 0) {
+            DVS_TRY(sel.reset_scan(*cur));
+            continue;
+        }
+        if (use_fast) ++exact_evals;
         if (!h.exact) {
             DVS_TRY(sel.update(*cur, n));
             DVS_TRY(sel.read(*cur));
@@ -966,8 +1081,8 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
         DVS_TRY(sel.read(*alt));
         const SelScal hb = *sel.h_sc;
         if (hb.panic) return panic_error(hb);
-        const double sa = (mode == DVS_MODE_MAX_COV) ? h.cov : h.stdv;
-        const double sb = (mode == DVS_MODE_MAX_COV) ? hb.cov : hb.stdv;
+        const double sa = use_cov ? h.cov : h.stdv;
+        const double sb = use_cov ? hb.cov : hb.stdv;
         if (sb > sa) {
             std::swap(cur, alt);
             ++n;

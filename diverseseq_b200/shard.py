@@ -2,9 +2,14 @@
 for the plumbing (NCCL on GPUs, gloo in the CPU tests).
 
 * counting / sketching: records are independent -> each rank counts its own shard, no collective.
-* nmost / max: the selection state is tiny and every decision is order dependent, so the per-rank
-  frequency rows (N x 4^k f64) are all-gathered once and every rank replays the same selection on
-  the full row set (replicated state, identical results on every rank, no per-step exchange).
+* nmost / max, two modes:
+  - "chunked" (default; the reference's own `-np N` semantics, diverse_seq/records.py:206-251): every
+    rank selects from its own records, the N x n winning rows are all-gathered (n x 4^k f64 per rank)
+    and merged with final_nmost / final_max (src/records.rs:363-382,456-507) - per-GPU work is
+    constant, i.e. true weak scaling;
+  - "union": the per-rank frequency rows (N x 4^k f64) are all-gathered once and every rank replays
+    the single-pass selection on the full row set (numprocs=1 semantics over all records; replicated
+    state, identical results on every rank, no per-step exchange).
 * distance matrices: rows of the symmetric matrix are block-partitioned; each rank computes its
   row block against all columns and the blocks are all-gathered for the (CPU) clustering.
 
@@ -96,3 +101,36 @@ def all_gather_kfreqs(ctx, kf, device, group=None):
     torch.cuda.synchronize(device)
     return _lib.KFreqs.from_device(ctx, g_rows.data_ptr(), g_ent.data_ptr(), g_valid.data_ptr(),
                                    g_rows.shape[0], g_rows.shape[1])
+
+
+def chunked_select(ctx, kf, local_order, mode: int, min_size: int, max_size: int, device, group=None):
+    """The reference's multi-process selection with one chunk per GPU: select locally, all-gather the
+    winners' rows, merge with final_nmost / final_max on every rank (identical results everywhere).
+
+    Returns (global ids, delta_jsd, stats5); a global id is rank * kf.nrec + local row."""
+    import torch
+    import torch.distributed as dist
+
+    from . import _lib
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    idx, _delta, _stats = kf.select(local_order, mode, min_size, max_size)
+    cap = max(int(min_size), int(max_size))
+    won = kf.take_rows(idx)
+    rows, _ent, _valid = kfreqs_as_tensors(won, device)
+    pad = torch.zeros((cap, kf.dim), dtype=torch.float64, device=device)
+    pad[: rows.shape[0]] = rows
+    ids = torch.full((cap,), -1, dtype=torch.int64, device=device)
+    ids[: len(idx)] = torch.from_numpy(idx.astype(np.int64) + rank * kf.nrec).to(device)
+    ctx.sync()
+    g_rows = all_gather_concat(pad, group)
+    g_ids = all_gather_concat(ids, group)
+    torch.cuda.synchronize(device)
+    keep = torch.nonzero(g_ids >= 0).flatten()
+    g_rows = g_rows[keep].contiguous()
+    g_ids = g_ids[keep].cpu().numpy()
+    # final_*: entropies recomputed from the stored rows (KmerSeq::new), examined in concatenation order
+    merged = _lib.KFreqs.from_device(ctx, g_rows.data_ptr(), None, None, g_rows.shape[0], g_rows.shape[1])
+    order = np.arange(g_rows.shape[0], dtype=np.uint32)
+    midx, mdelta, mstats = merged.select(order, mode, min_size, max_size)
+    return g_ids[midx], mdelta, mstats

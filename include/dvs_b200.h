@@ -103,8 +103,12 @@ int dvs_kfreqs_from_rows(dvs_ctx* ctx, const double* rows, const double* entropi
 /* multi-GPU plumbing: raw DEVICE pointers of the row matrix [nrec][dim] f64, the
  * entropies [nrec] f64 and the validity flags [nrec] u8, so a collective library (NCCL) can
  * all-gather shards; and the inverse, a kfreqs built by device-to-device copy from gathered
- * device buffers that live on ctx's GPU. */
+ * device buffers that live on ctx's GPU.  d_entropies == NULL recomputes every entropy from the
+ * rows exactly as KmerSeq::new does (src/records.rs:353), d_valid == NULL marks all rows valid. */
 int dvs_kfreqs_device_ptrs(const dvs_kfreqs* f, void** freqs, void** entropies, void** valid);
+/* a new kfreqs holding rows `rows[0..n)` of f (device gather; entropies / validity carried over):
+ * the records of a SummedRecordsResult, ready to be all-gathered for final_nmost / final_max */
+int dvs_kfreqs_take_rows(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* rows, uint32_t n, dvs_kfreqs** out);
 int dvs_kfreqs_from_device(dvs_ctx* ctx, const void* d_rows, const void* d_entropies, const void* d_valid,
                            uint32_t nrec, uint64_t dim, dvs_kfreqs** out);
 uint32_t dvs_kfreqs_nrec(const dvs_kfreqs* f);
