@@ -67,6 +67,7 @@ SIGNATURES = {
     "dvs_mash_distances": (_i32, [_vp, _vp, _i32, _u64, _u32, _u32, _vp, _vp, _vp]),
     "dvs_mash_sketch_host": (_i32, [_vp, _vp, _u64, _i32, _u64, _i32, _i32, _vp, _u64, C.POINTER(_u64)]),
     "dvs_euclid_distances": (_i32, [_vp, _vp, _u32, _u32, _vp]),
+    "dvs_debug_pack_host": (_i32, [_vp, _u64, _vp, _vp, _vp, _u32, C.POINTER(_u32)]),
     "dvs_debug_log2": (_i32, [_vp, _vp, _vp, _u64]),
     "dvs_debug_entropy": (_i32, [_vp, _vp, _u32, _u64, _vp, _vp]),
 }

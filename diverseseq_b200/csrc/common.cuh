@@ -101,6 +101,7 @@ struct dvs_ctx {
     uint64_t launches = 0;
     uint32_t last_accepts = 0;
     uint32_t last_exact_evals = 0;  // exact re-evaluations forced by the fast path's error bound
+    void* upload_stage = nullptr;  // pinned/device staging ring of the packed upload path (upload.cu)
     // pinned scratch for small device->host readbacks
     void* pinned = nullptr;
     size_t pinned_bytes = 0;

@@ -1,9 +1,13 @@
 // Context, error reporting and sequence-set residency for libdvs_b200.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
 
 namespace dvs {
+
+int upload_packed(dvs_ctx* ctx, const uint8_t* src, uint8_t* d_dst, size_t total);  // upload.cu
+void upload_stage_free(void* p);
 
 static thread_local std::string g_error;
 thread_local cudaStream_t tl_stream = nullptr;
@@ -78,6 +82,7 @@ void dvs_ctx_destroy(dvs_ctx* ctx) {
         cudaStreamDestroy(ctx->stream);
     }
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    upload_stage_free(ctx->upload_stage);
     for (int i = 0; i < kNumPhases; ++i) {
         if (ctx->ev_start[i]) cudaEventDestroy(ctx->ev_start[i]);
         if (ctx->ev_stop[i]) cudaEventDestroy(ctx->ev_stop[i]);
@@ -163,7 +168,17 @@ int dvs_seqset_upload(dvs_ctx* ctx, const uint8_t* seqs, const uint64_t* offsets
     dvs_seqset* s = nullptr;
     DVS_TRY(seqset_alloc(ctx, offsets, nrec, &s));
     PhaseTimer pt(ctx, DVS_PHASE_UPLOAD);
-    if (s->total) {
+    // large uploads go 2-bit packed over PCIe and are unpacked on the device (upload.cu);
+    // DVS_UPLOAD_PACKED=0 forces the plain copy, =1 forces packing for any size
+    const char* pk = getenv("DVS_UPLOAD_PACKED");
+    const bool packed = pk ? (pk[0] == '1') : (s->total >= (64ull << 20));
+    if (s->total && packed) {
+        int rc = upload_packed(ctx, seqs, s->data(), s->total);
+        if (rc != DVS_OK) {
+            delete s;
+            return rc;
+        }
+    } else if (s->total) {
         cudaError_t e = cudaMemcpyAsync(s->data(), seqs, s->total, cudaMemcpyHostToDevice, ctx->stream);
         if (e != cudaSuccess) {
             set_error("sequence upload failed: %s", cudaGetErrorString(e));

@@ -177,6 +177,11 @@ int dvs_mash_sketch_host(dvs_ctx* ctx, const uint8_t* seq, uint64_t len, int k, 
 int dvs_euclid_distances(dvs_ctx* ctx, const dvs_kfreqs* f, uint32_t row_begin, uint32_t row_end, double* dist);
 
 /* ---- test hooks ---------------------------------------------------------------------------- */
+/* host half of the packed upload (transfer encoding, no GPU needed): packs src[0..n) 4 bases per
+ * byte (b0 | b1<<2 | b2<<4 | b3<<6), bytes >= 4 become 0 and are listed as (position, value)
+ * exceptions; *nexc may exceed cap (overflow: the real path then ships the block unpacked) */
+int dvs_debug_pack_host(const uint8_t* src, uint64_t n, uint8_t* packed, uint32_t* exc_pos, uint8_t* exc_val,
+                        uint32_t cap, uint32_t* nexc);
 /* device evaluation of the glibc-log2 restatement on n doubles */
 int dvs_debug_log2(dvs_ctx* ctx, const double* x, double* y, uint64_t n);
 /* exact (reference-order) entropy of each host row on the device; err[r]=1 when the reference

@@ -105,3 +105,31 @@ def test_synth_host_is_deterministic_and_structured():
     lens = np.diff(oa.astype(np.int64))
     assert lens.min() >= 15000 and lens.max() <= 25000
     assert a.max() <= 4
+
+
+def test_host_pack_for_packed_upload():
+    """transfer encoding of the packed upload path (csrc/hostpack.cpp): 4 bases per byte + exceptions"""
+    import ctypes as C
+    from diverseseq_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(4)
+    for n in (0, 1, 3, 4, 5, 31, 32, 33, 1000, 100_003):
+        src = rng.integers(0, 4, size=n, dtype=np.uint8)
+        bad = rng.random(n) < 0.01
+        src[bad] = rng.integers(4, 256, size=int(bad.sum()), dtype=np.uint8)
+        packed = np.zeros(max((n + 3) // 4, 1), dtype=np.uint8)
+        pos = np.zeros(max(n, 1), dtype=np.uint32)
+        val = np.zeros(max(n, 1), dtype=np.uint8)
+        nexc = C.c_uint32(0)
+        lib.dvs_debug_pack_host(_lib.ptr(src) if n else None, n, _lib.ptr(packed), _lib.ptr(pos), _lib.ptr(val),
+                                pos.size, C.byref(nexc))
+        assert nexc.value == int(bad.sum())
+        clean = np.where(src > 3, 0, src)
+        pad = np.zeros((n + 3) // 4 * 4, dtype=np.uint8)
+        pad[:n] = clean
+        q = pad.reshape(-1, 4)
+        expect = (q[:, 0] | (q[:, 1] << 2) | (q[:, 2] << 4) | (q[:, 3] << 6)).astype(np.uint8)
+        assert np.array_equal(packed[: expect.size], expect)
+        order = np.argsort(pos[: nexc.value])
+        assert np.array_equal(pos[: nexc.value][order], np.nonzero(bad)[0].astype(np.uint32))
+        assert np.array_equal(val[: nexc.value][order], src[bad])

@@ -452,3 +452,25 @@ def test_dvs_on_disk_store_matches_in_memory(tmp_path, brca1, orc):
     ss, offsets = dvseqsz.load_seqset(ctx, ro, names, threads=4)
     assert np.array_equal(ss.download(), flat) and np.array_equal(offsets, off)
     assert ro.get_lazyseq("Human", 4).get_kcounts(2) == orc.kcounts(brca1["Human"], 2).tolist()
+
+
+def test_packed_upload_reconstructs_bytes_exactly(lib, ctx, monkeypatch):
+    """2-bit packed PCIe path (csrc/upload.cu): the device must end up with the caller's bytes, incl.
+    arbitrary bytes >= 4 (exceptions), a block with too many of them (raw fallback) and a ragged tail"""
+    rng = np.random.default_rng(12)
+    monkeypatch.setenv("DVS_UPLOAD_PACKED", "1")
+    n = (256 << 20) + (256 << 20) + 1_234_567  # three blocks, the last one short and odd sized
+    flat = rng.integers(0, 4, size=n, dtype=np.uint8)
+    bad = rng.integers(0, n, size=200_000)
+    flat[bad] = rng.integers(4, 256, size=bad.size, dtype=np.uint8)          # sparse exceptions everywhere
+    flat[(256 << 20) + 1000:(256 << 20) + 9_000_000] = 78                      # block 1: > 1/64 invalid -> raw
+    offsets = np.array([0, 5, 5, 1_000_003, (256 << 20) + 7, n], dtype=np.uint64)
+    ss = lib.SeqSet.upload(ctx, flat, offsets)
+    got = ss.download()
+    assert got.size == n and np.array_equal(got, flat)
+    small = rng.integers(0, 6, size=1001, dtype=np.uint8)
+    s2 = lib.SeqSet.upload(ctx, small, np.array([0, 1001], dtype=np.uint64))
+    assert np.array_equal(s2.download(), small)
+    monkeypatch.setenv("DVS_UPLOAD_PACKED", "0")
+    s3 = lib.SeqSet.upload(ctx, small, np.array([0, 1001], dtype=np.uint64))
+    assert np.array_equal(s3.download(), small)
