@@ -359,7 +359,10 @@ def main():
             e2e = {"value": total_bases / (ms_e2e * 1e-3) / 1e9, "unit": UNIT,
                    "h2d_bytes_per_step": int(bases + offsets.nbytes + order.nbytes), "d2h_bytes_per_step": int(d2h),
                    "ms_per_step": ms_e2e, "upload_ms": ctx.phase_ms(_lib.PHASE_UPLOAD),
-                   "note": "pinned host buffer -> cudaMemcpyAsync -> count -> nmost -> read back indices/deltas"}
+                   "h2d_wire_bytes_per_step": ctx.last_upload_wire_bytes,
+                   "note": "pinned host buffer (1 byte/base, the reference layout) -> dvs_seqset_upload (host threads "
+                           "pack 2 bits/base, PCIe, device unpack to the same bytes) -> count -> nmost -> read back "
+                           "indices/deltas; h2d_bytes_per_step counts the host bytes handed to the API"}
         except Exception as exc:  # e.g. not enough host memory to pin the whole input
             e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                    "error": f"{type(exc).__name__}: {exc}"}

@@ -30,6 +30,7 @@ SIGNATURES = {
     "dvs_ctx_sync": (_i32, [_vp]),
     "dvs_ctx_stream": (_vp, [_vp]),
     "dvs_ctx_launch_count": (_u64, [_vp]),
+    "dvs_ctx_last_upload_wire_bytes": (_u64, [_vp]),
     "dvs_ctx_enable_timing": (_i32, [_vp, _i32]),
     "dvs_ctx_phase_ms": (_f64, [_vp, _i32]),
     "dvs_seqset_upload": (_i32, [_vp, _vp, _vp, _u32, C.POINTER(_vp)]),
@@ -153,6 +154,10 @@ class Context:
     @property
     def stream(self) -> int:
         return int(self._lib.dvs_ctx_stream(self.handle) or 0)
+
+    @property
+    def last_upload_wire_bytes(self) -> int:
+        return int(self._lib.dvs_ctx_last_upload_wire_bytes(self.handle))
 
     @property
     def launch_count(self) -> int:

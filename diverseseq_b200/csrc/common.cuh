@@ -101,6 +101,7 @@ struct dvs_ctx {
     uint64_t launches = 0;
     uint32_t last_accepts = 0;
     uint32_t last_exact_evals = 0;  // exact re-evaluations forced by the fast path's error bound
+    uint64_t last_upload_wire_bytes = 0;
     void* upload_stage = nullptr;  // pinned/device staging ring of the packed upload path (upload.cu)
     // pinned scratch for small device->host readbacks
     void* pinned = nullptr;

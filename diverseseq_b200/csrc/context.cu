@@ -95,6 +95,8 @@ int dvs_ctx_sync(dvs_ctx* ctx) {
     return DVS_OK;
 }
 
+uint64_t dvs_ctx_last_upload_wire_bytes(dvs_ctx* ctx) { return ctx->last_upload_wire_bytes; }
+
 int dvs_ctx_enable_timing(dvs_ctx* ctx, int on) {
     DVS_CUDA_TRY(cudaSetDevice(ctx->device));
     if (on && !ctx->ev_start[0])
@@ -172,7 +174,9 @@ int dvs_seqset_upload(dvs_ctx* ctx, const uint8_t* seqs, const uint64_t* offsets
     // DVS_UPLOAD_PACKED=0 forces the plain copy, =1 forces packing for any size
     const char* pk = getenv("DVS_UPLOAD_PACKED");
     const bool packed = pk ? (pk[0] == '1') : (s->total >= (64ull << 20));
+    ctx->last_upload_wire_bytes = s->total;
     if (s->total && packed) {
+        ctx->last_upload_wire_bytes = 0;  // accumulated by upload_packed
         int rc = upload_packed(ctx, seqs, s->data(), s->total);
         if (rc != DVS_OK) {
             delete s;

@@ -58,27 +58,25 @@ static inline void pack_scalar(const uint8_t* src, size_t n, uint8_t* dst, uint3
 
 __attribute__((target("avx2"))) static void pack_avx2(const uint8_t* src, size_t n, uint8_t* dst, uint32_t rel0,
                                                       PackExc& ex) {
-    const __m256i three = _mm256_set1_epi8(3);
+    const __m256i hi6 = _mm256_set1_epi8((char)0xFC);
     const __m256i w1 = _mm256_set1_epi16(0x0401);      // byte pairs: b_even*1 + b_odd*4
     const __m256i w2 = _mm256_set1_epi32(0x00100001);  // 16-bit pairs: t_even*1 + t_odd*16
-    const __m256i pick = _mm256_setr_epi8(0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,  //
-                                          0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
+    const __m256i order = _mm256_setr_epi32(0, 4, 1, 5, 2, 6, 3, 7);
     size_t q = 0;
-    for (; q + 32 <= n; q += 32) {
-        __m256i v = _mm256_loadu_si256((const __m256i*)(src + q));
-        const __m256i ok = _mm256_cmpeq_epi8(_mm256_min_epu8(v, three), v);
-        const uint32_t bad = ~(uint32_t)_mm256_movemask_epi8(ok);
-        if (bad) {
-            pack_scalar(src + q, 32, dst + (q >> 2), rel0 + (uint32_t)q, ex);
+    for (; q + 64 <= n; q += 64) {
+        _mm_prefetch((const char*)(src + q + 1024), _MM_HINT_T0);
+        const __m256i v0 = _mm256_loadu_si256((const __m256i*)(src + q));
+        const __m256i v1 = _mm256_loadu_si256((const __m256i*)(src + q + 32));
+        if (!_mm256_testz_si256(_mm256_or_si256(v0, v1), hi6)) {  // some byte > 3: exceptions
+            pack_scalar(src + q, 64, dst + (q >> 2), rel0 + (uint32_t)q, ex);
             continue;
         }
-        const __m256i t = _mm256_maddubs_epi16(v, w1);
-        const __m256i u = _mm256_madd_epi16(t, w2);
-        const __m256i p = _mm256_shuffle_epi8(u, pick);
-        const uint32_t lo = (uint32_t)_mm256_cvtsi256_si32(p);
-        const uint32_t hi = (uint32_t)_mm256_extract_epi32(p, 4);
-        *(uint32_t*)(dst + (q >> 2)) = lo;
-        *(uint32_t*)(dst + (q >> 2) + 4) = hi;
+        const __m256i u0 = _mm256_madd_epi16(_mm256_maddubs_epi16(v0, w1), w2);  // 8 dwords, one packed byte each
+        const __m256i u1 = _mm256_madd_epi16(_mm256_maddubs_epi16(v1, w1), w2);
+        const __m256i p16 = _mm256_packus_epi32(u0, u1);   // lane0: u0 d0-3, u1 d0-3 | lane1: u0 d4-7, u1 d4-7
+        const __m256i p8 = _mm256_packus_epi16(p16, p16);  // low 8 bytes of each lane carry the data
+        const __m256i r = _mm256_permutevar8x32_epi32(p8, order);  // dwords: u0 d0-3, u0 d4-7, u1 d0-3, u1 d4-7
+        _mm_storeu_si128((__m128i*)(dst + (q >> 2)), _mm256_castsi256_si128(r));
     }
     if (q < n) pack_scalar(src + q, n - q, dst + (q >> 2), rel0 + (uint32_t)q, ex);
 }

@@ -12,6 +12,8 @@
 // calling thread ships every completed block (cudaMemcpyAsync of packed bytes + exceptions,
 // k_unpack, k_patch) and releases its ring slot with an event.  Blocks whose exception list
 // overflows (>= 1/64 invalid) are sent raw instead.
+#include <stdlib.h>
+
 #include <atomic>
 #include <chrono>
 #include <thread>
@@ -77,7 +79,7 @@ static int stage_init(dvs_ctx* ctx, UploadStage& st) {
     DVS_CUDA_TRY(cudaMalloc((void**)&st.d_packed, kUpRing * (kUpBlock / 4)));
     DVS_CUDA_TRY(cudaMalloc((void**)&st.d_pos, (size_t)kUpRing * kUpExcCap * sizeof(uint32_t)));
     DVS_CUDA_TRY(cudaMalloc((void**)&st.d_val, (size_t)kUpRing * kUpExcCap));
-    for (int i = 0; i < kUpRing; ++i) DVS_CUDA_TRY(cudaEventCreateWithFlags(&st.done[i], cudaEventDisableTiming));
+    for (int i = 0; i < kUpRing; ++i) DVS_CUDA_TRY(cudaEventCreateWithFlags(&st.done[i], cudaEventDisableTiming | cudaEventBlockingSync));
     st.ready = true;
     (void)ctx;
     return DVS_OK;
@@ -135,7 +137,11 @@ int upload_packed(dvs_ctx* ctx, const uint8_t* src, uint8_t* d_dst, size_t total
             sub_done[b].fetch_add(1, std::memory_order_release);
         }
     };
+    // one process per GPU: share the host cores between the local ranks (torchrun exports
+    // LOCAL_WORLD_SIZE); DVS_HOST_THREADS overrides
     unsigned nthreads = std::max(1u, std::thread::hardware_concurrency());
+    if (const char* lws = getenv("LOCAL_WORLD_SIZE")) nthreads = std::max(1u, nthreads / (unsigned)std::max(1, atoi(lws)));
+    if (const char* ht = getenv("DVS_HOST_THREADS")) nthreads = (unsigned)std::max(1, atoi(ht));
     nthreads = (unsigned)std::min<size_t>(nthreads, std::max<size_t>(1, nsubs));
     std::vector<std::thread> pool;
     for (unsigned t = 0; t < nthreads; ++t) pool.emplace_back(worker);
@@ -145,14 +151,17 @@ int upload_packed(dvs_ctx* ctx, const uint8_t* src, uint8_t* d_dst, size_t total
         const size_t off = b * kUpBlock;
         const size_t n = std::min(kUpBlock, total - off);
         const uint32_t want = (uint32_t)((n + kUpSub - 1) / kUpSub);
-        while (sub_done[b].load(std::memory_order_acquire) < want) std::this_thread::yield();
+        while (sub_done[b].load(std::memory_order_acquire) < want)  // the workers own the cores: do not spin
+            std::this_thread::sleep_for(std::chrono::microseconds(50));
         const int slot = (int)(b % kUpRing);
         const uint32_t nexc = exc_count[b].load();
         cudaError_t e = cudaSuccess;
         if (nexc > kUpExcCap) {
             // too many bytes >= 4 in this block: ship it as it is
             e = cudaMemcpyAsync(d_dst + off, src + off, n, cudaMemcpyHostToDevice, stream);
+            ctx->last_upload_wire_bytes += n;
         } else {
+            ctx->last_upload_wire_bytes += (n + 3) / 4 + (uint64_t)nexc * 5;
             uint8_t* dp = st.d_packed + (size_t)slot * (kUpBlock / 4);
             e = cudaMemcpyAsync(dp, st.h_packed + (size_t)slot * (kUpBlock / 4), (n + 3) / 4, cudaMemcpyHostToDevice, stream);
             if (e == cudaSuccess) {

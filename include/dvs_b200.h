@@ -67,6 +67,9 @@ uint64_t dvs_ctx_launch_count(dvs_ctx* ctx);
 #define DVS_PHASE_MASH_PAIRS 4     /* k_mash_pairs */
 #define DVS_PHASE_EUCLID 5         /* k_euclid_tiles */
 #define DVS_PHASE_UPLOAD 6         /* host->device sequence copy of dvs_seqset_upload */
+/* bytes that actually crossed PCIe during the last dvs_seqset_upload (2-bit packed + exceptions for
+ * large uploads, see csrc/upload.cu; equal to the input size for the plain copy) */
+uint64_t dvs_ctx_last_upload_wire_bytes(dvs_ctx* ctx);
 int dvs_ctx_enable_timing(dvs_ctx* ctx, int on);
 double dvs_ctx_phase_ms(dvs_ctx* ctx, int phase);
 
