@@ -149,7 +149,8 @@ k_count(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offsets, 
     const uint32_t mask = (kk >= 16) ? 0xFFFFFFFFu : ((1u << (2 * kk)) - 1u);
     const uint32_t mask4 = mask << 2;                                       // same, as a byte offset
     const uint32_t mask_k = (k >= 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
-    const uint32_t hist_words = (MODE == MODE_SUPER) ? (uint32_t)(dim * 4 + dim) : part_bins;
+    const uint32_t hist_words = (MODE == MODE_SUPER) ? (uint32_t)(dim * 4 + dim)
+                                                     : (MODE == MODE_SMEM_PARTS ? part_bins + 1 : part_bins);
     uint32_t* side = hist + dim * 4;  // MODE_SUPER only: single k-mer histogram after the (k+1)-mer table
     char* const hist_b = reinterpret_cast<char*>(hist);
 
@@ -172,8 +173,12 @@ k_count(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offsets, 
                 if (SCR) idx4 ^= (idx4 >> 5) & ~3u;
                 atomicAdd(reinterpret_cast<uint32_t*>(hist_b + idx4), 1u);
             } else if (MODE == MODE_SMEM_PARTS) {
-                uint32_t local = (idx4 >> 2) - part_base;
-                if (local < part_bins) atomicAdd(&hist[SCR ? scr_word(local) : local], 1u);
+                // branch-free: bins of the other part wrap to huge offsets and are clamped onto one
+                // dummy word behind the table (same-address ATOMS are merged by the hardware)
+                uint32_t local4 = idx4 - (part_base << 2);
+                if (SCR) local4 ^= (local4 >> 5) & ~3u;  // (garbage for foreign bins, clamped next)
+                local4 = min(local4, part_bins << 2);
+                atomicAdd(reinterpret_cast<uint32_t*>(hist_b + local4), 1u);
             } else {
                 atomicAdd(&grow[idx4 >> 2], 1u);
             }
@@ -473,7 +478,7 @@ int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dv
 
     // ---- histogram placement ----
     const bool ns4 = (num_states == 4);
-    const size_t max_hist_bytes = std::min<size_t>(ctx->smem_optin > 4096 ? ctx->smem_optin - 2048 : 0, 128 * 1024);
+    const size_t max_hist_bytes = std::min<size_t>(ctx->smem_optin > 4096 ? ctx->smem_optin - 2048 : 0, 128 * 1024 + 16);
     uint32_t nparts = 1, part_bins = (uint32_t)std::min<uint64_t>(dim, 1u << 31);
     int mode = MODE_SMEM;
     size_t hist_bytes = (size_t)dim * 4;
@@ -487,7 +492,7 @@ int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dv
             mode = MODE_SMEM_PARTS;
             nparts = (uint32_t)np;
             part_bins = (uint32_t)((dim + np - 1) / np);
-            hist_bytes = (size_t)part_bins * 4;
+            hist_bytes = (size_t)part_bins * 4 + 16;  // + the dummy word that absorbs the other part's bins
         } else {
             mode = MODE_GLOBAL;
             hist_bytes = 0;

@@ -317,26 +317,29 @@ __device__ FastSum block_entropy_fast(uint64_t dim, Elem elem) {
     __shared__ int s_bad[kFastThreads / 32];
     double e0 = 0.0, e1 = 0.0, t0 = 0.0, t1 = 0.0, a0 = 0.0, a1 = 0.0;
     int bad = 0;
-    uint64_t i = threadIdx.x;
-    for (; i + kFastThreads < dim; i += 2 * kFastThreads) {
-        const double x0 = elem(i), x1 = elem(i + kFastThreads);
-        if (!(x0 == 0.0)) {
-            bad |= !(x0 > 0.0);
-            const double tm = __dmul_rn(-x0, log2(x0));
-            e0 += tm; a0 += fabs(tm); t0 += x0;
+    // 8 elements per thread per pass: all frequencies (global loads + divides) are formed before the
+    // first log2 so one memory latency is exposed per pass, not one per element
+    constexpr int kBatch = 8;
+    for (uint64_t base = 0; base < dim; base += (uint64_t)kBatch * kFastThreads) {
+        double x[kBatch];
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) {
+            const uint64_t i = base + threadIdx.x + (uint64_t)q * kFastThreads;
+            x[q] = i < dim ? elem(i) : 0.0;
         }
-        if (!(x1 == 0.0)) {
-            bad |= !(x1 > 0.0);
-            const double tm = __dmul_rn(-x1, log2(x1));
-            e1 += tm; a1 += fabs(tm); t1 += x1;
-        }
-    }
-    if (i < dim) {
-        const double x0 = elem(i);
-        if (!(x0 == 0.0)) {
-            bad |= !(x0 > 0.0);
-            const double tm = __dmul_rn(-x0, log2(x0));
-            e0 += tm; a0 += fabs(tm); t0 += x0;
+#pragma unroll
+        for (int q = 0; q < kBatch; q += 2) {
+            const double x0 = x[q], x1 = x[q + 1];
+            if (!(x0 == 0.0)) {
+                bad |= !(x0 > 0.0);
+                const double tm = __dmul_rn(-x0, log2(x0));
+                e0 += tm; a0 += fabs(tm); t0 += x0;
+            }
+            if (!(x1 == 0.0)) {
+                bad |= !(x1 > 0.0);
+                const double tm = __dmul_rn(-x1, log2(x1));
+                e1 += tm; a1 += fabs(tm); t1 += x1;
+            }
         }
     }
     double e = e0 + e1, t = t0 + t1, a = a0 + a1;

@@ -101,6 +101,10 @@ void upload_stage_free(void* p) {
 }
 
 // Copies src[0..total) to d_dst[0..total) through the packed pipeline on ctx->stream.
+//
+// Work is claimed from both ends of the block list: worker threads pack sub-chunks from the front;
+// whenever the stream has drained (PCIe idle because packing is the slower side) the calling thread
+// steals the LAST unclaimed block and ships it raw, so the link and the host cores finish together.
 int upload_packed(dvs_ctx* ctx, const uint8_t* src, uint8_t* d_dst, size_t total) {
     if (!ctx->upload_stage) ctx->upload_stage = new UploadStage();
     UploadStage& st = *(UploadStage*)ctx->upload_stage;
@@ -108,7 +112,6 @@ int upload_packed(dvs_ctx* ctx, const uint8_t* src, uint8_t* d_dst, size_t total
     cudaStream_t stream = ctx->stream;
     const size_t nblocks = (total + kUpBlock - 1) / kUpBlock;
     const size_t subs_per_block = kUpBlock / kUpSub;
-    const size_t nsubs = (total + kUpSub - 1) / kUpSub;
 
     std::vector<std::atomic<uint32_t>> sub_done(nblocks);
     std::vector<std::atomic<uint32_t>> exc_count(nblocks);
@@ -116,14 +119,23 @@ int upload_packed(dvs_ctx* ctx, const uint8_t* src, uint8_t* d_dst, size_t total
         sub_done[b].store(0);
         exc_count[b].store(0);
     }
-    std::atomic<size_t> next_sub{0};
-    std::atomic<size_t> released{(size_t)kUpRing};  // blocks [0, released) may be written by workers
+    // claim state (under claim_lock): sub-chunks [0, front_sub) belong to the packers, blocks
+    // [tail_block, nblocks) were stolen for raw transfer
+    std::atomic_flag claim_lock = ATOMIC_FLAG_INIT;
+    size_t front_sub = 0, tail_block = nblocks;
+    auto lock = [&] { while (claim_lock.test_and_set(std::memory_order_acquire)) std::this_thread::yield(); };
+    auto unlock = [&] { claim_lock.clear(std::memory_order_release); };
+    std::atomic<size_t> released{(size_t)kUpRing};  // packed blocks [0, released) may be written by workers
     std::atomic<bool> abort{false};
 
     auto worker = [&] {
         for (;;) {
-            const size_t sidx = next_sub.fetch_add(1);
-            if (sidx >= nsubs || abort.load()) return;
+            lock();
+            const size_t sidx = front_sub;
+            const bool have = sidx / subs_per_block < tail_block && sidx * kUpSub < total;
+            if (have) ++front_sub;
+            unlock();
+            if (!have || abort.load()) return;
             const size_t b = sidx / subs_per_block;
             while (b >= released.load(std::memory_order_acquire)) {  // ring slot still in flight
                 if (abort.load()) return;
@@ -142,24 +154,59 @@ int upload_packed(dvs_ctx* ctx, const uint8_t* src, uint8_t* d_dst, size_t total
     unsigned nthreads = std::max(1u, std::thread::hardware_concurrency());
     if (const char* lws = getenv("LOCAL_WORLD_SIZE")) nthreads = std::max(1u, nthreads / (unsigned)std::max(1, atoi(lws)));
     if (const char* ht = getenv("DVS_HOST_THREADS")) nthreads = (unsigned)std::max(1, atoi(ht));
-    nthreads = (unsigned)std::min<size_t>(nthreads, std::max<size_t>(1, nsubs));
+    nthreads = (unsigned)std::min<size_t>(nthreads, std::max<size_t>(1, (total + kUpSub - 1) / kUpSub));
+    // measured on the 16-core bench host: stealing moved 8 of 42 GB raw but the upload took the same
+    // 0.40 s - host DRAM bandwidth (packing reads at ~108 GB/s) is the shared bottleneck, so it is off
+    // by default; DVS_UPLOAD_STEAL=1 enables it for hosts with fewer cores per GPU
+    const char* steal_env = getenv("DVS_UPLOAD_STEAL");
+    const bool steal = steal_env && steal_env[0] == '1';
     std::vector<std::thread> pool;
     for (unsigned t = 0; t < nthreads; ++t) pool.emplace_back(worker);
 
     int rc = DVS_OK;
-    for (size_t b = 0; b < nblocks && rc == DVS_OK; ++b) {
+    auto fail = [&](cudaError_t e) {
+        set_error("packed upload failed: %s", cudaGetErrorString(e));
+        rc = DVS_ERR_CUDA;
+    };
+    auto send_raw = [&](size_t b) {
+        const size_t off = b * kUpBlock, n = std::min(kUpBlock, total - off);
+        cudaError_t e = cudaMemcpyAsync(d_dst + off, src + off, n, cudaMemcpyHostToDevice, stream);
+        ctx->last_upload_wire_bytes += n;
+        if (e != cudaSuccess) fail(e);
+    };
+    size_t b = 0;  // next packed block to ship
+    while (rc == DVS_OK) {
+        lock();
+        const size_t tail = tail_block;
+        unlock();
+        if (b >= tail) break;
         const size_t off = b * kUpBlock;
         const size_t n = std::min(kUpBlock, total - off);
         const uint32_t want = (uint32_t)((n + kUpSub - 1) / kUpSub);
-        while (sub_done[b].load(std::memory_order_acquire) < want)  // the workers own the cores: do not spin
-            std::this_thread::sleep_for(std::chrono::microseconds(50));
+        if (sub_done[b].load(std::memory_order_acquire) < want) {
+            // block b is still being packed.  If the link is idle, take a raw block from the far end.
+            bool stole = false;
+            if (steal && cudaStreamQuery(stream) == cudaSuccess) {
+                lock();
+                // only whole blocks no packer has touched: strictly beyond the block of front_sub
+                if (tail_block > b + 1 && tail_block - 1 > (front_sub == 0 ? 0 : (front_sub - 1) / subs_per_block)) {
+                    --tail_block;
+                    const size_t sb = tail_block;
+                    unlock();
+                    send_raw(sb);
+                    stole = true;
+                } else {
+                    unlock();
+                }
+            }
+            if (!stole) std::this_thread::sleep_for(std::chrono::microseconds(50));  // the workers own the cores
+            continue;
+        }
         const int slot = (int)(b % kUpRing);
         const uint32_t nexc = exc_count[b].load();
         cudaError_t e = cudaSuccess;
         if (nexc > kUpExcCap) {
-            // too many bytes >= 4 in this block: ship it as it is
-            e = cudaMemcpyAsync(d_dst + off, src + off, n, cudaMemcpyHostToDevice, stream);
-            ctx->last_upload_wire_bytes += n;
+            send_raw(b);  // too many bytes >= 4 in this block: ship it as it is
         } else {
             ctx->last_upload_wire_bytes += (n + 3) / 4 + (uint64_t)nexc * 5;
             uint8_t* dp = st.d_packed + (size_t)slot * (kUpBlock / 4);
@@ -182,10 +229,9 @@ int upload_packed(dvs_ctx* ctx, const uint8_t* src, uint8_t* d_dst, size_t total
                 }
             }
         }
-        if (e == cudaSuccess) e = cudaEventRecord(st.done[slot], stream);
+        if (rc == DVS_OK && e == cudaSuccess) e = cudaEventRecord(st.done[slot], stream);
         if (e != cudaSuccess) {
-            set_error("packed upload failed: %s", cudaGetErrorString(e));
-            rc = DVS_ERR_CUDA;
+            fail(e);
             break;
         }
         // the slot of block b is reused by block b + kUpRing: release it once this block has landed.
@@ -194,12 +240,12 @@ int upload_packed(dvs_ctx* ctx, const uint8_t* src, uint8_t* d_dst, size_t total
             const size_t rel_block = b + 1 - ((size_t)kUpRing - 1);  // oldest block still owning a slot
             e = cudaEventSynchronize(st.done[rel_block % kUpRing]);
             if (e != cudaSuccess) {
-                set_error("packed upload failed: %s", cudaGetErrorString(e));
-                rc = DVS_ERR_CUDA;
+                fail(e);
                 break;
             }
             released.store(rel_block + 1 + kUpRing, std::memory_order_release);
         }
+        ++b;
     }
     if (rc != DVS_OK) abort.store(true);
     released.store(nblocks + kUpRing + 1, std::memory_order_release);
