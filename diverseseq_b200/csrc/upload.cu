@@ -155,11 +155,12 @@ int upload_packed(dvs_ctx* ctx, const uint8_t* src, uint8_t* d_dst, size_t total
     if (const char* lws = getenv("LOCAL_WORLD_SIZE")) nthreads = std::max(1u, nthreads / (unsigned)std::max(1, atoi(lws)));
     if (const char* ht = getenv("DVS_HOST_THREADS")) nthreads = (unsigned)std::max(1, atoi(ht));
     nthreads = (unsigned)std::min<size_t>(nthreads, std::max<size_t>(1, (total + kUpSub - 1) / kUpSub));
-    // measured on the 16-core bench host: stealing moved 8 of 42 GB raw but the upload took the same
-    // 0.40 s - host DRAM bandwidth (packing reads at ~108 GB/s) is the shared bottleneck, so it is off
-    // by default; DVS_UPLOAD_STEAL=1 enables it for hosts with fewer cores per GPU
+    // Stealing balances the two resources whatever the host looks like: on the 16-core 1-GPU bench host
+    // packing (host DRAM bandwidth, ~108 GB/s) and the link finish together either way (0.40 s); with
+    // two ranks sharing 24 cores the packers alone fell to 0.71 s per rank while each GPU's own link sat
+    // idle.  DVS_UPLOAD_STEAL=0 disables it.
     const char* steal_env = getenv("DVS_UPLOAD_STEAL");
-    const bool steal = steal_env && steal_env[0] == '1';
+    const bool steal = !(steal_env && steal_env[0] == '0');
     std::vector<std::thread> pool;
     for (unsigned t = 0; t < nthreads; ++t) pool.emplace_back(worker);
 

@@ -134,3 +134,69 @@ def chunked_select(ctx, kf, local_order, mode: int, min_size: int, max_size: int
     order = np.arange(g_rows.shape[0], dtype=np.uint32)
     midx, mdelta, mstats = merged.select(order, mode, min_size, max_size)
     return g_ids[midx], mdelta, mstats
+
+
+def row_blocks(n: int, world: int, align: int = 128) -> list[tuple[int, int]]:
+    """block partition of the rows of an n x n matrix; block starts are multiples of `align` (the
+    Euclidean kernel mirrors tiles only when its row range is tile aligned)"""
+    per = -(-n // world)
+    per = -(-per // align) * align
+    return [(min(n, r * per), min(n, (r + 1) * per)) for r in range(world)]
+
+
+def gather_row_blocks(local_rows: np.ndarray, n: int, device, group=None) -> np.ndarray:
+    """all-gather the per-rank row blocks of an n x n matrix (ctree's distance matrix) -> full matrix on
+    every rank (`ncclAllGather` of row blocks before the CPU clustering)"""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    blocks = row_blocks(n, world)
+    per = max(e - b for b, e in blocks)
+    pad = torch.zeros((per, n), dtype=torch.float64, device=device)
+    b, e = blocks[rank]
+    if e > b:
+        pad[: e - b] = torch.from_numpy(np.ascontiguousarray(local_rows)).to(device)
+    full = all_gather_concat(pad, group)
+    out = np.empty((n, n), dtype=np.float64)
+    for r, (b, e) in enumerate(blocks):
+        if e > b:
+            out[b:e] = full[r * per: r * per + (e - b)].cpu().numpy()
+    return out
+
+
+def sharded_mash_distances(ctx, seqset_local, k: int, sketch_size: int, num_states: int, canonical: bool, device,
+                           group=None):
+    """ctree mash on N GPUs: every rank sketches its own records, the sketches are all-gathered
+    (records are rank-ordered), every rank computes its row block of the matrix, blocks are gathered."""
+    import torch
+    import torch.distributed as dist
+
+    from . import _lib
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sk = _lib.Sketches.sketch(ctx, seqset_local, k, sketch_size, num_states, canonical)
+    data, lens = sk.download()
+    stride = torch.tensor([data.shape[1]], dtype=torch.int64, device=device)
+    dist.all_reduce(stride, op=dist.ReduceOp.MAX, group=group)
+    wide = np.zeros((data.shape[0], int(stride.item())), dtype=np.uint32)
+    wide[:, : data.shape[1]] = data
+    g_data = all_gather_concat(torch.from_numpy(wide.view(np.int32)).to(device), group).cpu().numpy().view(np.uint32)
+    g_lens = all_gather_concat(torch.from_numpy(lens.view(np.int32)).to(device), group).cpu().numpy().view(np.uint32)
+    allsk = _lib.Sketches.from_host(ctx, g_data, g_lens)
+    n = allsk.nrec
+    b, e = row_blocks(n, world)[rank]
+    local = allsk.distances(k, sketch_size, b, e) if e > b else np.zeros((0, n))
+    return gather_row_blocks(local, n, device, group)
+
+
+def sharded_euclidean(ctx, kf_local, device, group=None):
+    """ctree Euclidean on N GPUs: all-gather the frequency rows, row block per rank, gather blocks"""
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    allf = all_gather_kfreqs(ctx, kf_local, device, group)
+    n = allf.nrec
+    b, e = row_blocks(n, world)[rank]
+    local = allf.euclidean(b, e) if e > b else np.zeros((0, n))
+    return gather_row_blocks(local, n, device, group)
