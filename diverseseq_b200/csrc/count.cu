@@ -513,7 +513,8 @@ int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dv
     {
         // aim for >= 8 items per CTA, multiples of the 8 KB stripe.  Every item pays a zero + flush of its
         // table, so big tables (k >= 7) take up to 2-8 MB per item, small ones 64 KB .. 1 MB
-        const uint64_t flush_bins = (mode == MODE_SUPER) ? dim : part_bins;  // global atomics per item
+        // global atomics per item at flush time (none for MODE_GLOBAL, which updates the row directly)
+        const uint64_t flush_bins = (mode == MODE_GLOBAL) ? 0 : (mode == MODE_SUPER ? dim : part_bins);
         const uint64_t max_chunk = flush_bins >= 32768 ? (8u << 20) : (flush_bins >= 16384 ? (2u << 20) : (1u << 20));
         uint64_t want_items = (uint64_t)grid * 8;
         uint64_t c = (s->total + want_items - 1) / std::max<uint64_t>(want_items, 1);

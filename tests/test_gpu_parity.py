@@ -225,6 +225,20 @@ def test_select_fast_path_equals_exact_only(lib, ctx, orc, monkeypatch):
     assert i1.tolist() == exp.ids.tolist() and np.array_equal(d1, exp.delta_jsd)
 
 
+def test_select_large_sets_match_oracle(lib, ctx, orc):
+    """bigger selections (n well above one warp / one CTA of members) and a long max growth phase"""
+    flat, off = lib.synth_host(123, 2500, 20, 3000)
+    kf = lib.KFreqs.count(ctx, lib.SeqSet.upload(ctx, flat, off), 4)
+    _, of, oe, ov = orc.count_batch(flat, off, 4)
+    order = np.random.default_rng(5).permutation(2500).astype(np.uint32)
+    for mode, omode, lo, hi in ((lib.MODE_NMOST, "nmost", 700, 700), (lib.MODE_MAX_COV, "cov", 50, 400),
+                                (lib.MODE_MAX_STDEV, "stdev", 20, 2500)):
+        exp = orc.select_rows(of, oe, order, omode, lo, hi, valid=ov)
+        idx, delta, stats = kf.select(order, mode, lo, hi)
+        assert idx.tolist() == exp.ids.tolist() and np.array_equal(delta, exp.delta_jsd)
+        assert stats[0] == exp.total_jsd and stats[2] == exp.std_delta_jsd
+
+
 def test_select_errors(lib, ctx):
     seqs = [np.array(s, dtype=np.uint8) for s in ([0, 0, 1, 1], [1, 1, 1, 3], [4, 4], [4])]
     kf = lib.KFreqs.count(ctx, lib.SeqSet.from_seqs(ctx, seqs), 1)
@@ -424,6 +438,11 @@ def test_chunked_select_world1_matches_oracle(lib, ctx, orc):
         allf = shard.all_gather_kfreqs(ctx, kf, torch.device("cuda", 0))
         i2, d2, s2 = allf.select(order, lib.MODE_NMOST, 12)
         assert i2.tolist() == first.ids.tolist() and np.array_equal(d2, first.delta_jsd)
+        # ctree matrices through the sharded helpers (row blocks + gather) == the single-call matrices
+        ss = lib.SeqSet.upload(ctx, flat, off)
+        full_mash = lib.Sketches.sketch(ctx, ss, 8, 64, 4, True).distances(8, 64)
+        assert np.array_equal(shard.sharded_mash_distances(ctx, ss, 8, 64, 4, True, torch.device("cuda", 0)), full_mash)
+        assert np.array_equal(shard.sharded_euclidean(ctx, kf, torch.device("cuda", 0)), kf.euclidean())
     finally:
         dist.destroy_process_group()
 

@@ -29,15 +29,72 @@ def main() -> int:
     ap.add_argument("--quick", action="store_true", help="1/10 size (smoke)")
     ap.add_argument("--only", default="max,mash,euclid,count12")
     a = ap.parse_args()
+    import os
+
     from diverseseq_b200 import _lib
 
-    ctx = _lib.Context(0)
+    world, rank, local = (int(os.environ.get(v, d)) for v, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+    ctx = _lib.Context(local)
     ctx.enable_timing(True)
     which = set(a.only.split(","))
     scale = 10 if a.quick else 1
 
     def emit(**kw):
-        print(json.dumps(kw), flush=True)
+        if rank == 0:
+            print(json.dumps(kw), flush=True)
+
+    if world > 1:
+        # torchrun: tile/row-sharded ctree matrices over N GPUs: records sharded for
+        # sketching / counting, all-gather, one row block of the matrix per rank, gather of the blocks
+        import torch
+        import torch.distributed as dist
+
+        from diverseseq_b200 import shard
+
+        torch.cuda.set_device(local)
+        device = torch.device("cuda", local)
+        dist.init_process_group("nccl", device_id=device)
+
+        def timed(fn):
+            dist.barrier(); torch.cuda.synchronize(device)
+            t0 = time.perf_counter()
+            out = fn()
+            torch.cuda.synchronize(device); dist.barrier()
+            return shard.max_over_ranks(time.perf_counter() - t0, device), out
+
+        if "mash" in which:
+            nrec, mean_len, k, s = 1000 // scale, 4_000_000 // scale, 16, 3000
+            b, e = shard.shard_bounds(nrec, world, rank)
+            flat, off = None, None
+            ss_all = _lib.SeqSet.synth(ctx, SEED, nrec, 64, mean_len)  # same set on every rank; keep own shard
+            offs = ss_all.offsets()
+            part = ss_all.download(b, e - b)
+            ss = _lib.SeqSet.upload(ctx, part, (offs[b:e + 1] - offs[b]).astype(np.uint64))
+            del ss_all
+            shard.sharded_mash_distances(ctx, ss, k, s, 4, True, device)
+            dt, d = timed(lambda: shard.sharded_mash_distances(ctx, ss, k, s, 4, True, device))
+            emit(config="configs[3] ctree mash k=16 s=3000 canonical", n_gpus=world, nrec=nrec, wall_s=dt,
+                 pairs=nrec * (nrec - 1) // 2, pairs_per_s_wall=nrec * (nrec - 1) // 2 / dt, mean_dist=float(d.mean()),
+                 note="sketch (record-sharded) + all-gather sketches + row-block pairs + gather of row blocks")
+        if "euclid" in which:
+            nrec, mean_len, k = 10500 // scale, 400_000, 8
+            b, e = shard.shard_bounds(nrec, world, rank)
+            ss_all = _lib.SeqSet.synth(ctx, SEED, nrec, 64, mean_len)
+            offs = ss_all.offsets()
+            part = ss_all.download(b, e - b)
+            ss = _lib.SeqSet.upload(ctx, part, (offs[b:e + 1] - offs[b]).astype(np.uint64))
+            del ss_all
+            kf = _lib.KFreqs.count(ctx, ss, k)
+            if (e - b) * world != nrec:
+                raise SystemExit("euclid multi-GPU bench needs nrec divisible by the world size")
+            shard.sharded_euclidean(ctx, kf, device)
+            dt, d = timed(lambda: shard.sharded_euclidean(ctx, kf, device))
+            npairs = nrec * (nrec - 1) // 2
+            emit(config="configs[4] ctree euclidean k=8", n_gpus=world, nrec=nrec, wall_s=dt, pairs=npairs,
+                 pairs_per_s_wall=npairs / dt, mean_dist=float(d.mean()),
+                 note="all-gather rows + row-block tiles per rank + gather of row blocks (host matrix included)")
+        dist.destroy_process_group()
+        return 0
 
     if "max" in which:
         nrec, mean_len, k = 10500 // scale, 4_000_000 // scale, 8
