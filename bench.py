@@ -338,8 +338,26 @@ def main():
     # ---- end to end through the host-buffer API: pinned host -> device copy inside the timed region ----
     e2e = None
     if not a.no_e2e:
+        # stage 1 (collective decision): can every local rank pin its whole input?  Refuse (e2e.value =
+        # null with the reason) rather than risk the host OOM killer when the box cannot hold N x 42 GB.
+        why, pinned = None, None
         try:
+            lws = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+            avail = None
+            for ln in open("/proc/meminfo"):
+                if ln.startswith("MemAvailable"):
+                    avail = float(ln.split()[1]) * 1024
+            if avail is not None and bases * lws * 1.25 > avail:
+                raise MemoryError(f"host MemAvailable {avail / 1e9:.0f} GB < {lws} ranks x {bases / 1e9:.0f} GB pinned input")
             pinned = torch.empty(int(bases) + 64, dtype=torch.uint8, pin_memory=True)
+        except Exception as exc:
+            why = f"{type(exc).__name__}: {exc}"
+        all_ok = shard.sum_over_ranks(0.0 if why is None else 1.0, device) == 0.0
+        if not all_ok:
+            e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                   "error": why or "another rank could not pin its input"}
+            pinned = None
+        else:
             host = pinned.numpy()
             seqset.download(0, a.nrec, out=host)
             offsets = seqset.offsets()
@@ -363,9 +381,6 @@ def main():
                    "note": "pinned host buffer (1 byte/base, the reference layout) -> dvs_seqset_upload (host threads "
                            "pack 2 bits/base, PCIe, device unpack to the same bytes) -> count -> nmost -> read back "
                            "indices/deltas; h2d_bytes_per_step counts the host bytes handed to the API"}
-        except Exception as exc:  # e.g. not enough host memory to pin the whole input
-            e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                   "error": f"{type(exc).__name__}: {exc}"}
 
     base = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
