@@ -303,6 +303,19 @@ class SummedRecordsWrapper:
             raise ValueError(f"delta_jsd('{seqid}') failed: No valid k-mers for '{seqid}'")
         return self._summed.delta_jsd(q, 0, is_member=seqid in self._member_names)
 
+    def delta_jsd_many(self, seqids_seqs) -> list[float]:
+        """batch form of delta_jsd (one count + one scoring launch for all queries); same values and the
+        same ValueError for a query without valid k-mers"""
+        seqids_seqs = list(seqids_seqs)
+        seqset = _lib.SeqSet.from_seqs(self._ctx, [_lib.as_u8(s) for _, s in seqids_seqs])
+        q = _lib.KFreqs.count(self._ctx, seqset, self._k, self._num_states)
+        member = np.array([sid in self._member_names for sid, _ in seqids_seqs], dtype=np.uint8)
+        out = self._summed.delta_jsd_batch(q, member)
+        for (sid, _), v in zip(seqids_seqs, out):
+            if v != v:
+                raise ValueError(f"delta_jsd('{sid}') failed: No valid k-mers for '{sid}'")
+        return out.tolist()
+
     def get_result(self) -> SummedRecordsResult:
         idx, delta, stats, _low = self._summed.result()
         rows = np.stack([self._kf.download(int(r), 1, counts=False)[1][0] for r in idx])

@@ -57,6 +57,7 @@ SIGNATURES = {
     "dvs_select_last_exact_evals": (_u32, [_vp]),
     "dvs_summed_create": (_i32, [_vp, _vp, _vp, _u32, C.POINTER(_vp)]),
     "dvs_summed_delta_jsd": (_i32, [_vp, _vp, _vp, _u32, _i32, C.POINTER(_f64)]),
+    "dvs_summed_delta_jsd_batch": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "dvs_summed_result": (_i32, [_vp, _vp, _vp, _vp, _vp, C.POINTER(_u32), C.POINTER(_u32)]),
     "dvs_summed_free": (None, [_vp]),
     "dvs_mash_sketch": (_i32, [_vp, _vp, _i32, _u64, _i32, _i32, C.POINTER(_vp)]),
@@ -373,6 +374,13 @@ class Summed(_Handle):
         check(self.ctx._lib.dvs_summed_delta_jsd(self.ctx.handle, self.handle, query.handle, row, int(is_member),
                                                  C.byref(out)))
         return out.value
+
+    def delta_jsd_batch(self, queries: KFreqs, is_member=None) -> np.ndarray:
+        """delta_jsd of every row of `queries` (NaN for rows without valid k-mers)"""
+        out = np.zeros(queries.nrec, dtype=np.float64)
+        mem = None if is_member is None else np.ascontiguousarray(is_member, dtype=np.uint8)
+        check(self.ctx._lib.dvs_summed_delta_jsd_batch(self.ctx.handle, self.handle, queries.handle, ptr(mem), ptr(out)))
+        return out
 
     def result(self):
         idx = np.zeros(self.size, dtype=np.uint32)

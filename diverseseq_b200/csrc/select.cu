@@ -17,6 +17,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <limits>
 
 #include "common.cuh"
 #include "entropy.cuh"
@@ -1189,6 +1190,47 @@ int dvs_summed_delta_jsd(dvs_ctx* ctx, dvs_summed* s, const dvs_kfreqs* q, uint3
         set_error("cannot calculate entropy as frequency vector total !=1.0");
         return DVS_ERR_VALUE;
     }
+    return DVS_OK;
+}
+
+int dvs_summed_delta_jsd_batch(dvs_ctx* ctx, dvs_summed* s, const dvs_kfreqs* q, const uint8_t* is_member_or_null,
+                               double* out) {
+    if (!ctx || !s || !q || !out || q->dim != s->f->dim) {
+        set_error("dvs_summed_delta_jsd_batch: bad argument");
+        return DVS_ERR_ARG;
+    }
+    const uint32_t nq = q->nrec;
+    if (nq == 0) return DVS_OK;
+    DVS_CUDA_TRY(dvs::enter(ctx));
+    Selector sel{ctx, s->f, s->f->dim, ctx->stream, (SelScal*)ctx->pinned};
+    DevBuf<double> d_out;
+    DevBuf<uint8_t> d_mem;
+    DVS_TRY(d_out.alloc(nq));
+    DVS_TRY(d_mem.alloc(nq));
+    std::vector<uint8_t> h_mem(nq, 0), h_valid(nq);
+    if (is_member_or_null)
+        for (uint32_t i = 0; i < nq; ++i) h_mem[i] = is_member_or_null[i] ? 1 : 0;
+    DVS_CUDA_TRY(cudaMemcpyAsync(d_mem.p, h_mem.data(), nq, cudaMemcpyHostToDevice, ctx->stream));
+    DVS_CUDA_TRY(cudaMemsetAsync(d_out.p, 0, nq * sizeof(double), ctx->stream));
+    DVS_TRY(sel.reset_scan(s->st));
+    // one CTA per query row; position == row (order == nullptr); invalid / member rows are skipped
+    k_sel_scan<<<nq, kEntThreads, kEntSmemBytes, ctx->stream>>>(s->f->freqs.p, s->f->entropy.p, s->f->dim, s->st.S(),
+                                                                 s->st.members(), s->st.sc.p, q->freqs.p,
+                                                                 q->entropy.p, q->valid.p, d_mem.p, nullptr, 0u,
+                                                                 d_out.p);
+    DVS_LAUNCHED(ctx);
+    DVS_CUDA_TRY(cudaMemcpyAsync(out, d_out.p, nq * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    DVS_CUDA_TRY(cudaMemcpyAsync(h_valid.data(), q->valid.p, nq, cudaMemcpyDeviceToHost, ctx->stream));
+    DVS_TRY(sel.read(s->st));
+    const SelScal h = *sel.h_sc;
+    DVS_TRY(sel.reset_scan(s->st));
+    DVS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (h.first_panic != kNone) {
+        set_error("cannot calculate entropy as frequency vector total !=1.0 (query %u)", h.first_panic);
+        return DVS_ERR_VALUE;
+    }
+    for (uint32_t i = 0; i < nq; ++i)
+        if (!h_valid[i]) out[i] = std::numeric_limits<double>::quiet_NaN();
     return DVS_OK;
 }
 

@@ -152,7 +152,12 @@ int upload_packed(dvs_ctx* ctx, const uint8_t* src, uint8_t* d_dst, size_t total
     // one process per GPU: share the host cores between the local ranks (torchrun exports
     // LOCAL_WORLD_SIZE); DVS_HOST_THREADS overrides
     unsigned nthreads = std::max(1u, std::thread::hardware_concurrency());
-    if (const char* lws = getenv("LOCAL_WORLD_SIZE")) nthreads = std::max(1u, nthreads / (unsigned)std::max(1, atoi(lws)));
+    if (const char* lws = getenv("LOCAL_WORLD_SIZE")) {
+        // leave one core per rank for the thread that drives the GPU (an 8-GPU box with 32 cores was
+        // measured: fully subscribing the cores starved the other ranks' kernel-launching threads)
+        const unsigned share = nthreads / (unsigned)std::max(1, atoi(lws));
+        nthreads = atoi(lws) > 1 ? std::max(1u, share > 1 ? share - 1 : share) : std::max(1u, share);
+    }
     if (const char* ht = getenv("DVS_HOST_THREADS")) nthreads = (unsigned)std::max(1, atoi(ht));
     nthreads = (unsigned)std::min<size_t>(nthreads, std::max<size_t>(1, (total + kUpSub - 1) / kUpSub));
     // Stealing balances the two resources whatever the host looks like: on the 16-core 1-GPU bench host

@@ -149,6 +149,11 @@ int dvs_summed_create(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* members
  * query's seqid is already in the set -> 0.0 */
 int dvs_summed_delta_jsd(dvs_ctx* ctx, dvs_summed* s, const dvs_kfreqs* q, uint32_t q_row, int is_member,
                          double* out);
+/* delta_jsd of EVERY row of `q` in one launch (the dvs_delta_jsd app scores many queries against one
+ * state, diverse_seq/records.py:377-429).  is_member_or_null[r] != 0 -> 0.0 (seqid already in the set);
+ * rows without valid k-mers get NaN (the reference raises ValueError for those). */
+int dvs_summed_delta_jsd_batch(dvs_ctx* ctx, dvs_summed* s, const dvs_kfreqs* q, const uint8_t* is_member_or_null,
+                               double* out);
 int dvs_summed_result(dvs_ctx* ctx, dvs_summed* s, uint32_t* sel_idx, double* sel_delta, double* stats5,
                       uint32_t* size_out, uint32_t* lowest_out);
 void dvs_summed_free(dvs_summed* s);

@@ -274,6 +274,10 @@ def test_dvs_summed_goldens(orc):  # records.rs:602-621, 676-685 through the dro
     assert better > r.total_jsd and better == orc.Summed([list(b) for _, b in recs], 1).delta_jsd([0, 1, 2, 1])
     with pytest.raises(ValueError, match=r"delta_jsd\('bad'\) failed: No valid k-mers for 'bad'"):
         calc.delta_jsd("bad", bytes([4, 4, 4]))  # records_py.rs:113-118, tests/test_records.py:285-291
+    many = calc.delta_jsd_many([("seq4", bytes([0, 1, 2, 1])), ("seq1", bytes([0, 1, 2, 3])), ("q", bytes([3, 3, 1]))])
+    assert many[0] == better and many[1] == 0.0 and many[2] == calc.delta_jsd("q", bytes([3, 3, 1]))
+    with pytest.raises(ValueError, match="No valid k-mers for 'bad'"):
+        calc.delta_jsd_many([("seq4", bytes([0, 1, 2, 1])), ("bad", bytes([4]))])
 
 
 def test_dvs_nmost_max_pickle_and_errors(brca1, orc):
