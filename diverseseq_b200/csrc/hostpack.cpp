@@ -62,6 +62,7 @@ __attribute__((target("avx2"))) static void pack_avx2(const uint8_t* src, size_t
     const __m256i w1 = _mm256_set1_epi16(0x0401);      // byte pairs: b_even*1 + b_odd*4
     const __m256i w2 = _mm256_set1_epi32(0x00100001);  // 16-bit pairs: t_even*1 + t_odd*16
     const __m256i order = _mm256_setr_epi32(0, 4, 1, 5, 2, 6, 3, 7);
+    const bool aligned = ((uintptr_t)dst & 15) == 0;
     size_t q = 0;
     for (; q + 64 <= n; q += 64) {
         _mm_prefetch((const char*)(src + q + 1024), _MM_HINT_T0);
@@ -76,8 +77,14 @@ __attribute__((target("avx2"))) static void pack_avx2(const uint8_t* src, size_t
         const __m256i p16 = _mm256_packus_epi32(u0, u1);   // lane0: u0 d0-3, u1 d0-3 | lane1: u0 d4-7, u1 d4-7
         const __m256i p8 = _mm256_packus_epi16(p16, p16);  // low 8 bytes of each lane carry the data
         const __m256i r = _mm256_permutevar8x32_epi32(p8, order);  // dwords: u0 d0-3, u0 d4-7, u1 d0-3, u1 d4-7
-        _mm_storeu_si128((__m128i*)(dst + (q >> 2)), _mm256_castsi256_si128(r));
+        // non-temporal store: the packed block is only read again by the DMA engine, and a regular
+        // store would first read the destination line (write-allocate) on a DRAM-bandwidth-bound loop
+        if (aligned)
+            _mm_stream_si128((__m128i*)(dst + (q >> 2)), _mm256_castsi256_si128(r));
+        else
+            _mm_storeu_si128((__m128i*)(dst + (q >> 2)), _mm256_castsi256_si128(r));
     }
+    _mm_sfence();
     if (q < n) pack_scalar(src + q, n - q, dst + (q >> 2), rel0 + (uint32_t)q, ex);
 }
 
