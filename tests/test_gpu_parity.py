@@ -109,6 +109,12 @@ def test_count_long_records_split_across_ctas(lib, ctx, orc):
     _check_counts(lib, ctx, orc, seqs, 8)
 
 
+def test_count_k12_global_atomic_path(lib, ctx, orc, brca1):
+    """north-star headline k: 4^12 bins per record, global RED.ADD path"""
+    seqs = [brca1["Human"], brca1["Dugong"], np.zeros(5, np.uint8)]
+    _check_counts(lib, ctx, orc, seqs, 12)
+
+
 @pytest.mark.parametrize("ns,k", [(5, 3), (20, 2), (2, 7), (3, 1)])
 def test_count_other_num_states(lib, ctx, orc, ns, k):
     rng = np.random.default_rng(ns * 31 + k)
