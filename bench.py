@@ -51,6 +51,7 @@ def parse_args():
                          "final_nmost); 'union' = single-pass selection over all records on every GPU")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ctree", action="store_true", help="skip the ctree pairs/s side measurements (N=1 only)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of one CPU sample")
     return ap.parse_args()
 
@@ -389,6 +390,39 @@ def main():
         base = cpu_baseline(a, seqset, a.cpu_seconds)
         base = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
+    # BASELINE.json's third metric, "ctree distance pairs/s" (configs[3] and configs[4]); outside the timed step
+    ctree = None
+    if rank == 0 and world == 1 and not a.no_ctree:
+        try:
+            del seqset
+            seqset = None
+            ss = _lib.SeqSet.synth(ctx, SEED, 1000, a.nfam, a.mean_len)
+            sk = _lib.Sketches.sketch(ctx, ss, 16, 3000, 4, True)
+            sk = _lib.Sketches.sketch(ctx, ss, 16, 3000, 4, True)
+            sk_ms = ctx.phase_ms(_lib.PHASE_SKETCH)
+            t0 = time.perf_counter()
+            sk.distances(16, 3000)
+            mash_wall = time.perf_counter() - t0
+            mash_ms = ctx.phase_ms(_lib.PHASE_MASH_PAIRS)
+            mash_bases = ss.total_bases
+            del sk, ss
+            ss = _lib.SeqSet.synth(ctx, SEED, a.nrec, a.nfam, 400_000)  # rows depend on nrec x 4^8 only
+            kf8 = _lib.KFreqs.count(ctx, ss, 8)
+            t0 = time.perf_counter()
+            kf8.euclidean()
+            eu_wall = time.perf_counter() - t0
+            eu_ms = ctx.phase_ms(_lib.PHASE_EUCLID)
+            del kf8, ss
+            npm, npe = 1000 * 999 // 2, a.nrec * (a.nrec - 1) // 2
+            ctree = {"mash_k16_s3000_1k_genomes": {"sketch_ms": sk_ms, "sketch_gbp_per_s": mash_bases / sk_ms / 1e6,
+                                                   "pairs": npm, "pairs_kernel_ms": mash_ms,
+                                                   "pairs_per_s": npm / mash_ms * 1e3, "pairs_per_s_with_d2h": npm / mash_wall},
+                     f"euclid_k8_{a.nrec}_genomes": {"pairs": npe, "kernel_ms": eu_ms, "pairs_per_s": npe / eu_ms * 1e3,
+                                                     "pairs_per_s_with_d2h": npe / eu_wall,
+                                                     "fp64_tflops": 2.0 * 65536 * npe / eu_ms / 1e9}}
+        except Exception as exc:
+            ctree = {"error": f"{type(exc).__name__}: {exc}"}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -399,7 +433,7 @@ def main():
                           "freq_entropy_ms": float(np.mean(fe_ms)), "nmost_wall_s": float(np.mean(sel_ms)) * 1e-3,
                           "nmost_accepts": accepts, "total_gbp": total_bases / 1e9,
                           "selected_head": idx[:8].tolist(), "total_jsd": float(stats[0]),
-                          "host_wall_ms_last_step": phase.get("host_wall_ms")}}
+                          "host_wall_ms_last_step": phase.get("host_wall_ms"), "ctree": ctree}}
         emit(line)
     if world > 1:
         dist.destroy_process_group()
