@@ -148,6 +148,11 @@ struct dvs_seqset {
     dvs::DevBuf<uint8_t> raw;        // kSeqFrontPad + total + kSeqTailPad
     dvs::DevBuf<uint64_t> offsets;   // nrec+1 (device)
     std::vector<uint64_t> h_offsets;  // nrec+1 (host)
+    // counting work list of the last (chunk, nparts) asked for, kept on the device so that repeated
+    // counting of one seqset (several k, several passes) does not rebuild and re-send it
+    mutable dvs::DevBuf<uint8_t> work_cache;
+    mutable uint64_t work_chunk = 0;
+    mutable uint32_t work_nparts = 0, work_items = 0;
     const uint8_t* data() const { return raw.p + kSeqFrontPad; }
     uint8_t* data() { return raw.p + kSeqFrontPad; }
 };

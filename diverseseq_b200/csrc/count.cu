@@ -525,21 +525,34 @@ int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dv
         // time with 8 KB items (measured at k=12: 37 Gbp/s with 9 rows in flight, DRAM sector bound)
         if (mode == MODE_GLOBAL && dim * 4 >= (16u << 20)) chunk = 8192;
     }
-    std::vector<CountWork> work;
-    for (uint32_t r = 0; r < s->nrec; ++r) {
-        uint64_t b = s->h_offsets[r], e = s->h_offsets[r + 1];
-        if (e <= b) continue;
-        uint64_t a0 = b & ~15ULL, a1 = (e + 15) & ~15ULL;
-        for (uint64_t a = a0; a < a1; a += chunk)
-            for (uint32_t p = 0; p < nparts; ++p) work.push_back({a, std::min(a + chunk, a1), r, p});
+    if (s->work_chunk != chunk || s->work_nparts != nparts || !s->work_cache.p) {
+        std::vector<CountWork> work;
+        for (uint32_t r = 0; r < s->nrec; ++r) {
+            uint64_t b = s->h_offsets[r], e = s->h_offsets[r + 1];
+            if (e <= b) continue;
+            uint64_t a0 = b & ~15ULL, a1 = (e + 15) & ~15ULL;
+            for (uint64_t a = a0; a < a1; a += chunk)
+                for (uint32_t p = 0; p < nparts; ++p) work.push_back({a, std::min(a + chunk, a1), r, p});
+        }
+        if (work.size() > 0xFFFFFFFFull) {
+            dvs::set_error("too many counting work items");
+            return fail(DVS_ERR_ARG);
+        }
+        s->work_chunk = 0;
+        if (s->work_cache.alloc(work.size() * sizeof(CountWork)) != DVS_OK) return fail(DVS_ERR_CUDA);
+        // pageable source: the copy is staged before the call returns, so `work` may die here
+        TRY_F(cudaMemcpyAsync(s->work_cache.p, work.data(), work.size() * sizeof(CountWork), cudaMemcpyHostToDevice, st));
+        s->work_chunk = chunk;
+        s->work_nparts = nparts;
+        s->work_items = (uint32_t)work.size();
     }
-    DevBuf<CountWork> d_work;
+    const CountWork* d_work = reinterpret_cast<const CountWork*>(s->work_cache.p);
+    const uint32_t n_work = s->work_items;
     DevBuf<uint32_t> d_next;
-    if (!work.empty()) {
-        if (d_work.alloc(work.size()) != DVS_OK || d_next.alloc(1) != DVS_OK) return fail(DVS_ERR_CUDA);
-        TRY_F(cudaMemcpyAsync(d_work.p, work.data(), work.size() * sizeof(CountWork), cudaMemcpyHostToDevice, st));
+    if (n_work) {
+        if (d_next.alloc(1) != DVS_OK) return fail(DVS_ERR_CUDA);
         TRY_F(cudaMemsetAsync(d_next.p, 0, sizeof(uint32_t), st));
-        const uint32_t g = (uint32_t)std::min<size_t>(grid, work.size());
+        const uint32_t g = (uint32_t)std::min<size_t>(grid, n_work);
         auto set_smem = [&](auto kern) -> cudaError_t {
             return hist_bytes > 48 * 1024
                        ? cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes)
@@ -548,7 +561,7 @@ int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dv
         auto launch4 = [&](auto kern) -> cudaError_t {
             cudaError_t e = set_smem(kern);
             if (e != cudaSuccess) return e;
-            kern<<<g, threads4, hist_bytes, st>>>(s->data(), s->offsets.p, d_work.p, (uint32_t)work.size(),
+            kern<<<g, threads4, hist_bytes, st>>>(s->data(), s->offsets.p, d_work, n_work,
                                                   d_next.p, k, dim, part_bins, f->counts.p);
             ctx->launches++;
             return cudaGetLastError();
@@ -556,7 +569,7 @@ int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dv
         auto launch_generic = [&](auto kern) -> cudaError_t {
             cudaError_t e = set_smem(kern);
             if (e != cudaSuccess) return e;
-            kern<<<g, kCountThreads, hist_bytes, st>>>(s->data(), s->offsets.p, d_work.p, (uint32_t)work.size(),
+            kern<<<g, kCountThreads, hist_bytes, st>>>(s->data(), s->offsets.p, d_work, n_work,
                                                        d_next.p, k, (uint32_t)num_states, dim, part_bins,
                                                        f->counts.p);
             ctx->launches++;
