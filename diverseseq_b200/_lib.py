@@ -17,6 +17,7 @@ LIB_PATH = _HERE / "libdvs_b200.so"
 DVS_OK, DVS_ERR_VALUE, DVS_ERR_CUDA, DVS_ERR_ARG = 0, 1, 2, 3
 MODE_NMOST, MODE_MAX_STDEV, MODE_MAX_COV = 0, 1, 2
 PHASE_COUNT_KERNEL, PHASE_FREQ_ENTROPY, PHASE_SELECT, PHASE_SKETCH, PHASE_MASH_PAIRS, PHASE_EUCLID, PHASE_UPLOAD = range(7)
+PHASE_PREP = 7
 
 _vp = C.c_void_p
 _u32, _u64, _i32, _f64 = C.c_uint32, C.c_uint64, C.c_int, C.c_double
@@ -42,6 +43,7 @@ SIGNATURES = {
     "dvs_seqset_offsets": (_i32, [_vp, _vp]),
     "dvs_seqset_download": (_i32, [_vp, _vp, _u32, _u32, _vp]),
     "dvs_seqset_free": (None, [_vp]),
+    "dvs_prep_fasta": (_i32, [_vp, _vp, _vp, _u32, C.c_char_p, C.c_char_p, _i32, _i32, C.POINTER(_vp)]),
     "dvs_count_kmers": (_i32, [_vp, _vp, _i32, _i32, C.POINTER(_vp)]),
     "dvs_kfreqs_from_rows": (_i32, [_vp, _vp, _vp, _u32, _u64, C.POINTER(_vp)]),
     "dvs_kfreqs_device_ptrs": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
@@ -236,6 +238,23 @@ class SeqSet(_Handle):
     def synth(cls, ctx: Context, seed: int, nrec: int, nfam: int, mean_len: int) -> "SeqSet":
         h = _vp()
         check(ctx._lib.dvs_seqset_synth(ctx.handle, seed, nrec, nfam, mean_len, C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def prep_fasta(cls, ctx: Context, text, file_offsets, alphabet: str | None = None,
+                   delete_chars: bytes | None = None, sep_char: int = -1, device_ptr: int | None = None) -> "SeqSet":
+        """FASTA text of several files -> one encoded record per file (dvs_prep_fasta).  `text` is a
+        uint8 array / bytes holding the files back to back, or None with `device_ptr` (device text)."""
+        file_offsets = np.ascontiguousarray(file_offsets, dtype=np.uint64)
+        h = _vp()
+        if device_ptr is not None:
+            tp, on_dev = _vp(device_ptr), 1
+        else:
+            text = as_u8(text)
+            tp, on_dev = (ptr(text) if text.size else None), 0
+        check(ctx._lib.dvs_prep_fasta(ctx.handle, tp, ptr(file_offsets), len(file_offsets) - 1,
+                                      alphabet.encode() if alphabet is not None else None,
+                                      delete_chars, sep_char, on_dev, C.byref(h)))
         return cls(ctx, h)
 
     @property

@@ -86,7 +86,7 @@ struct DevBuf {
 
 }  // namespace dvs
 
-constexpr int kNumPhases = 8;
+constexpr int kNumPhases = 12;
 
 struct dvs_ctx {
     int device = 0;

@@ -1,0 +1,401 @@
+// `dvs prep` encode on the device: FASTA text -> one index-encoded record per file.
+//
+// Reference behaviour restated:
+//   diverse_seq/io.py:30-34   converter_fasta: a-z -> A-Z, delete b"\n\r\t- "
+//   diverse_seq/io.py:47-57   cogent3 iter_fasta_records(path, converter): the file is split at every
+//                             '>' byte; a piece without '\n' is dropped; otherwise the first line is
+//                             the label and the rest, run through the converter, the sequence
+//   diverse_seq/io.py:95-104  one record per FILE: b"-".join(seqs) -> str2arr
+//   diverse_seq/util.py:32-45 str2arr: most_degen_alphabet().to_indices (bytes.translate with an
+//                             identity default: a byte outside the alphabet keeps its own value)
+//
+// As a byte-level state machine (state H = inside a label line, B = inside a sequence body; a file
+// starts in H because the text before the first '>' is also cut at its first '\n'):
+//   H: '\n' -> B, and emit one separator code unless this is the file's first label end; else nothing
+//   B: '>'  -> H;  delete-set byte -> nothing;  any other byte c -> emit table[upper(c)]
+// The state before a byte only depends on the last '>' or '\n' before it, so the text is cut into
+// fixed chunks, one warp per chunk:
+//   k_prep<false>  per chunk and for both possible entry states: emitted bytes, label ends, exit state
+//   k_prep_carry   one thread per file chains its chunks: entry state, label ends so far, output offset
+//   k_prep<true>   re-reads the chunk, translates + compacts through a per-warp shared-memory stage and
+//                  writes the record bytes with aligned 16-byte stores
+// Algorithmic traffic: text read once + record bytes written once (≈2 B/base); this two-pass form reads
+// the text twice (≈3 B/base).
+#include <algorithm>
+#include <cstring>
+
+#include "common.cuh"
+
+using dvs::DevBuf;
+using dvs::set_error;
+
+extern "C" int dvs_seqset_alloc_internal(dvs_ctx* ctx, const uint64_t* offsets, uint32_t nrec, dvs_seqset** out);
+
+namespace {
+
+constexpr uint32_t kPrepChunk = 32 * 1024;  // bytes of text per warp work item
+constexpr int kPrepThreads = 512;
+constexpr int kPrepWarps = kPrepThreads / 32;
+constexpr int kStageBytes = 16 + 512 + 16;  // pending (<16) + one 4-row step + slack
+
+// table entry: low byte = output code, flags above
+constexpr uint32_t F_DEL = 0x100, F_GT = 0x200, F_NL = 0x400;
+
+struct PrepChunk {
+    uint64_t begin;  // absolute byte offset in the text
+    uint32_t len;
+    uint32_t file;
+};
+
+struct PrepSum {  // per chunk, for entry state H ([0]) and B ([1])
+    uint32_t emit[2];  // emitted sequence bytes (separators not included)
+    uint32_t ends[2];  // label ends
+    uint32_t exit_state[2];
+};
+
+struct PrepCarry {
+    uint64_t out_off;     // output offset of the chunk inside its record
+    uint32_t ends_before;  // label ends before the chunk (saturating)
+    uint32_t state;        // entry state: 1 = H, 0 = B
+};
+
+struct RowOut {
+    uint32_t out4;   // lane: bytes that produce output (sequence or separator)
+    uint32_t sep4;   // lane: subset of out4 that are separators
+    uint32_t state;  // warp: state after the row
+    uint32_t ends;   // warp: label ends in the row
+    uint32_t emit;   // warp: sequence bytes emitted in the row
+};
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// classify the lane's four bytes of a 128-byte row and run the label/body state machine over the row
+__device__ __forceinline__ RowOut prep_row(const uint32_t c[4], uint32_t state, uint32_t ends_before) {
+    uint32_t gt4 = 0, nl4 = 0, del4 = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        gt4 |= ((c[i] >> 9) & 1u) << i;
+        nl4 |= ((c[i] >> 10) & 1u) << i;
+        del4 |= ((c[i] >> 8) & 1u) << i;
+    }
+    RowOut r;
+    r.sep4 = 0;
+    r.ends = 0;
+    r.state = state;
+    const uint32_t any_gt = __ballot_sync(0xffffffffu, gt4 != 0);
+    const uint32_t any_nl = __ballot_sync(0xffffffffu, nl4 != 0);
+    if (state == 0 && any_gt == 0) {  // body all the way
+        r.out4 = ~del4 & 0xFu;
+    } else if (state == 1 && any_nl == 0) {  // label all the way
+        r.out4 = 0;
+    } else {
+        const uint32_t sp4 = gt4 | nl4;
+        const uint32_t m = any_gt | any_nl;
+        const uint32_t last_is_gt = sp4 ? ((gt4 >> (31 - __clz(sp4))) & 1u) : 0u;
+        const uint32_t prev = m & lanemask_lt();
+        const uint32_t from = __shfl_sync(0xffffffffu, last_is_gt, prev ? (31 - __clz(prev)) : 0);
+        uint32_t s = prev ? from : state;
+        uint32_t emit4 = 0, he4 = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t bit = 1u << i;
+            if (s) {
+                if (nl4 & bit) {
+                    he4 |= bit;
+                    s = 0;
+                }
+            } else if (gt4 & bit) {
+                s = 1;
+            } else if (!(del4 & bit)) {
+                emit4 |= bit;
+            }
+        }
+        const uint32_t nhe = __popc(he4);  // 0..2
+        const uint32_t b0 = __ballot_sync(0xffffffffu, nhe & 1u), b1 = __ballot_sync(0xffffffffu, nhe & 2u);
+        const uint32_t lt = lanemask_lt();
+        const uint32_t before = ends_before + __popc(b0 & lt) + 2 * __popc(b1 & lt);
+        r.ends = __popc(b0) + 2 * __popc(b1);
+        r.sep4 = he4;
+        if (before == 0 && he4) r.sep4 = he4 & (he4 - 1);  // the file's first label end joins nothing
+        r.out4 = emit4 | r.sep4;
+        r.state = __shfl_sync(0xffffffffu, last_is_gt, 31 - __clz(m));  // m != 0 on this path
+    }
+    // warp totals of emitted sequence bytes (0..4 per lane)
+    const uint32_t ne = __popc(r.out4 & ~r.sep4);
+    const uint32_t e0 = __ballot_sync(0xffffffffu, ne & 1u), e1 = __ballot_sync(0xffffffffu, ne & 2u),
+                   e2 = __ballot_sync(0xffffffffu, ne & 4u);
+    r.emit = __popc(e0) + 2 * __popc(e1) + 4 * __popc(e2);
+    return r;
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(kPrepThreads)
+k_prep(const uint8_t* __restrict__ text, const PrepChunk* __restrict__ chunks, uint32_t nchunks,
+       const uint16_t* __restrict__ table, uint32_t sep_code, PrepSum* __restrict__ sums,
+       const PrepCarry* __restrict__ carry, const uint64_t* __restrict__ rec_offsets, uint8_t* __restrict__ out) {
+    __shared__ uint16_t tab[256];
+    __shared__ __align__(16) uint8_t stage_all[WRITE ? kPrepWarps * kStageBytes : 16];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = table[i];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nwarps = gridDim.x * kPrepWarps;
+    uint8_t* stage = stage_all + (WRITE ? warp * kStageBytes : 0);
+    const uint32_t lt = lanemask_lt();
+
+    for (uint32_t ci = blockIdx.x * kPrepWarps + warp; ci < nchunks; ci += nwarps) {
+        const PrepChunk ch = chunks[ci];
+        const uint64_t begin = ch.begin, end = ch.begin + ch.len;
+        const uint64_t row0 = begin & ~127ull;
+        const uint32_t nrows = (uint32_t)((end - row0 + 127) >> 7);
+        // WRITE: real entry state; else both hypotheses (index 0: entered in H, 1: entered in B)
+        uint32_t st[2] = {1u, 0u}, emit[2] = {0, 0}, ends[2] = {0, 0};
+        uint64_t gbase = 0;
+        uint32_t fill = 0, head_skip = 0;
+        if (WRITE) {
+            const PrepCarry cy = carry[ci];
+            st[0] = cy.state;
+            ends[0] = cy.ends_before;
+            const uint64_t o0 = rec_offsets[ch.file] + cy.out_off;
+            gbase = o0 & ~15ull;
+            fill = head_skip = (uint32_t)(o0 & 15);
+        }
+        uint32_t w[4], wn[4];
+        auto load_step = [&](uint32_t row, uint32_t* dst) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint64_t p = row0 + ((uint64_t)(row + j) << 7) + 4 * lane;
+                dst[j] = (row + j < nrows && p + 4 > begin && p < end)
+                             ? __ldg(reinterpret_cast<const uint32_t*>(text + p))
+                             : 0u;
+            }
+        };
+        load_step(0, w);
+        for (uint32_t row = 0; row < nrows; row += 4) {
+            load_step(row + 4, wn);  // next step in flight while this one is processed
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (row + j >= nrows) break;  // warp-uniform
+                const uint64_t p = row0 + ((uint64_t)(row + j) << 7) + 4 * lane;
+                uint32_t c[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const bool ok = (p + i >= begin) && (p + i < end);
+                    c[i] = ok ? tab[(w[j] >> (8 * i)) & 0xFFu] : F_DEL;
+                }
+                if (WRITE) {
+                    const RowOut r = prep_row(c, st[0], ends[0]);
+                    st[0] = r.state;
+                    ends[0] = min(ends[0] + r.ends, 0x7fffffffu);
+                    const uint32_t n = __popc(r.out4);
+                    const uint32_t n0 = __ballot_sync(0xffffffffu, n & 1u), n1 = __ballot_sync(0xffffffffu, n & 2u),
+                                   n2 = __ballot_sync(0xffffffffu, n & 4u);
+                    uint32_t pos = fill + __popc(n0 & lt) + 2 * __popc(n1 & lt) + 4 * __popc(n2 & lt);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (r.out4 & (1u << i)) stage[pos++] = (uint8_t)((r.sep4 & (1u << i)) ? sep_code : (c[i] & 0xFFu));
+                    fill += __popc(n0) + 2 * __popc(n1) + 4 * __popc(n2);
+                } else if (st[0] == st[1]) {
+                    const RowOut r = prep_row(c, st[0], 1);
+                    st[0] = st[1] = r.state;
+                    emit[0] += r.emit;
+                    emit[1] += r.emit;
+                    ends[0] += r.ends;
+                    ends[1] += r.ends;
+                } else {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const RowOut r = prep_row(c, st[h], 1);
+                        st[h] = r.state;
+                        emit[h] += r.emit;
+                        ends[h] += r.ends;
+                    }
+                }
+            }
+            if (WRITE) {
+                __syncwarp();
+                const uint32_t nfull = fill >> 4;
+                for (uint32_t q = lane; q < nfull; q += 32) {
+                    if (q == 0 && head_skip) {  // the bytes before head_skip belong to the previous chunk
+                        for (uint32_t b = head_skip; b < 16; ++b) out[gbase + b] = stage[b];
+                    } else {
+                        *reinterpret_cast<uint4*>(out + gbase + 16ull * q) = *reinterpret_cast<const uint4*>(stage + 16 * q);
+                    }
+                }
+                if (nfull) {
+                    const uint32_t rem = fill & 15;
+                    const uint8_t keep = lane < rem ? stage[16 * nfull + lane] : (uint8_t)0;
+                    __syncwarp();
+                    if (lane < rem) stage[lane] = keep;
+                    gbase += 16ull * nfull;
+                    fill = rem;
+                    head_skip = 0;
+                }
+                __syncwarp();
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w[j] = wn[j];
+        }
+        if (WRITE) {
+            if (lane < fill && lane >= head_skip) out[gbase + lane] = stage[lane];
+            __syncwarp();
+        } else if (lane == 0) {
+            PrepSum s;
+            for (int h = 0; h < 2; ++h) {
+                s.emit[h] = emit[h];
+                s.ends[h] = ends[h];
+                s.exit_state[h] = st[h];
+            }
+            sums[ci] = s;
+        }
+    }
+}
+
+// one thread per file: chain the chunk summaries (entry state, label ends so far, output offsets)
+__global__ void k_prep_carry(const PrepSum* __restrict__ sums, const uint32_t* __restrict__ first_chunk,
+                             uint32_t nfiles, PrepCarry* __restrict__ carry, uint64_t* __restrict__ rec_len) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nfiles) return;
+    uint32_t state = 1, ends = 0;
+    uint64_t off = 0;
+    for (uint32_t c = first_chunk[f]; c < first_chunk[f + 1]; ++c) {
+        const PrepSum s = sums[c];
+        const int h = state ? 0 : 1;
+        carry[c] = PrepCarry{off, ends, state};
+        const uint32_t seps = s.ends[h] - ((ends == 0 && s.ends[h] > 0) ? 1u : 0u);
+        off += (uint64_t)s.emit[h] + seps;
+        ends = min(ends + s.ends[h], 0x7fffffffu);
+        state = s.exit_state[h];
+    }
+    rec_len[f] = off;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dvs_prep_fasta(dvs_ctx* ctx, const uint8_t* text, const uint64_t* file_offsets, uint32_t nfiles,
+                   const char* alphabet, const char* delete_chars, int sep_char, int text_on_device,
+                   dvs_seqset** out) {
+    if (!ctx || !file_offsets || !out || (!text && file_offsets[nfiles] > 0)) {
+        set_error("dvs_prep_fasta: NULL argument");
+        return DVS_ERR_ARG;
+    }
+    for (uint32_t f = 0; f < nfiles; ++f)
+        if (file_offsets[f + 1] < file_offsets[f]) {
+            set_error("dvs_prep_fasta: file_offsets must be non-decreasing (file %u)", f);
+            return DVS_ERR_ARG;
+        }
+    if (!alphabet) alphabet = DVS_DNA_ALPHABET;
+    if (!delete_chars) delete_chars = "\n\r\t- ";
+    if (sep_char < 0) sep_char = '-';
+    const size_t na = strlen(alphabet);
+    if (na == 0 || na > 255) {
+        set_error("dvs_prep_fasta: alphabet must have 1..255 characters");
+        return DVS_ERR_ARG;
+    }
+    // translate table: upper-case, then alphabet position, identity for bytes outside the alphabet
+    uint8_t code[256];
+    for (int b = 0; b < 256; ++b) code[b] = (uint8_t)b;
+    for (size_t i = 0; i < na; ++i) code[(uint8_t)alphabet[i]] = (uint8_t)i;
+    uint16_t table[256];
+    for (int b = 0; b < 256; ++b) {
+        const int up = (b >= 'a' && b <= 'z') ? b - 32 : b;
+        table[b] = code[up];
+    }
+    for (const char* d = delete_chars; *d; ++d) table[(uint8_t)*d] |= F_DEL;
+    table[(uint8_t)'\n'] |= F_NL;
+    table[(uint8_t)'>'] |= F_GT;
+    const uint32_t sep_code = code[(uint8_t)sep_char];
+
+    DVS_CUDA_TRY(dvs::enter(ctx));
+    cudaStream_t st = ctx->stream;
+    const uint64_t total = file_offsets[nfiles];
+
+    std::vector<PrepChunk> chunks;
+    std::vector<uint32_t> first_chunk(nfiles + 1, 0);
+    for (uint32_t f = 0; f < nfiles; ++f) {
+        first_chunk[f] = (uint32_t)chunks.size();
+        for (uint64_t b = file_offsets[f]; b < file_offsets[f + 1]; b += kPrepChunk)
+            chunks.push_back({b, (uint32_t)std::min<uint64_t>(kPrepChunk, file_offsets[f + 1] - b), f});
+        if (chunks.size() > 0xFFFFFFF0ull) {
+            set_error("dvs_prep_fasta: text too large");
+            return DVS_ERR_ARG;
+        }
+    }
+    first_chunk[nfiles] = (uint32_t)chunks.size();
+    const uint32_t nchunks = (uint32_t)chunks.size();
+
+    DevBuf<uint8_t> d_text;
+    const uint8_t* dtext = text;
+    if (!text_on_device && total) {
+        DVS_TRY(d_text.alloc(total + 256));
+        PhaseTimer up(ctx, DVS_PHASE_UPLOAD);
+        DVS_CUDA_TRY(cudaMemcpyAsync(d_text.p, text, total, cudaMemcpyHostToDevice, st));
+        up.stop();
+        dtext = d_text.p;
+    }
+    DevBuf<PrepChunk> d_chunks;
+    DevBuf<uint32_t> d_first;
+    DevBuf<PrepSum> d_sums;
+    DevBuf<PrepCarry> d_carry;
+    DevBuf<uint64_t> d_len;
+    DevBuf<uint16_t> d_table;
+    DVS_TRY(d_chunks.alloc(nchunks));
+    DVS_TRY(d_first.alloc(nfiles + 1));
+    DVS_TRY(d_sums.alloc(nchunks));
+    DVS_TRY(d_carry.alloc(nchunks));
+    DVS_TRY(d_len.alloc(nfiles));
+    DVS_TRY(d_table.alloc(256));
+    if (nchunks)
+        DVS_CUDA_TRY(cudaMemcpyAsync(d_chunks.p, chunks.data(), (size_t)nchunks * sizeof(PrepChunk),
+                                     cudaMemcpyHostToDevice, st));
+    DVS_CUDA_TRY(cudaMemcpyAsync(d_first.p, first_chunk.data(), (nfiles + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    DVS_CUDA_TRY(cudaMemcpyAsync(d_table.p, table, sizeof(table), cudaMemcpyHostToDevice, st));
+
+    const uint32_t grid = (uint32_t)std::max<uint64_t>(
+        1, std::min<uint64_t>((uint64_t)ctx->sm_count * 4, (nchunks + kPrepWarps - 1) / kPrepWarps));
+    std::vector<uint64_t> rec_offsets(nfiles + 1, 0);
+    PhaseTimer pt(ctx, DVS_PHASE_PREP);
+    if (nfiles) {
+        if (nchunks) {
+            k_prep<false><<<grid, kPrepThreads, 0, st>>>(dtext, d_chunks.p, nchunks, d_table.p, sep_code, d_sums.p,
+                                                         nullptr, nullptr, nullptr);
+            DVS_LAUNCHED(ctx);
+        }
+        k_prep_carry<<<(nfiles + 127) / 128, 128, 0, st>>>(d_sums.p, d_first.p, nfiles, d_carry.p, d_len.p);
+        DVS_LAUNCHED(ctx);
+        std::vector<uint64_t> len(nfiles);
+        DVS_CUDA_TRY(cudaMemcpyAsync(len.data(), d_len.p, nfiles * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        DVS_CUDA_TRY(cudaStreamSynchronize(st));
+        for (uint32_t f = 0; f < nfiles; ++f) rec_offsets[f + 1] = rec_offsets[f] + len[f];
+    }
+    dvs_seqset* s = nullptr;
+    DVS_TRY(dvs_seqset_alloc_internal(ctx, rec_offsets.data(), nfiles, &s));
+    if (nchunks && s->total) {
+        k_prep<true><<<grid, kPrepThreads, 0, st>>>(dtext, d_chunks.p, nchunks, d_table.p, sep_code, nullptr, d_carry.p,
+                                                    s->offsets.p, s->data());
+        ctx->launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e), __FILE__, __LINE__);
+            delete s;
+            return DVS_ERR_CUDA;
+        }
+    }
+    pt.stop();
+    // the caller's text (possibly pageable) and our local tables must outlive the copies
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        set_error("dvs_prep_fasta failed: %s", cudaGetErrorString(e));
+        delete s;
+        return DVS_ERR_CUDA;
+    }
+    *out = s;
+    return DVS_OK;
+}
+
+}  // extern "C"

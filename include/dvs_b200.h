@@ -67,6 +67,7 @@ uint64_t dvs_ctx_launch_count(dvs_ctx* ctx);
 #define DVS_PHASE_MASH_PAIRS 4     /* k_mash_pairs */
 #define DVS_PHASE_EUCLID 5         /* k_euclid_tiles */
 #define DVS_PHASE_UPLOAD 6         /* host->device sequence copy of dvs_seqset_upload */
+#define DVS_PHASE_PREP 7           /* all device work of one dvs_prep_fasta (k_prep x2 + k_prep_carry) */
 /* bytes that actually crossed PCIe during the last dvs_seqset_upload (2-bit packed + exceptions for
  * large uploads, see csrc/upload.cu; equal to the input size for the plain copy) */
 uint64_t dvs_ctx_last_upload_wire_bytes(dvs_ctx* ctx);
@@ -91,6 +92,21 @@ int dvs_seqset_offsets(const dvs_seqset* s, uint64_t* offsets_out /* nrec+1 */);
 int dvs_seqset_download(dvs_ctx* ctx, const dvs_seqset* s, uint32_t first, uint32_t count,
                         uint8_t* seqs_out);
 void dvs_seqset_free(dvs_seqset* s);
+
+/* ---- `dvs prep` encode: FASTA text -> index-encoded records, one record per FILE -------------
+ * Replaces diverse_seq/io.py:30-34 (converter_fasta: a-z -> A-Z, delete "\n\r\t- "), :47-57
+ * (cogent3 iter_fasta_records: split at every '>', first line of a piece is the label, a piece
+ * without a newline is dropped), :95-104 (dvs_load_seqs: b"-".join(seqs) -> str2arr) and
+ * diverse_seq/util.py:32-45 (str2arr = most_degen_alphabet().to_indices: position in the alphabet,
+ * bytes outside it keep their own value).  `text` holds the bytes of `nfiles` files back to back,
+ * file f = [file_offsets[f], file_offsets[f+1]).  alphabet NULL = DVS_DNA_ALPHABET, delete_chars
+ * NULL = "\n\r\t- ", sep_char < 0 = '-'.  text_on_device != 0: `text` is a 4-byte aligned device
+ * pointer (readable up to 3 bytes past the end).  Codes 0..3 (T,C,A,G) are what the hot path
+ * consumes; every other code is >= 4 = invalid for it. */
+#define DVS_DNA_ALPHABET "TCAG-NRYWSKMBDHV?"
+int dvs_prep_fasta(dvs_ctx* ctx, const uint8_t* text, const uint64_t* file_offsets, uint32_t nfiles,
+                   const char* alphabet, const char* delete_chars, int sep_char, int text_on_device,
+                   dvs_seqset** out);
 
 /* ---- k-mer counting + frequencies + entropy -------------------------------------------------
  * SeqRecord::to_kcounts / to_kmerseq / entropy  (src/record.rs:41-84, 124-141, 86-106).

@@ -391,3 +391,44 @@ def log2_samples(seed: int, n: int):
     ys = np.zeros(n, dtype=np.float64)
     lib().dvso_log2_samples(seed, n, xs, ys)
     return xs, ys
+
+
+# ---- `dvs prep` encode ------------------------------------------------
+# PARITY UNPINNED: cogent3 (the parser and the alphabet) is not installed here and the reference holds
+# no golden vector for the encode step, so this restates the published behaviour of
+#   diverse_seq/io.py:30-34   converter_fasta = convert_alphabet(a-z -> A-Z, delete=b"\n\r\t- ")
+#   diverse_seq/io.py:47-57   cogent3.parse.fasta.iter_fasta_records(path, converter)
+#   diverse_seq/io.py:95-104  dvs_load_seqs.main: b"-".join(seqs) -> str2arr
+#   diverse_seq/util.py:32-45 str2arr: most_degen_alphabet().to_indices
+# with bytes.split / bytes.translate, the way the parser itself is written.  The codes of the four
+# canonical bases (T,C,A,G -> 0..3, src/distance.rs:6-8) are pinned by the reference's own tests; the
+# order of the codes >= 4 follows cogent3's degenerate gapped DNA alphabet as remembered and does not
+# influence any hot-path result (every code >= num_states is equally invalid).
+DNA_ALPHABET = "TCAG-NRYWSKMBDHV?"
+_FASTA_DELETE = b"\n\r\t- "
+
+
+def _converter_fasta(body: bytes) -> bytes:
+    import string
+
+    table = bytes.maketrans(string.ascii_lowercase.encode(), string.ascii_uppercase.encode())
+    return body.translate(table, delete=_FASTA_DELETE)
+
+
+def iter_fasta_records(data: bytes):
+    """(label, converted sequence bytes) of every '>'-delimited piece that has a label line"""
+    for piece in data.split(b">"):
+        if not piece:
+            continue
+        eol = piece.find(b"\n")
+        if eol == -1:
+            continue
+        yield piece[:eol].strip().decode("utf8", errors="replace"), _converter_fasta(piece[eol + 1:])
+
+
+def prep_fasta(data: bytes, alphabet: str = DNA_ALPHABET) -> np.ndarray:
+    """index-encoded record of one FASTA file (all its sequences joined with '-')"""
+    joined = b"-".join(seq for _, seq in iter_fasta_records(data))
+    chars = alphabet.encode()
+    table = bytes.maketrans(chars, bytes(range(len(chars))))  # bytes outside the alphabet map to themselves
+    return np.frombuffer(joined.translate(table), dtype=np.uint8).copy()
