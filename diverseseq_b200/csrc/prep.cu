@@ -59,6 +59,13 @@ struct PrepCarry {
     uint32_t state;        // entry state: 1 = H, 0 = B
 };
 
+struct PrepParams {
+    uint32_t sep_code;
+    uint32_t swar;     // 1: the SWAR fast classification below is valid for this table
+    uint32_t letters;  // the four canonical letters (upper case), byte s = the letter with ((c >> 1) & 3) == s
+    uint32_t codes;    // their codes, same byte order
+};
+
 struct RowOut {
     uint32_t out4;   // lane: bytes that produce output (sequence or separator)
     uint32_t sep4;   // lane: subset of out4 that are separators
@@ -73,15 +80,60 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
     return m;
 }
 
-// classify the lane's four bytes of a 128-byte row and run the label/body state machine over the row
-__device__ __forceinline__ RowOut prep_row(const uint32_t c[4], uint32_t state, uint32_t ends_before) {
-    uint32_t gt4 = 0, nl4 = 0, del4 = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        gt4 |= ((c[i] >> 9) & 1u) << i;
-        nl4 |= ((c[i] >> 10) & 1u) << i;
-        del4 |= ((c[i] >> 8) & 1u) << i;
+// 0x80 in every byte of x that is non-zero
+__device__ __forceinline__ uint32_t nz_flags(uint32_t x) {
+    return (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+}
+// per-byte flags (0x80 each) <-> 4-bit masks
+__device__ __forceinline__ uint32_t flags_to_mask4(uint32_t f) { return (((f >> 7) * 0x01020408u) >> 24) & 0xFu; }
+__device__ __forceinline__ uint32_t mask4_to_flags(uint32_t m) { return ((m * 0x00204081u) & 0x01010101u) << 7; }
+
+// Classes of the four bytes of `w` as 0x80-per-byte flags: deleted, '>' and '\n'; with CODES also the
+// output codes.  Fast classification (p.swar): canonical letters in either case are recognised with a
+// PRMT lookup keyed by bits 1-2 of the byte, '\n' by a SWAR compare; any other byte goes through the
+// 256-entry table in shared memory.
+template <bool CODES>
+__device__ __forceinline__ void classify(uint32_t w, const uint16_t* tab, const PrepParams& p, uint32_t& codes,
+                                         uint32_t& delf, uint32_t& gtf, uint32_t& nlf) {
+    uint32_t other;
+    delf = gtf = nlf = 0;
+    codes = 0;
+    if (p.swar) {
+        if (CODES) {
+            const uint32_t u = w & 0xDFDFDFDFu;
+            const uint32_t x = (u >> 1) & 0x03030303u;
+            uint32_t sel = (x & 0x00030003u) | ((x >> 4) & 0x00300030u);
+            sel = (sel | (sel >> 8)) & 0x3333u;
+            other = nz_flags(__byte_perm(p.letters, 0, sel) ^ u);
+            codes = __byte_perm(p.codes, 0, sel);
+        } else {
+            other = ~w & (~w << 1) & 0x80808080u;  // bytes < 0x40: the only ones that can be deleted or special
+        }
+        if (other) {
+            nlf = ~nz_flags(w ^ 0x0A0A0A0Au) & 0x80808080u;
+            delf = nlf;
+            other &= ~nlf;
+        }
+    } else {
+        other = 0x80808080u;
     }
+    if (other) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (other & (0x80u << (8 * i))) {
+                const uint32_t e = tab[(w >> (8 * i)) & 0xFFu];
+                if (CODES) codes = (codes & ~(0xFFu << (8 * i))) | ((e & 0xFFu) << (8 * i));
+                delf |= ((e >> 8) & 1u) << (8 * i + 7);
+                gtf |= ((e >> 9) & 1u) << (8 * i + 7);
+                nlf |= ((e >> 10) & 1u) << (8 * i + 7);
+            }
+        }
+    }
+}
+
+// the label/body state machine over one 128-byte row (lane = 4 bytes), general case
+__device__ __forceinline__ RowOut prep_row(uint32_t gt4, uint32_t nl4, uint32_t del4, uint32_t state,
+                                           uint32_t ends_before) {
     RowOut r;
     r.sep4 = 0;
     r.ends = 0;
@@ -135,7 +187,7 @@ __device__ __forceinline__ RowOut prep_row(const uint32_t c[4], uint32_t state, 
 template <bool WRITE>
 __global__ void __launch_bounds__(kPrepThreads)
 k_prep(const uint8_t* __restrict__ text, const PrepChunk* __restrict__ chunks, uint32_t nchunks,
-       const uint16_t* __restrict__ table, uint32_t sep_code, PrepSum* __restrict__ sums,
+       const uint16_t* __restrict__ table, PrepParams prm, PrepSum* __restrict__ sums,
        const PrepCarry* __restrict__ carry, const uint64_t* __restrict__ rec_offsets, uint8_t* __restrict__ out) {
     __shared__ uint16_t tab[256];
     __shared__ __align__(16) uint8_t stage_all[WRITE ? kPrepWarps * kStageBytes : 16];
@@ -144,15 +196,16 @@ k_prep(const uint8_t* __restrict__ text, const PrepChunk* __restrict__ chunks, u
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t nwarps = gridDim.x * kPrepWarps;
     uint8_t* stage = stage_all + (WRITE ? warp * kStageBytes : 0);
-    const uint32_t lt = lanemask_lt();
 
     for (uint32_t ci = blockIdx.x * kPrepWarps + warp; ci < nchunks; ci += nwarps) {
         const PrepChunk ch = chunks[ci];
-        const uint64_t begin = ch.begin, end = ch.begin + ch.len;
-        const uint64_t row0 = begin & ~127ull;
-        const uint32_t nrows = (uint32_t)((end - row0 + 127) >> 7);
-        // WRITE: real entry state; else both hypotheses (index 0: entered in H, 1: entered in B)
+        const uint64_t row0 = ch.begin & ~127ull;
+        const uint32_t rel_begin = (uint32_t)(ch.begin - row0), rel_end = rel_begin + ch.len;  // bytes from row0
+        const uint32_t nrows = (rel_end + 127) >> 7;
+        const uint8_t* base = text + row0 + 4 * lane;
+        // WRITE: the real entry state in [0]; else both hypotheses ([0]: entered in H, [1]: entered in B)
         uint32_t st[2] = {1u, 0u}, emit[2] = {0, 0}, ends[2] = {0, 0};
+        uint32_t lane_emit[2] = {0, 0};  // per-lane partial counts of the fast path (summed at the end)
         uint64_t gbase = 0;
         uint32_t fill = 0, head_skip = 0;
         if (WRITE) {
@@ -167,55 +220,73 @@ k_prep(const uint8_t* __restrict__ text, const PrepChunk* __restrict__ chunks, u
         auto load_step = [&](uint32_t row, uint32_t* dst) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const uint64_t p = row0 + ((uint64_t)(row + j) << 7) + 4 * lane;
-                dst[j] = (row + j < nrows && p + 4 > begin && p < end)
-                             ? __ldg(reinterpret_cast<const uint32_t*>(text + p))
-                             : 0u;
+                const uint32_t q = ((row + j) << 7) + 4 * lane;  // offset of the lane's word from row0
+                dst[j] = (q + 4 > rel_begin && q < rel_end) ? __ldg(reinterpret_cast<const uint32_t*>(base + ((row + j) << 7)))
+                                                            : 0u;
             }
         };
         load_step(0, w);
         for (uint32_t row = 0; row < nrows; row += 4) {
             load_step(row + 4, wn);  // next step in flight while this one is processed
+            uint32_t codes[4], delf[4], gtf[4], nlf[4];
+            const bool inside = (row << 7) >= rel_begin && ((row + 4) << 7) <= rel_end;  // warp-uniform
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                if (row + j >= nrows) break;  // warp-uniform
-                const uint64_t p = row0 + ((uint64_t)(row + j) << 7) + 4 * lane;
-                uint32_t c[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const bool ok = (p + i >= begin) && (p + i < end);
-                    c[i] = ok ? tab[(w[j] >> (8 * i)) & 0xFFu] : F_DEL;
-                }
-                if (WRITE) {
-                    const RowOut r = prep_row(c, st[0], ends[0]);
-                    st[0] = r.state;
-                    ends[0] = min(ends[0] + r.ends, 0x7fffffffu);
-                    const uint32_t n = __popc(r.out4);
-                    const uint32_t n0 = __ballot_sync(0xffffffffu, n & 1u), n1 = __ballot_sync(0xffffffffu, n & 2u),
-                                   n2 = __ballot_sync(0xffffffffu, n & 4u);
-                    uint32_t pos = fill + __popc(n0 & lt) + 2 * __popc(n1 & lt) + 4 * __popc(n2 & lt);
+                classify<WRITE>(w[j], tab, prm, codes[j], delf[j], gtf[j], nlf[j]);
+                if (!inside) {  // bytes outside [begin, end) count as deleted
+                    const uint32_t q = ((row + j) << 7) + 4 * lane;
+                    uint32_t valid = 0;
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        if (r.out4 & (1u << i)) stage[pos++] = (uint8_t)((r.sep4 & (1u << i)) ? sep_code : (c[i] & 0xFFu));
-                    fill += __popc(n0) + 2 * __popc(n1) + 4 * __popc(n2);
-                } else if (st[0] == st[1]) {
-                    const RowOut r = prep_row(c, st[0], 1);
-                    st[0] = st[1] = r.state;
-                    emit[0] += r.emit;
-                    emit[1] += r.emit;
-                    ends[0] += r.ends;
-                    ends[1] += r.ends;
-                } else {
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const RowOut r = prep_row(c, st[h], 1);
-                        st[h] = r.state;
-                        emit[h] += r.emit;
-                        ends[h] += r.ends;
-                    }
+                        if (q + i >= rel_begin && q + i < rel_end) valid |= 0x80u << (8 * i);
+                    delf[j] = (delf[j] & valid) | (~valid & 0x80808080u);
+                    gtf[j] &= valid;
+                    nlf[j] &= valid;
                 }
             }
+            const uint32_t any_gt = __ballot_sync(0xffffffffu, (gtf[0] | gtf[1] | gtf[2] | gtf[3]) != 0);
+            const uint32_t any_nl = __ballot_sync(0xffffffffu, (nlf[0] | nlf[1] | nlf[2] | nlf[3]) != 0);
+            uint32_t outf[4];  // WRITE: bytes of the step that produce output
             if (WRITE) {
+                if (st[0] == 0 && !any_gt) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) outf[j] = ~delf[j] & 0x80808080u;
+                } else if (st[0] == 1 && !any_nl) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) outf[j] = 0;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const RowOut r = prep_row(flags_to_mask4(gtf[j]), flags_to_mask4(nlf[j]), flags_to_mask4(delf[j]),
+                                                  st[0], ends[0]);
+                        st[0] = r.state;
+                        ends[0] = min(ends[0] + r.ends, 0x7fffffffu);
+                        outf[j] = mask4_to_flags(r.out4);
+                        const uint32_t sepf = mask4_to_flags(r.sep4);
+                        const uint32_t sm = (sepf >> 7) * 0xFFu;  // 0xFF in separator bytes
+                        codes[j] = (codes[j] & ~sm) | ((prm.sep_code * 0x01010101u) & sm);
+                    }
+                }
+                // positions: one packed scan over (row, lane) order, 8 bits per row (<= 128 each)
+                const uint32_t c = __popc(outf[0]) | (__popc(outf[1]) << 8) | (__popc(outf[2]) << 16) | (__popc(outf[3]) << 24);
+                uint32_t incl = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= (uint32_t)d) incl += v;
+                }
+                const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+                const uint32_t excl = incl - c;
+                uint32_t rowbase = fill;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t pos = rowbase + ((excl >> (8 * j)) & 0xFFu);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (outf[j] & (0x80u << (8 * i))) stage[pos++] = (uint8_t)(codes[j] >> (8 * i));
+                    rowbase += (tot >> (8 * j)) & 0xFFu;
+                }
+                fill = rowbase;
                 __syncwarp();
                 const uint32_t nfull = fill >> 4;
                 for (uint32_t q = lane; q < nfull; q += 32) {
@@ -235,6 +306,38 @@ k_prep(const uint8_t* __restrict__ text, const PrepChunk* __restrict__ chunks, u
                     head_skip = 0;
                 }
                 __syncwarp();
+            } else {
+                const bool conv = st[0] == st[1];
+                const uint32_t kept = __popc(~delf[0] & 0x80808080u) + __popc(~delf[1] & 0x80808080u) +
+                                      __popc(~delf[2] & 0x80808080u) + __popc(~delf[3] & 0x80808080u);
+                if (conv && st[0] == 0 && !any_gt) {
+                    lane_emit[0] += kept;
+                    lane_emit[1] += kept;
+                } else if (conv && st[0] == 1 && !any_nl) {
+                } else if (!conv && !any_gt && !any_nl) {
+                    lane_emit[1] += kept;  // entered in B: body so far; entered in H: still in the label
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t g4 = flags_to_mask4(gtf[j]), n4 = flags_to_mask4(nlf[j]), d4 = flags_to_mask4(delf[j]);
+                        if (st[0] == st[1]) {
+                            const RowOut r = prep_row(g4, n4, d4, st[0], 1);
+                            st[0] = st[1] = r.state;
+                            emit[0] += r.emit;
+                            emit[1] += r.emit;
+                            ends[0] += r.ends;
+                            ends[1] += r.ends;
+                        } else {
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const RowOut r = prep_row(g4, n4, d4, st[h], 1);
+                                st[h] = r.state;
+                                emit[h] += r.emit;
+                                ends[h] += r.ends;
+                            }
+                        }
+                    }
+                }
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) w[j] = wn[j];
@@ -242,14 +345,20 @@ k_prep(const uint8_t* __restrict__ text, const PrepChunk* __restrict__ chunks, u
         if (WRITE) {
             if (lane < fill && lane >= head_skip) out[gbase + lane] = stage[lane];
             __syncwarp();
-        } else if (lane == 0) {
-            PrepSum s;
-            for (int h = 0; h < 2; ++h) {
-                s.emit[h] = emit[h];
-                s.ends[h] = ends[h];
-                s.exit_state[h] = st[h];
+        } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int d = 16; d; d >>= 1) lane_emit[h] += __shfl_xor_sync(0xffffffffu, lane_emit[h], d);
+            if (lane == 0) {
+                PrepSum s;
+                for (int h = 0; h < 2; ++h) {
+                    s.emit[h] = emit[h] + lane_emit[h];
+                    s.ends[h] = ends[h];
+                    s.exit_state[h] = st[h];
+                }
+                sums[ci] = s;
             }
-            sums[ci] = s;
         }
     }
 }
@@ -309,7 +418,23 @@ int dvs_prep_fasta(dvs_ctx* ctx, const uint8_t* text, const uint64_t* file_offse
     for (const char* d = delete_chars; *d; ++d) table[(uint8_t)*d] |= F_DEL;
     table[(uint8_t)'\n'] |= F_NL;
     table[(uint8_t)'>'] |= F_GT;
-    const uint32_t sep_code = code[(uint8_t)sep_char];
+    PrepParams prm{};
+    prm.sep_code = code[(uint8_t)sep_char];
+    {
+        // SWAR fast path: four upper-case letters with distinct ((c >> 1) & 3), kept (not deleted), every
+        // deleted byte and '>' below 0x40, and '\n' deleted.  Otherwise every byte takes the table.
+        bool ok = na >= 4 && (table[(uint8_t)'\n'] & F_DEL);
+        uint32_t seen = 0;
+        for (int i = 0; i < 4 && ok; ++i) {
+            const uint8_t c = (uint8_t)alphabet[i];
+            ok = c >= 'A' && c <= 'Z' && !(table[c] & F_DEL) && !(table[c | 0x20] & F_DEL) && !(seen & (1u << ((c >> 1) & 3)));
+            seen |= 1u << ((c >> 1) & 3);
+            prm.letters |= (uint32_t)c << (8 * ((c >> 1) & 3));
+            prm.codes |= (uint32_t)code[c] << (8 * ((c >> 1) & 3));
+        }
+        for (int b = 0x40; b < 256 && ok; ++b) ok = !(table[b] & (F_DEL | F_GT | F_NL));
+        prm.swar = ok ? 1u : 0u;
+    }
 
     DVS_CUDA_TRY(dvs::enter(ctx));
     cudaStream_t st = ctx->stream;
@@ -362,7 +487,7 @@ int dvs_prep_fasta(dvs_ctx* ctx, const uint8_t* text, const uint64_t* file_offse
     PhaseTimer pt(ctx, DVS_PHASE_PREP);
     if (nfiles) {
         if (nchunks) {
-            k_prep<false><<<grid, kPrepThreads, 0, st>>>(dtext, d_chunks.p, nchunks, d_table.p, sep_code, d_sums.p,
+            k_prep<false><<<grid, kPrepThreads, 0, st>>>(dtext, d_chunks.p, nchunks, d_table.p, prm, d_sums.p,
                                                          nullptr, nullptr, nullptr);
             DVS_LAUNCHED(ctx);
         }
@@ -376,7 +501,7 @@ int dvs_prep_fasta(dvs_ctx* ctx, const uint8_t* text, const uint64_t* file_offse
     dvs_seqset* s = nullptr;
     DVS_TRY(dvs_seqset_alloc_internal(ctx, rec_offsets.data(), nfiles, &s));
     if (nchunks && s->total) {
-        k_prep<true><<<grid, kPrepThreads, 0, st>>>(dtext, d_chunks.p, nchunks, d_table.p, sep_code, nullptr, d_carry.p,
+        k_prep<true><<<grid, kPrepThreads, 0, st>>>(dtext, d_chunks.p, nchunks, d_table.p, prm, nullptr, d_carry.p,
                                                     s->offsets.p, s->data());
         ctx->launches++;
         cudaError_t e = cudaGetLastError();
