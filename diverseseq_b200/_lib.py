@@ -18,6 +18,7 @@ DVS_OK, DVS_ERR_VALUE, DVS_ERR_CUDA, DVS_ERR_ARG = 0, 1, 2, 3
 MODE_NMOST, MODE_MAX_STDEV, MODE_MAX_COV = 0, 1, 2
 PHASE_COUNT_KERNEL, PHASE_FREQ_ENTROPY, PHASE_SELECT, PHASE_SKETCH, PHASE_MASH_PAIRS, PHASE_EUCLID, PHASE_UPLOAD = range(7)
 PHASE_PREP = 7
+PHASE_CLUSTER = 8
 
 _vp = C.c_void_p
 _u32, _u64, _i32, _f64 = C.c_uint32, C.c_uint64, C.c_int, C.c_double
@@ -43,6 +44,7 @@ SIGNATURES = {
     "dvs_seqset_offsets": (_i32, [_vp, _vp]),
     "dvs_seqset_download": (_i32, [_vp, _vp, _u32, _u32, _vp]),
     "dvs_seqset_free": (None, [_vp]),
+    "dvs_linkage_average": (_i32, [_vp, _vp, _u32, _vp, _vp, _vp]),
     "dvs_prep_fasta": (_i32, [_vp, _vp, _vp, _u32, C.c_char_p, C.c_char_p, _i32, _i32, C.POINTER(_vp)]),
     "dvs_count_kmers": (_i32, [_vp, _vp, _i32, _i32, C.POINTER(_vp)]),
     "dvs_kfreqs_from_rows": (_i32, [_vp, _vp, _vp, _u32, _u64, C.POINTER(_vp)]),
@@ -373,6 +375,11 @@ class KFreqs(_Handle):
         check(self.ctx._lib.dvs_euclid_distances(self.ctx.handle, self.handle, row_begin, row_end, ptr(out)))
         return out
 
+    def euclidean_into(self, device_ptr: int, row_begin: int = 0, row_end: int | None = None) -> None:
+        """same matrix written to device memory at `device_ptr` ((row_end-row_begin) x nrec f64)"""
+        row_end = self.nrec if row_end is None else row_end
+        check(self.ctx._lib.dvs_euclid_distances(self.ctx.handle, self.handle, row_begin, row_end, _vp(device_ptr)))
+
 
 class Summed(_Handle):
     """Device-resident SummedRecords state (dvs_summed)."""
@@ -456,6 +463,29 @@ class Sketches(_Handle):
         check(self.ctx._lib.dvs_mash_distances(self.ctx.handle, self.handle, int(k), int(sketch_size), row_begin,
                                                row_end, ptr(dist), ptr(inter), ptr(uni)))
         return (dist, inter, uni) if want_counts else dist
+
+    def distances_into(self, device_ptr: int, k: int, sketch_size: int) -> None:
+        """the full nrec x nrec f64 matrix written to device memory at `device_ptr`"""
+        check(self.ctx._lib.dvs_mash_distances(self.ctx.handle, self.handle, int(k), int(sketch_size), 0, self.nrec,
+                                               _vp(device_ptr), None, None))
+
+
+def linkage_average(ctx: Context, dist=None, n: int | None = None, device_ptr: int | None = None):
+    """children_ (n-1, 2), merge heights and cluster sizes of the average-linkage tree of an n x n
+    distance matrix held in a numpy array or in device memory (dvs_linkage_average)"""
+    if device_ptr is None:
+        dist = np.ascontiguousarray(dist, dtype=np.float64)
+        if dist.ndim != 2 or dist.shape[0] != dist.shape[1]:
+            raise ValueError("distance matrix must be square")
+        n, dp = dist.shape[0], ptr(dist)
+    else:
+        dp = _vp(device_ptr)
+    m = max(int(n) - 1, 0)
+    children = np.zeros((m, 2), dtype=np.int32)
+    heights = np.zeros(m, dtype=np.float64)
+    counts = np.zeros(m, dtype=np.uint32)
+    check(ctx._lib.dvs_linkage_average(ctx.handle, dp, int(n), ptr(children), ptr(heights), ptr(counts)))
+    return children, heights, counts
 
 
 def debug_log2(ctx: Context, x: np.ndarray) -> np.ndarray:

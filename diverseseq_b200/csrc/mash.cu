@@ -612,9 +612,9 @@ int dvs_mash_distances(dvs_ctx* ctx, const dvs_sketches* sk, int k, uint64_t ske
     pt.stop();
     DVS_LAUNCHED(ctx);
     int h_err = 0;
-    DVS_CUDA_TRY(cudaMemcpyAsync(dist, d_dist.p, total * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (inter) DVS_CUDA_TRY(cudaMemcpyAsync(inter, d_inter.p, total * 4, cudaMemcpyDeviceToHost, st));
-    if (uni) DVS_CUDA_TRY(cudaMemcpyAsync(uni, d_uni.p, total * 4, cudaMemcpyDeviceToHost, st));
+    DVS_CUDA_TRY(cudaMemcpyAsync(dist, d_dist.p, total * sizeof(double), cudaMemcpyDefault, st));
+    if (inter) DVS_CUDA_TRY(cudaMemcpyAsync(inter, d_inter.p, total * 4, cudaMemcpyDefault, st));
+    if (uni) DVS_CUDA_TRY(cudaMemcpyAsync(uni, d_uni.p, total * 4, cudaMemcpyDefault, st));
     DVS_CUDA_TRY(cudaMemcpyAsync(&h_err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     DVS_CUDA_TRY(cudaStreamSynchronize(st));
     if (h_err) {

@@ -88,45 +88,44 @@ __device__ __forceinline__ uint32_t nz_flags(uint32_t x) {
 __device__ __forceinline__ uint32_t flags_to_mask4(uint32_t f) { return (((f >> 7) * 0x01020408u) >> 24) & 0xFu; }
 __device__ __forceinline__ uint32_t mask4_to_flags(uint32_t m) { return ((m * 0x00204081u) & 0x01010101u) << 7; }
 
-// Classes of the four bytes of `w` as 0x80-per-byte flags: deleted, '>' and '\n'; with CODES also the
-// output codes.  Fast classification (p.swar): canonical letters in either case are recognised with a
-// PRMT lookup keyed by bits 1-2 of the byte, '\n' by a SWAR compare; any other byte goes through the
-// 256-entry table in shared memory.
-template <bool CODES>
-__device__ __forceinline__ void classify(uint32_t w, const uint16_t* tab, const PrepParams& p, uint32_t& codes,
-                                         uint32_t& delf, uint32_t& gtf, uint32_t& nlf) {
-    uint32_t other;
-    delf = gtf = nlf = 0;
+// Classes of the four bytes of `w` as 0x80-per-byte flags: deleted and '\n' (nlf, also deleted), plus
+// `other` = bytes that need the 256-entry table.  SWAR form: with CODES, canonical letters of either
+// case are recognised and translated by two PRMT lookups keyed by bits 1-2 of the byte; without, only
+// bytes < 0x40 can be deleted or special at all.  '\n' is found by a SWAR compare.  Branch-free.
+template <bool CODES, bool SWAR>
+__device__ __forceinline__ void classify(uint32_t w, const PrepParams& p, uint32_t& codes, uint32_t& nlf,
+                                         uint32_t& other) {
     codes = 0;
-    if (p.swar) {
-        if (CODES) {
-            const uint32_t u = w & 0xDFDFDFDFu;
-            const uint32_t x = (u >> 1) & 0x03030303u;
-            uint32_t sel = (x & 0x00030003u) | ((x >> 4) & 0x00300030u);
-            sel = (sel | (sel >> 8)) & 0x3333u;
-            other = nz_flags(__byte_perm(p.letters, 0, sel) ^ u);
-            codes = __byte_perm(p.codes, 0, sel);
-        } else {
-            other = ~w & (~w << 1) & 0x80808080u;  // bytes < 0x40: the only ones that can be deleted or special
-        }
-        if (other) {
-            nlf = ~nz_flags(w ^ 0x0A0A0A0Au) & 0x80808080u;
-            delf = nlf;
-            other &= ~nlf;
-        }
-    } else {
+    if (!SWAR) {
+        nlf = 0;
         other = 0x80808080u;
+        return;
     }
-    if (other) {
+    nlf = ~nz_flags(w ^ 0x0A0A0A0Au) & 0x80808080u;
+    if (CODES) {
+        const uint32_t u = w & 0xDFDFDFDFu;
+        const uint32_t x = (u >> 1) & 0x03030303u;
+        uint32_t sel = (x & 0x00030003u) | ((x >> 4) & 0x00300030u);
+        sel = (sel | (sel >> 8)) & 0x3333u;
+        other = nz_flags(__byte_perm(p.letters, 0, sel) ^ u) & ~nlf;
+        codes = __byte_perm(p.codes, 0, sel);
+    } else {
+        other = ~w & (~w << 1) & 0x80808080u & ~nlf;  // bytes < 0x40 are the only deleted / special ones
+    }
+}
+
+// table lookups for the bytes flagged in `other` (rare: labels, ambiguity codes, CR, blanks)
+template <bool CODES>
+__device__ __forceinline__ void classify_table(uint32_t w, uint32_t other, const uint16_t* tab, uint32_t& codes,
+                                               uint32_t& delf, uint32_t& gtf, uint32_t& nlf) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (other & (0x80u << (8 * i))) {
-                const uint32_t e = tab[(w >> (8 * i)) & 0xFFu];
-                if (CODES) codes = (codes & ~(0xFFu << (8 * i))) | ((e & 0xFFu) << (8 * i));
-                delf |= ((e >> 8) & 1u) << (8 * i + 7);
-                gtf |= ((e >> 9) & 1u) << (8 * i + 7);
-                nlf |= ((e >> 10) & 1u) << (8 * i + 7);
-            }
+    for (int i = 0; i < 4; ++i) {
+        if (other & (0x80u << (8 * i))) {
+            const uint32_t e = tab[(w >> (8 * i)) & 0xFFu];
+            if (CODES) codes = (codes & ~(0xFFu << (8 * i))) | ((e & 0xFFu) << (8 * i));
+            delf |= ((e >> 8) & 1u) << (8 * i + 7);
+            gtf |= ((e >> 9) & 1u) << (8 * i + 7);
+            nlf |= ((e >> 10) & 1u) << (8 * i + 7);
         }
     }
 }
@@ -184,7 +183,7 @@ __device__ __forceinline__ RowOut prep_row(uint32_t gt4, uint32_t nl4, uint32_t 
     return r;
 }
 
-template <bool WRITE>
+template <bool WRITE, bool SWAR>
 __global__ void __launch_bounds__(kPrepThreads)
 k_prep(const uint8_t* __restrict__ text, const PrepChunk* __restrict__ chunks, uint32_t nchunks,
        const uint16_t* __restrict__ table, PrepParams prm, PrepSum* __restrict__ sums,
@@ -201,7 +200,8 @@ k_prep(const uint8_t* __restrict__ text, const PrepChunk* __restrict__ chunks, u
         const PrepChunk ch = chunks[ci];
         const uint64_t row0 = ch.begin & ~127ull;
         const uint32_t rel_begin = (uint32_t)(ch.begin - row0), rel_end = rel_begin + ch.len;  // bytes from row0
-        const uint32_t nrows = (rel_end + 127) >> 7;
+        const uint32_t nsteps = (rel_end + 511) >> 9;                                       // 512-byte steps
+        const uint32_t s_lo = rel_begin ? 1u : 0u, s_hi = rel_end >> 9;  // steps [s_lo, s_hi) lie fully inside
         const uint8_t* base = text + row0 + 4 * lane;
         // WRITE: the real entry state in [0]; else both hypotheses ([0]: entered in H, [1]: entered in B)
         uint32_t st[2] = {1u, 0u}, emit[2] = {0, 0}, ends[2] = {0, 0};
@@ -217,24 +217,39 @@ k_prep(const uint8_t* __restrict__ text, const PrepChunk* __restrict__ chunks, u
             fill = head_skip = (uint32_t)(o0 & 15);
         }
         uint32_t w[4], wn[4];
-        auto load_step = [&](uint32_t row, uint32_t* dst) {
+        auto load_step = [&](uint32_t s, uint32_t* dst) {
+            const uint8_t* q0 = base + ((uint64_t)s << 9);
+            if (s >= s_lo && s < s_hi) {  // warp-uniform: no guards
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t q = ((row + j) << 7) + 4 * lane;  // offset of the lane's word from row0
-                dst[j] = (q + 4 > rel_begin && q < rel_end) ? __ldg(reinterpret_cast<const uint32_t*>(base + ((row + j) << 7)))
-                                                            : 0u;
+                for (int j = 0; j < 4; ++j) dst[j] = __ldg(reinterpret_cast<const uint32_t*>(q0 + 128 * j));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t q = (s << 9) + 128 * j + 4 * lane;  // offset of the lane's word from row0
+                    dst[j] = (s < nsteps && q + 4 > rel_begin && q < rel_end)
+                                 ? __ldg(reinterpret_cast<const uint32_t*>(q0 + 128 * j))
+                                 : 0u;
+                }
             }
         };
         load_step(0, w);
-        for (uint32_t row = 0; row < nrows; row += 4) {
-            load_step(row + 4, wn);  // next step in flight while this one is processed
-            uint32_t codes[4], delf[4], gtf[4], nlf[4];
-            const bool inside = (row << 7) >= rel_begin && ((row + 4) << 7) <= rel_end;  // warp-uniform
+        for (uint32_t s = 0; s < nsteps; ++s) {
+            load_step(s + 1, wn);  // next step in flight while this one is processed
+            uint32_t codes[4], delf[4], gtf[4], nlf[4], other[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                classify<WRITE>(w[j], tab, prm, codes[j], delf[j], gtf[j], nlf[j]);
-                if (!inside) {  // bytes outside [begin, end) count as deleted
-                    const uint32_t q = ((row + j) << 7) + 4 * lane;
+                classify<WRITE, SWAR>(w[j], prm, codes[j], nlf[j], other[j]);
+                delf[j] = nlf[j];
+                gtf[j] = 0;
+            }
+            if (other[0] | other[1] | other[2] | other[3]) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) classify_table<WRITE>(w[j], other[j], tab, codes[j], delf[j], gtf[j], nlf[j]);
+            }
+            if (!(s >= s_lo && s < s_hi)) {  // warp-uniform: bytes outside [begin, end) count as deleted
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t q = (s << 9) + 128 * j + 4 * lane;
                     uint32_t valid = 0;
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
@@ -246,8 +261,8 @@ k_prep(const uint8_t* __restrict__ text, const PrepChunk* __restrict__ chunks, u
             }
             const uint32_t any_gt = __ballot_sync(0xffffffffu, (gtf[0] | gtf[1] | gtf[2] | gtf[3]) != 0);
             const uint32_t any_nl = __ballot_sync(0xffffffffu, (nlf[0] | nlf[1] | nlf[2] | nlf[3]) != 0);
-            uint32_t outf[4];  // WRITE: bytes of the step that produce output
             if (WRITE) {
+                uint32_t outf[4];  // bytes of the step that produce output
                 if (st[0] == 0 && !any_gt) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) outf[j] = ~delf[j] & 0x80808080u;
@@ -280,10 +295,17 @@ k_prep(const uint8_t* __restrict__ text, const PrepChunk* __restrict__ chunks, u
                 uint32_t rowbase = fill;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    uint32_t pos = rowbase + ((excl >> (8 * j)) & 0xFFu);
+                    uint8_t* dst = stage + rowbase + ((excl >> (8 * j)) & 0xFFu);
+                    if (outf[j] == 0x80808080u) {  // the common word: nothing deleted
+                        dst[0] = (uint8_t)codes[j];
+                        dst[1] = (uint8_t)(codes[j] >> 8);
+                        dst[2] = (uint8_t)(codes[j] >> 16);
+                        dst[3] = (uint8_t)(codes[j] >> 24);
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if (outf[j] & (0x80u << (8 * i))) stage[pos++] = (uint8_t)(codes[j] >> (8 * i));
+                        for (int i = 0; i < 4; ++i)
+                            if (outf[j] & (0x80u << (8 * i))) *dst++ = (uint8_t)(codes[j] >> (8 * i));
+                    }
                     rowbase += (tot >> (8 * j)) & 0xFFu;
                 }
                 fill = rowbase;
@@ -351,13 +373,13 @@ k_prep(const uint8_t* __restrict__ text, const PrepChunk* __restrict__ chunks, u
 #pragma unroll
                 for (int d = 16; d; d >>= 1) lane_emit[h] += __shfl_xor_sync(0xffffffffu, lane_emit[h], d);
             if (lane == 0) {
-                PrepSum s;
+                PrepSum sm;
                 for (int h = 0; h < 2; ++h) {
-                    s.emit[h] = emit[h] + lane_emit[h];
-                    s.ends[h] = ends[h];
-                    s.exit_state[h] = st[h];
+                    sm.emit[h] = emit[h] + lane_emit[h];
+                    sm.ends[h] = ends[h];
+                    sm.exit_state[h] = st[h];
                 }
-                sums[ci] = s;
+                sums[ci] = sm;
             }
         }
     }
@@ -487,8 +509,12 @@ int dvs_prep_fasta(dvs_ctx* ctx, const uint8_t* text, const uint64_t* file_offse
     PhaseTimer pt(ctx, DVS_PHASE_PREP);
     if (nfiles) {
         if (nchunks) {
-            k_prep<false><<<grid, kPrepThreads, 0, st>>>(dtext, d_chunks.p, nchunks, d_table.p, prm, d_sums.p,
-                                                         nullptr, nullptr, nullptr);
+            if (prm.swar)
+                k_prep<false, true><<<grid, kPrepThreads, 0, st>>>(dtext, d_chunks.p, nchunks, d_table.p, prm, d_sums.p,
+                                                                   nullptr, nullptr, nullptr);
+            else
+                k_prep<false, false><<<grid, kPrepThreads, 0, st>>>(dtext, d_chunks.p, nchunks, d_table.p, prm, d_sums.p,
+                                                                    nullptr, nullptr, nullptr);
             DVS_LAUNCHED(ctx);
         }
         k_prep_carry<<<(nfiles + 127) / 128, 128, 0, st>>>(d_sums.p, d_first.p, nfiles, d_carry.p, d_len.p);
@@ -501,8 +527,12 @@ int dvs_prep_fasta(dvs_ctx* ctx, const uint8_t* text, const uint64_t* file_offse
     dvs_seqset* s = nullptr;
     DVS_TRY(dvs_seqset_alloc_internal(ctx, rec_offsets.data(), nfiles, &s));
     if (nchunks && s->total) {
-        k_prep<true><<<grid, kPrepThreads, 0, st>>>(dtext, d_chunks.p, nchunks, d_table.p, prm, nullptr, d_carry.p,
-                                                    s->offsets.p, s->data());
+        if (prm.swar)
+            k_prep<true, true><<<grid, kPrepThreads, 0, st>>>(dtext, d_chunks.p, nchunks, d_table.p, prm, nullptr,
+                                                              d_carry.p, s->offsets.p, s->data());
+        else
+            k_prep<true, false><<<grid, kPrepThreads, 0, st>>>(dtext, d_chunks.p, nchunks, d_table.p, prm, nullptr,
+                                                               d_carry.p, s->offsets.p, s->data());
         ctx->launches++;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) {

@@ -67,6 +67,7 @@ uint64_t dvs_ctx_launch_count(dvs_ctx* ctx);
 #define DVS_PHASE_MASH_PAIRS 4     /* k_mash_pairs */
 #define DVS_PHASE_EUCLID 5         /* k_euclid_tiles */
 #define DVS_PHASE_UPLOAD 6         /* host->device sequence copy of dvs_seqset_upload */
+#define DVS_PHASE_CLUSTER 8        /* k_cl_symmetrise + k_cl_nn_chain of one dvs_linkage_average */
 #define DVS_PHASE_PREP 7           /* all device work of one dvs_prep_fasta (k_prep x2 + k_prep_carry) */
 /* bytes that actually crossed PCIe during the last dvs_seqset_upload (2-bit packed + exceptions for
  * large uploads, see csrc/upload.cu; equal to the input size for the plain copy) */
@@ -188,7 +189,8 @@ int dvs_sketches_download(dvs_ctx* ctx, const dvs_sketches* sk, uint32_t* sketch
                           uint32_t* lens);
 void dvs_sketches_free(dvs_sketches* sk);
 /* rows [row_begin,row_end) of the symmetric nrec x nrec matrix (2-D sharding hook); outputs are
- * (row_end-row_begin) x nrec, row-major; inter/uni may be NULL. */
+ * (row_end-row_begin) x nrec, row-major; inter/uni may be NULL.  The output pointers may be host or
+ * device memory (unified addressing). */
 int dvs_mash_distances(dvs_ctx* ctx, const dvs_sketches* sk, int k, uint64_t sketch_size, uint32_t row_begin,
                        uint32_t row_end, double* dist, uint32_t* inter, uint32_t* uni);
 /* host->host single record, mirrors _dvs.mash_sketch(seq_array, k, sketch_size, num_states, canonical) */
@@ -197,8 +199,19 @@ int dvs_mash_sketch_host(dvs_ctx* ctx, const uint8_t* seq, uint64_t len, int k, 
 
 /* ---- Euclidean k-mer distance matrix --------------------------------------------------------
  * euclidean_distances (diverse_seq/distance.py:294-336, cluster.py:647-680): ||f_i - f_j||_2 over
- * frequency rows, rows [row_begin,row_end) x all columns, zero diagonal. */
+ * frequency rows, rows [row_begin,row_end) x all columns, zero diagonal; `dist` may be host or device memory. */
 int dvs_euclid_distances(dvs_ctx* ctx, const dvs_kfreqs* f, uint32_t row_begin, uint32_t row_end, double* dist);
+
+/* ---- `dvs ctree` tail: average-linkage tree of a precomputed distance matrix -----------------
+ * Replaces sklearn AgglomerativeClustering(metric="precomputed", linkage="average").fit(D) in
+ * make_cluster_tree (diverse_seq/cluster.py:191-237), i.e. scipy's nearest-neighbour-chain linkage on
+ * the upper triangle of D followed by its stable sort and relabelling.  dist: n x n row-major f64 on
+ * the host OR the device (e.g. straight from dvs_euclid_distances / dvs_mash_distances, which accept
+ * device output pointers too).  children: (n-1) x 2, identical to sklearn's children_ (values < n are
+ * leaves, n + i is the cluster made by row i); heights / counts (may be NULL): merge distance and
+ * cluster size per row. */
+int dvs_linkage_average(dvs_ctx* ctx, const double* dist, uint32_t n, int32_t* children, double* heights,
+                        uint32_t* counts);
 
 /* ---- test hooks ---------------------------------------------------------------------------- */
 /* host half of the packed upload (transfer encoding, no GPU needed): packs src[0..n) 4 bases per

@@ -408,14 +408,14 @@ DNA_ALPHABET = "TCAG-NRYWSKMBDHV?"
 _FASTA_DELETE = b"\n\r\t- "
 
 
-def _converter_fasta(body: bytes) -> bytes:
+def _converter_fasta(body: bytes, delete: bytes = _FASTA_DELETE) -> bytes:
     import string
 
     table = bytes.maketrans(string.ascii_lowercase.encode(), string.ascii_uppercase.encode())
-    return body.translate(table, delete=_FASTA_DELETE)
+    return body.translate(table, delete=delete)
 
 
-def iter_fasta_records(data: bytes):
+def iter_fasta_records(data: bytes, delete: bytes = _FASTA_DELETE):
     """(label, converted sequence bytes) of every '>'-delimited piece that has a label line"""
     for piece in data.split(b">"):
         if not piece:
@@ -423,12 +423,81 @@ def iter_fasta_records(data: bytes):
         eol = piece.find(b"\n")
         if eol == -1:
             continue
-        yield piece[:eol].strip().decode("utf8", errors="replace"), _converter_fasta(piece[eol + 1:])
+        yield piece[:eol].strip().decode("utf8", errors="replace"), _converter_fasta(piece[eol + 1:], delete)
 
 
-def prep_fasta(data: bytes, alphabet: str = DNA_ALPHABET) -> np.ndarray:
+def prep_fasta(data: bytes, alphabet: str = DNA_ALPHABET, delete: bytes = _FASTA_DELETE) -> np.ndarray:
     """index-encoded record of one FASTA file (all its sequences joined with '-')"""
-    joined = b"-".join(seq for _, seq in iter_fasta_records(data))
+    joined = b"-".join(seq for _, seq in iter_fasta_records(data, delete))
     chars = alphabet.encode()
     table = bytes.maketrans(chars, bytes(range(len(chars))))  # bytes outside the alphabet map to themselves
     return np.frombuffer(joined.translate(table), dtype=np.uint8).copy()
+
+
+# ---- average-linkage tree (SURVEY.md §8(f) rank 4) ----------------------------------------------
+# Restatement of what diverse_seq/cluster.py:191-237 (make_cluster_tree) gets from
+# sklearn.cluster.AgglomerativeClustering(metric="precomputed", linkage="average").children_:
+# scipy's nn_chain + stable sort + label() on the upper triangle.  PINNED: tests/test_cluster.py checks
+# it against scikit-learn itself (installed here and on the GPU box; it is the reference's own
+# dependency), ties included.
+def linkage_average(dist: np.ndarray):
+    """(children (n-1,2) int, heights (n-1,), counts (n-1,)) of a symmetric n x n distance matrix"""
+    d = np.array(dist, dtype=np.float64)
+    n = d.shape[0]
+    iu = np.triu_indices(n, 1)
+    w = np.zeros((n, n))
+    w[iu] = d[iu]
+    w = w + w.T  # exact: one of the two addends is 0.0
+    size = np.ones(n, dtype=np.int64)
+    chain, merges = [], []
+    for _ in range(n - 1):
+        if not chain:
+            chain.append(int(np.flatnonzero(size > 0)[0]))
+        while True:
+            x = chain[-1]
+            if len(chain) > 1:
+                y = chain[-2]
+                cur = w[x, y]
+            else:
+                y, cur = -1, np.inf
+            row = np.where((size > 0) & (np.arange(n) != x), w[x], np.inf)
+            i = int(np.argmin(row))  # first index of the minimum
+            if row[i] < cur:
+                cur, y = row[i], i
+            if len(chain) > 1 and y == chain[-2]:
+                break
+            chain.append(y)
+        chain.pop()
+        chain.pop()
+        if x > y:
+            x, y = y, x
+        nx, ny = int(size[x]), int(size[y])
+        merges.append((x, y, float(cur), nx + ny))
+        size[x] = 0
+        size[y] = nx + ny
+        live = (size > 0) & (np.arange(n) != y)
+        new = (nx * w[live, x] + ny * w[live, y]) / (nx + ny)
+        w[live, y] = new
+        w[y, live] = new
+    order = sorted(range(n - 1), key=lambda r: merges[r][2])  # sorted() is stable
+    parent = list(range(2 * n - 1))
+    csize = [1] * (2 * n - 1)
+
+    def find(a):
+        while parent[a] != a:
+            a = parent[a]
+        return a
+
+    children = np.zeros((n - 1, 2), dtype=np.int64)
+    heights = np.zeros(n - 1)
+    counts = np.zeros(n - 1, dtype=np.int64)
+    nxt = n
+    for r, idx in enumerate(order):
+        x, y, h, _ = merges[idx]
+        xr, yr = find(x), find(y)
+        children[r] = (min(xr, yr), max(xr, yr))
+        parent[xr] = parent[yr] = nxt
+        csize[nxt] = csize[xr] + csize[yr]
+        heights[r], counts[r] = h, csize[nxt]
+        nxt += 1
+    return children, heights, counts

@@ -47,16 +47,16 @@ def ctx():
     return _lib.Context(0)
 
 
-def _check(ctx, blobs):
+def _check(ctx, blobs, alphabet=None, delete=None):
     from diverseseq_b200 import _lib
 
     text, offsets = _lib.concat([np.frombuffer(b, dtype=np.uint8) for b in blobs])
-    ss = _lib.SeqSet.prep_fasta(ctx, text, offsets)
+    ss = _lib.SeqSet.prep_fasta(ctx, text, offsets, alphabet=alphabet, delete_chars=delete)
     off = ss.offsets()
     flat = ss.download()
     assert ss.nrec == len(blobs)
     for i, b in enumerate(blobs):
-        want = oracle.prep_fasta(b)
+        want = oracle.prep_fasta(b, alphabet or oracle.DNA_ALPHABET, delete or b"\n\r\t- ")
         got = flat[int(off[i]):int(off[i + 1])]
         assert got.size == want.size, (i, got.size, want.size, b[:80])
         bad = np.flatnonzero(got != want)
@@ -97,6 +97,17 @@ def test_prep_fuzz_vs_oracle(ctx, p_gt, p_nl):
     rng = np.random.default_rng(int(p_gt * 1e6) * 7919 + int(p_nl * 1e6) + 5)
     sizes = [0, 1, 3, 4, 5, 127, 128, 129, 511, 513, 4097, 32767, 32768, 32769, 65536, 100_003, 300_001]
     _check(ctx, [_fuzz(rng, n, p_gt, p_nl) for n in sizes])
+
+
+@gpu
+@pytest.mark.parametrize("alphabet,delete", [("ABCD-", None), ("TCAG-N", b"\n\r\t- Xx"), ("TCAG", b"\r\t "),
+                                             ("GATC-", b"\n")])
+def test_prep_table_only_path(ctx, alphabet, delete):
+    """alphabets / delete sets the SWAR classification cannot serve run every byte through the table"""
+    rng = np.random.default_rng(17)
+    blobs = [_fuzz(rng, n, 0.01, 0.02) for n in (0, 5, 600, 40_000, 70_001)]
+    blobs.append(b">a\nABCDabcdXx-\n>b\nTCAGtcag\n")
+    _check(ctx, blobs, alphabet, delete)
 
 
 @gpu

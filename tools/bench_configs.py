@@ -7,6 +7,7 @@
   max     configs[2]: dvs max (min/max size sweep), k=8, 10.5k genomes
   mash    configs[3]: ctree mash distance k=16 sketch 3000, 1k genomes (sketch Gbp/s, pairs/s)
   euclid  configs[4]: ctree Euclidean k=8, 10.5k genomes (pairs/s, FP64 TFLOP/s)
+  cluster ctree tail: average-linkage tree of the 10.5k x 10.5k Euclidean matrix (device) vs scikit-learn (host)
   count12 north-star headline: k-mer counting at k=12 (Gbp/s); dense u32 rows, few records at a time
 """
 from __future__ import annotations
@@ -27,7 +28,7 @@ SEED = 20261017
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true", help="1/10 size (smoke)")
-    ap.add_argument("--only", default="max,mash,euclid,count12")
+    ap.add_argument("--only", default="max,mash,euclid,cluster,count12")
     a = ap.parse_args()
     import os
 
@@ -155,6 +156,30 @@ def main() -> int:
              fp64_tflops_useful=2.0 * dim * npairs / eu_ms / 1e9,  # 2*D flops per pair
              fp64_tflops_issued=3.0 * dim * (npairs + nrec / 2) / eu_ms / 1e9, mean_dist=float(d.mean()))
         del kf, ss
+
+    if "cluster" in which:
+        import torch
+
+        nrec, mean_len, k = 10500 // scale, 100_000, 6  # the tree only needs the matrix
+        ss = _lib.SeqSet.synth(ctx, SEED, nrec, 64, mean_len)
+        kf = _lib.KFreqs.count(ctx, ss, k)
+        dmat = torch.empty((nrec, nrec), dtype=torch.float64, device="cuda:0")
+        kf.euclidean_into(dmat.data_ptr())
+        for _ in range(2):
+            t0 = time.perf_counter()
+            children, heights, counts = _lib.linkage_average(ctx, n=nrec, device_ptr=dmat.data_ptr())
+            t_gpu = time.perf_counter() - t0
+        cl_ms = ctx.phase_ms(_lib.PHASE_CLUSTER)
+        host = dmat.cpu().numpy()
+        from sklearn.cluster import AgglomerativeClustering
+
+        t0 = time.perf_counter()
+        ref = AgglomerativeClustering(metric="precomputed", linkage="average").fit(host)
+        t_ref = time.perf_counter() - t0
+        emit(config="ctree tail: average-linkage tree", nrec=nrec, device_ms=cl_ms, wall_s=t_gpu,
+             sklearn_wall_s=t_ref, identical_children=bool(np.array_equal(children, ref.children_)),
+             note="sklearn time excludes the 882 MB device->host copy the device path avoids")
+        del kf, ss, dmat
 
     if "count12" in which:
         k = 12
