@@ -118,7 +118,7 @@ k_count_generic(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ o
 // Each warp walks a contiguous span of its work item in 512-byte steps (lane l owns bytes
 // [16l,16l+16)); the k-byte halo of lane l is the packed block of lane l-1 (warp shuffle), lane 0
 // keeps lane 31's block of the previous step, so every sequence byte is loaded exactly once.
-constexpr int MODE_SMEM = 0, MODE_SMEM_PARTS = 1, MODE_GLOBAL = 2, MODE_SUPER = 3;
+constexpr int MODE_SMEM = 0, MODE_SMEM_PARTS = 1, MODE_GLOBAL = 2, MODE_SUPER = 3, MODE_SUPER3 = 4;
 
 // 16 packed bases from 16 bytes: four multiplies put each word's 8 bits in its top byte, three
 // PRMTs gather the top bytes (first base most significant)
@@ -139,9 +139,10 @@ template <int MODE, bool SCR, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k_count(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offsets, const CountWork* __restrict__ work,
         uint32_t nwork, uint32_t* __restrict__ next_item, int k, uint64_t dim, uint32_t part_bins,
-        uint32_t* __restrict__ counts) {
+        uint32_t* __restrict__ counts, const uint32_t* __restrict__ nwork_dev) {
     extern __shared__ uint32_t hist[];
     __shared__ uint32_t s_item;
+    if (nwork_dev) nwork = *nwork_dev;  // retry pass of k_count_s3: the list length only exists on the device
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int kWarps = THREADS / 32;
     constexpr uint32_t kFull = 0xffffffffu;
@@ -304,6 +305,209 @@ k_count(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offsets, 
                     if (c && (uint64_t)part_base + i < dim) atomicAdd(&grow[part_base + i], c);
                 }
             }
+        }
+        __syncthreads();  // s_item / hist reuse
+    }
+}
+
+// ---- MODE_SUPER3: (k+2)-mers at every THIRD position, 16-bit packed counters ------------------------
+// The k-mer kernels above sit on the shared-memory atomic rate (~4 bank-conflict wavefronts per ATOMS,
+// the floor for 32 random banks), so the remaining lever is fewer atomics per base.  Here the (k+2)-mer
+// ending at every absolute position p == 2 (mod 3) is histogrammed: it carries the three k-mers ending
+// at p-2, p-1 and p, i.e. one ATOMS per three bases (5.33 per 16-base block instead of 8).  4^(k+2)
+// counters only fit shared memory as 16-bit halves of 32-bit words (k = 6: 128 KB); a half can
+// overflow after 65,535 hits in one work item, which is detected exactly at the flush: every overflow
+// (carry into the neighbour half or out of the word) lowers the sum of all halves, so sum == number of
+// increments  <=>  no overflow.  An item that fails the check is not added; it is appended to a retry
+// list and recounted by the 32-bit (k+1)-mer kernel.
+// Ownership: the lane whose block contains p handles the triplet (the k-mers at p-2, p-1 may sit in the
+// previous block: they are in the halo).  Triplets cut by an invalid byte, the record start or a short
+// window fall back to single k-mers in the side table (per-byte path); a record that ends before its
+// last triplet completes flushes the pending k-mers at its last byte, so the block holding the last
+// byte always takes the per-byte path when end % 3 != 0.
+template <bool SCR, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+k_count_s3(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offsets, const CountWork* __restrict__ work,
+           uint32_t nwork, uint32_t* __restrict__ next_item, int k, uint64_t dim, uint32_t* __restrict__ counts,
+           CountWork* __restrict__ retry, uint32_t* __restrict__ retry_count) {
+    extern __shared__ uint32_t hist[];  // [4^(k+2) / 2] packed halves, then side[4^k]
+    __shared__ uint32_t s_item, s_sum, s_inc;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int kWarps = THREADS / 32;
+    constexpr uint32_t kFull = 0xffffffffu;
+    const int kk = k + 2;
+    const uint32_t mask = (1u << (2 * kk)) - 1u;  // kk <= 8
+    const uint32_t mask_k = (1u << (2 * k)) - 1u;
+    const uint32_t hwords = (uint32_t)(dim * 8);  // 4^(k+2) / 2
+    uint32_t* side = hist + hwords;
+    char* const hist_b = reinterpret_cast<char*>(hist);
+
+    for (;;) {
+        if (tid == 0) {
+            s_item = atomicAdd(next_item, 1u);
+            s_sum = 0;
+            s_inc = 0;
+        }
+        __syncthreads();
+        const uint32_t item = s_item;
+        if (item >= nwork) break;
+        const CountWork w = work[item];
+        const uint64_t start = offsets[w.rec], end = offsets[w.rec + 1];
+        uint32_t* grow = counts + (size_t)w.rec * dim;
+        {
+            uint4* h4 = reinterpret_cast<uint4*>(hist);
+            const uint32_t n4 = (hwords + (uint32_t)dim) / 4;  // both multiples of 4 for k >= 1
+            for (uint32_t i = tid; i < n4; i += THREADS) h4[i] = make_uint4(0, 0, 0, 0);
+        }
+        __syncthreads();
+        uint32_t n_inc = 0;
+        auto bump = [&](uint32_t y) {  // y = (k+2)-mer
+            uint32_t off = (y & ~1u) << 1;  // byte offset of its word
+            if (SCR) off ^= (off >> 5) & ~3u;
+            atomicAdd(reinterpret_cast<uint32_t*>(hist_b + off), 1u << ((y & 1u) << 4));
+        };
+
+        const uint32_t item_len = (uint32_t)(w.end - w.begin);
+        const uint32_t rs = start > w.begin ? (uint32_t)min(start - w.begin, (uint64_t)item_len) : 0u;
+        const uint32_t re = end < w.end ? (end > w.begin ? (uint32_t)(end - w.begin) : 0u) : item_len;
+        // the full block that holds the record's last byte must flush pending k-mers (per-byte path)
+        const uint32_t tail_a = (end > w.begin && end <= w.end && (end % 3ull) != 0 && re >= 16 && (re & 15u) == 0) ? re - 16 : 0xffffffffu;
+        const uint32_t span = ((item_len + kWarps - 1) / kWarps + 511u) & ~511u;
+        const uint32_t r0 = min(item_len, (uint32_t)warp * span);
+        const uint32_t r1 = min(item_len, r0 + span);
+        const uint8_t* base = seqs + w.begin;
+        uint32_t carry_pc = 0;
+        bool carry_ok = false;
+        // phase of the lane's block start (absolute position mod 3); 16 == 1 and 512 == 2 (mod 3)
+        uint32_t ph = (uint32_t)((w.begin + r0 + 16ull * lane) % 3ull);
+        uint4 ring[kPrefetch];
+#pragma unroll
+        for (int u = 0; u < kPrefetch; ++u) {
+            const uint32_t a = r0 + 512u * u + 16 * lane;
+            ring[u] = (a < r1) ? ldg16(base + a) : make_uint4(~0u, ~0u, ~0u, ~0u);
+        }
+        if (r0 < r1) {
+            const uint4 h = ldg16(base + r0 - 16);
+            const uint64_t a0 = w.begin + r0;
+            carry_ok = (((h.x | h.y | h.z | h.w) & 0xFCFCFCFCu) == 0) && (a0 >= start + 16) && (a0 <= end);
+            carry_pc = pack16p(h);
+        }
+        for (uint32_t rbase = r0; rbase < r1; rbase += 512u * kPrefetch) {
+#pragma unroll
+          for (int u = 0; u < kPrefetch; ++u) {
+            const uint32_t r = rbase + 512u * u;
+            if (r >= r1) break;  // warp-uniform
+            const uint32_t a = r + 16 * lane;
+            const uint4 cur = ring[u];
+            const bool ok = (((cur.x | cur.y | cur.z | cur.w) & 0xFCFCFCFCu) == 0) && (a >= rs) && (a + 16 <= re) &&
+                            (a < r1) && (a != tail_a);
+            const uint32_t pc = pack16p(cur);
+            // refill the slot only now: in the common path `cur` is dead from here on, so the load lands in
+            // the same registers without a copy (the per-byte path re-reads its 32 bytes)
+            ring[u] = (a + 512u * kPrefetch < r1) ? ldg16(base + a + 512u * kPrefetch) : make_uint4(~0u, ~0u, ~0u, ~0u);
+            uint32_t pp = __shfl_up_sync(kFull, pc, 1);
+            if (lane == 0) pp = carry_pc;
+            const uint32_t okmask = __ballot_sync(kFull, ok);
+            const bool prev_ok = lane == 0 ? carry_ok : ((okmask >> (lane - 1)) & 1u) != 0;
+            if (ok && prev_ok) {
+                // (k+2)-mers ending at j = j0, j0+3, ... (< 16), j0 = 2 - ph
+                uint32_t sh = 2u * (13u + ph);  // 2 * (15 - j0)
+#pragma unroll
+                for (int t = 0; t < 5; ++t) {
+                    bump(__funnelshift_r(pc, pp, sh) & mask);
+                    sh -= 6u;
+                }
+                if (ph == 2) bump(pc & mask);  // j0 = 0: a sixth one ends at j = 15
+                n_inc += 5u + (ph == 2 ? 1u : 0u);
+            } else if (a < r1) {
+                const uint4 prev = ldg16(base + a - 16), cur2 = ldg16(base + a);
+                const uint32_t wv[8] = {prev.x, prev.y, prev.z, prev.w, cur2.x, cur2.y, cur2.z, cur2.w};
+                uint32_t run = 0, idx = 0, run1 = 0, idx1 = 0, run2 = 0, idx2 = 0;
+                uint32_t pm = (ph + 2u) % 3u;  // phase of position a - 16
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const uint64_t p = w.begin + a + i - 16;
+                    uint32_t bb = (wv[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+                    if (p < start || p >= end) bb = 0xFFu;
+                    run2 = run1;
+                    idx2 = idx1;
+                    run1 = run;
+                    idx1 = idx;
+                    if (bb >= 4u) {
+                        run = 0;
+                        idx = 0;
+                    } else {
+                        idx = ((idx << 2) | bb) & mask;
+                        ++run;
+                    }
+                    if (i >= 16 && p < end) {  // (past the end nothing is pending: the last byte flushed it)
+                        if (pm == 2) {
+                            if (run >= (uint32_t)kk) {
+                                bump(idx);
+                                ++n_inc;
+                            } else {
+                                if (run2 >= (uint32_t)k) atomicAdd(&side[idx2 & mask_k], 1u);
+                                if (run1 >= (uint32_t)k) atomicAdd(&side[idx1 & mask_k], 1u);
+                                if (run >= (uint32_t)k) atomicAdd(&side[idx & mask_k], 1u);
+                            }
+                        } else if (p + 1 == end) {  // the record ends inside a triplet: flush what is pending
+                            if (pm == 1 && run1 >= (uint32_t)k) atomicAdd(&side[idx1 & mask_k], 1u);
+                            if (run >= (uint32_t)k) atomicAdd(&side[idx & mask_k], 1u);
+                        }
+                    }
+                    pm = pm == 2 ? 0u : pm + 1u;
+                }
+            }
+            carry_pc = __shfl_sync(kFull, pc, 31);
+            carry_ok = (okmask >> 31) != 0;
+            ph = ph == 0 ? 2u : ph - 1u;  // + 512 == + 2 (mod 3)
+          }
+        }
+        __syncthreads();
+        // fold: cnt[x] = side[x] + sum of the (k+2)-mers that hold x at offset 0, 1 or 2
+        uint32_t pre_sum = 0;
+        auto word_at = [&](uint32_t wd) { return hist[SCR ? (wd ^ (wd >> 5)) : wd]; };
+        for (uint32_t x = tid; x < (uint32_t)dim; x += THREADS) {
+            uint32_t c = side[x], pre = 0;
+#pragma unroll
+            for (uint32_t t = 0; t < 8; ++t) {  // x first: y = x * 16 + (0..15) = 8 whole words
+                const uint32_t v = word_at((x << 3) | t);
+                pre += (v & 0xFFFFu) + (v >> 16);
+            }
+            c += pre;
+            pre_sum += pre;
+#pragma unroll
+            for (uint32_t a4 = 0; a4 < 4; ++a4) {  // x in the middle: y = a | x | b
+#pragma unroll
+                for (uint32_t t = 0; t < 2; ++t) {
+                    const uint32_t v = word_at((a4 << (2 * k + 1)) | (x << 1) | t);
+                    c += (v & 0xFFFFu) + (v >> 16);
+                }
+            }
+#pragma unroll
+            for (uint32_t t = 0; t < 16; ++t) {  // x last: y = t * 4^k + x
+                const uint32_t v = word_at((t << (2 * k - 1)) | (x >> 1));
+                c += (x & 1u) ? (v >> 16) : (v & 0xFFFFu);
+            }
+            side[x] = c;  // thread-private slot until the overflow check has passed
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            pre_sum += __shfl_xor_sync(kFull, pre_sum, o);
+            n_inc += __shfl_xor_sync(kFull, n_inc, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&s_sum, pre_sum);
+            atomicAdd(&s_inc, n_inc);
+        }
+        __syncthreads();
+        if (s_sum == s_inc) {
+            for (uint32_t x = tid; x < (uint32_t)dim; x += THREADS) {
+                const uint32_t c = side[x];
+                if (c) atomicAdd(&grow[x], c);
+            }
+        } else if (tid == 0) {
+            retry[atomicAdd(retry_count, 1u)] = w;
         }
         __syncthreads();  // s_item / hist reuse
     }
@@ -482,7 +686,18 @@ int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dv
     uint32_t nparts = 1, part_bins = (uint32_t)std::min<uint64_t>(dim, 1u << 31);
     int mode = MODE_SMEM;
     size_t hist_bytes = (size_t)dim * 4;
-    if (ns4 && dim * 20 <= 96 * 1024) {  // (k+1)-mer table + side table: k <= 6 -> at most 80 KB
+    // DVS_COUNT_S3=1 selects the (k+2)-mer / 16-bit kernel for k = 4..6.  Off by default: it cuts the shared
+    // atomic wavefronts by 27 % but needs ~150 instructions per 512-byte step (runtime shifts, half select,
+    // address forming) and ends up issue-bound: 13.7 ms vs 11.2 ms for the (k+1)-mer kernel on the
+    // benchmark set (profiles/r1_ncu_k_count_s3.txt).
+    const char* s3_env = getenv("DVS_COUNT_S3");
+    const bool want_s3 = s3_env && s3_env[0] == '1';
+    if (ns4 && want_s3 && k >= 4 && dim * 36 + 2048 <= ctx->smem_optin && dim * 36 <= 160 * 1024) {
+        // (k+2)-mers at every third position, 16-bit packed counters + side table: k = 4..6 -> at most 144 KB.
+        // Smaller k would overflow the 16-bit halves routinely (4^(k+2) bins share the item's increments).
+        mode = MODE_SUPER3;
+        hist_bytes = (size_t)dim * 36;
+    } else if (ns4 && dim * 20 <= 96 * 1024) {  // (k+1)-mer table + side table: k <= 6 -> at most 80 KB
         mode = MODE_SUPER;
         hist_bytes = (size_t)dim * 20;
     } else if (dim * 4 > max_hist_bytes) {
@@ -508,13 +723,14 @@ int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dv
     int ctas_per_sm = 4;
     if (smem) ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (ctx->smem_optin + 1024) / (hist_bytes + 1024)));
     const uint32_t grid = (uint32_t)(ctx->sm_count * ctas_per_sm);
-    const int threads4 = (mode == MODE_SMEM_PARTS) ? 1024 : kCountThreads;
+    const int threads4 = (mode == MODE_SMEM_PARTS || mode == MODE_SUPER3) ? 1024 : kCountThreads;
     uint64_t chunk = 1 << 20;
     {
         // aim for >= 8 items per CTA, multiples of the 8 KB stripe.  Every item pays a zero + flush of its
         // table, so big tables (k >= 7) take up to 2-8 MB per item, small ones 64 KB .. 1 MB
         // global atomics per item at flush time (none for MODE_GLOBAL, which updates the row directly)
-        const uint64_t flush_bins = (mode == MODE_GLOBAL) ? 0 : (mode == MODE_SUPER ? dim : part_bins);
+        const uint64_t flush_bins =
+            (mode == MODE_GLOBAL) ? 0 : (mode == MODE_SUPER ? dim : (mode == MODE_SUPER3 ? dim * 16 : part_bins));
         const uint64_t max_chunk = flush_bins >= 32768 ? (8u << 20) : (flush_bins >= 16384 ? (2u << 20) : (1u << 20));
         uint64_t want_items = (uint64_t)grid * 8;
         uint64_t c = (s->total + want_items - 1) / std::max<uint64_t>(want_items, 1);
@@ -548,7 +764,8 @@ int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dv
     }
     const CountWork* d_work = reinterpret_cast<const CountWork*>(s->work_cache.p);
     const uint32_t n_work = s->work_items;
-    DevBuf<uint32_t> d_next;
+    DevBuf<uint32_t> d_next, d_rc;
+    DevBuf<CountWork> d_retry;
     if (n_work) {
         if (d_next.alloc(1) != DVS_OK) return fail(DVS_ERR_CUDA);
         TRY_F(cudaMemsetAsync(d_next.p, 0, sizeof(uint32_t), st));
@@ -562,7 +779,7 @@ int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dv
             cudaError_t e = set_smem(kern);
             if (e != cudaSuccess) return e;
             kern<<<g, threads4, hist_bytes, st>>>(s->data(), s->offsets.p, d_work, n_work,
-                                                  d_next.p, k, dim, part_bins, f->counts.p);
+                                                  d_next.p, k, dim, part_bins, f->counts.p, nullptr);
             ctx->launches++;
             return cudaGetLastError();
         };
@@ -579,7 +796,29 @@ int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dv
         PhaseTimer pt(ctx, DVS_PHASE_COUNT_KERNEL);
         if (!ns4)
             e = smem ? launch_generic(k_count_generic<true>) : launch_generic(k_count_generic<false>);
-        else if (mode == MODE_SUPER)
+        else if (mode == MODE_SUPER3) {
+            // main pass + retry pass (items whose 16-bit halves overflowed, recounted with 32-bit counters)
+            e = cudaSuccess;
+            if (d_retry.alloc(n_work) != DVS_OK || d_rc.alloc(2) != DVS_OK) return fail(DVS_ERR_CUDA);
+            TRY_F(cudaMemsetAsync(d_rc.p, 0, 2 * sizeof(uint32_t), st));
+            auto s3 = scramble ? k_count_s3<true, 1024> : k_count_s3<false, 1024>;
+            auto rk = scramble ? k_count<MODE_SUPER, true, 512> : k_count<MODE_SUPER, false, 512>;
+            TRY_F(cudaFuncSetAttribute(s3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
+            const size_t retry_bytes = (size_t)dim * 20;
+            if (retry_bytes > 48 * 1024)
+                TRY_F(cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)retry_bytes));
+            s3<<<g, 1024, hist_bytes, st>>>(s->data(), s->offsets.p, d_work, n_work, d_next.p, k, dim, f->counts.p,
+                                            d_retry.p, d_rc.p);
+            ctx->launches++;
+            e = cudaGetLastError();
+            if (e == cudaSuccess) {
+                const uint32_t g2 = (uint32_t)std::min<size_t>((size_t)ctx->sm_count * 2, n_work);
+                rk<<<g2, 512, retry_bytes, st>>>(s->data(), s->offsets.p, d_retry.p, 0u, d_rc.p + 1, k, dim,
+                                                 (uint32_t)dim, f->counts.p, d_rc.p);
+                ctx->launches++;
+                e = cudaGetLastError();
+            }
+        } else if (mode == MODE_SUPER)
             e = scramble ? launch4(k_count<MODE_SUPER, true, 512>) : launch4(k_count<MODE_SUPER, false, 512>);
         else if (mode == MODE_SMEM)
             e = scramble ? launch4(k_count<MODE_SMEM, true, 512>) : launch4(k_count<MODE_SMEM, false, 512>);

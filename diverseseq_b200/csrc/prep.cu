@@ -420,6 +420,10 @@ int dvs_prep_fasta(dvs_ctx* ctx, const uint8_t* text, const uint64_t* file_offse
             set_error("dvs_prep_fasta: file_offsets must be non-decreasing (file %u)", f);
             return DVS_ERR_ARG;
         }
+    if (text_on_device && ((uintptr_t)text & 3)) {
+        set_error("dvs_prep_fasta: device text must be 4-byte aligned");
+        return DVS_ERR_ARG;
+    }
     if (!alphabet) alphabet = DVS_DNA_ALPHABET;
     if (!delete_chars) delete_chars = "\n\r\t- ";
     if (sep_char < 0) sep_char = '-';

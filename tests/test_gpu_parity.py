@@ -109,6 +109,53 @@ def test_count_long_records_split_across_ctas(lib, ctx, orc):
     _check_counts(lib, ctx, orc, seqs, 8)
 
 
+@pytest.mark.parametrize("k", [4, 5, 6])
+def test_count_s3_16bit_overflow_retry(lib, ctx, orc, k, monkeypatch):
+    """(k+2)-mers at every third position with 16-bit packed counters: homopolymers / period-3 repeats
+    push one half past 65,535, which must be detected and the item recounted exactly"""
+    monkeypatch.setenv("DVS_COUNT_S3", "1")
+    rng = np.random.default_rng(40 + k)
+    poly = np.zeros(400_000, dtype=np.uint8)                       # one (k+2)-mer 133k times
+    rep3 = np.tile(np.array([0, 1, 2], dtype=np.uint8), 150_000)  # period 3: the same (k+2)-mer at every p
+    mixed = rng.integers(0, 4, size=500_000, dtype=np.uint8)
+    mixed[100_000:330_000] = 3                                     # overflow inside an otherwise random record
+    mixed[rng.integers(0, 500_000, size=50)] = 4
+    edge = np.full(3 * 65_536 + 7, 2, dtype=np.uint8)              # just at / over the limit
+    seqs = [poly, rep3, mixed, edge, rng.integers(0, 4, size=70_000, dtype=np.uint8)]
+    _check_counts(lib, ctx, orc, seqs, k)
+
+
+@pytest.mark.parametrize("k", [4, 6])
+def test_count_s3_phase_and_record_end_cases(lib, ctx, orc, k, monkeypatch):
+    """record lengths / starts in every residue mod 3 and mod 16, ends on block boundaries, invalid bytes
+    next to triplet boundaries"""
+    monkeypatch.setenv("DVS_COUNT_S3", "1")
+    rng = np.random.default_rng(50 + k)
+    seqs = []
+    for n in list(range(0, 70)) + [95, 96, 97, 111, 112, 113, 127, 128, 129, 511, 512, 513, 1023, 1024, 1025, 8191,
+                                   8192, 8193, 16384, 16385, 16386, 65535, 65536, 65537]:
+        s = rng.integers(0, 4, size=n, dtype=np.uint8)
+        if n > 40:
+            s[rng.integers(0, n, size=max(1, n // 200))] = 4
+        seqs.append(s)
+    _check_counts(lib, ctx, orc, seqs, k)
+    # the same records in another order shift every start by a different amount
+    rng.shuffle(seqs)
+    _check_counts(lib, ctx, orc, seqs, k)
+    clean = [rng.integers(0, 4, size=n, dtype=np.uint8) for n in (48, 49, 50, 160, 161, 162, 4096, 4097, 4098)]
+    _check_counts(lib, ctx, orc, clean, k)
+
+
+@pytest.mark.parametrize("k", [5, 6])
+def test_count_s3_kernel_general_records(lib, ctx, orc, k, monkeypatch):
+    """DVS_COUNT_S3=1: the opt-in (k+2)-mer / 16-bit kernel on ragged records with invalid bytes"""
+    monkeypatch.setenv("DVS_COUNT_S3", "1")
+    rng = np.random.default_rng(60 + k)
+    seqs = [rng.integers(0, 5, size=int(n), dtype=np.uint8) for n in rng.integers(0, 30_000, size=20)]
+    seqs.append(rng.integers(0, 4, size=1_500_000, dtype=np.uint8))
+    _check_counts(lib, ctx, orc, seqs, k)
+
+
 def test_count_k12_global_atomic_path(lib, ctx, orc, brca1):
     """north-star headline k: 4^12 bins per record, global RED.ADD path"""
     seqs = [brca1["Human"], brca1["Dugong"], np.zeros(5, np.uint8)]
