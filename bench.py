@@ -72,31 +72,94 @@ def workload_config(a, world):
 
 # --------------------------------------------------------------------------- clocks ----
 class ClockSampler:
+    """SM clock + clock-event reasons DURING the timed region.  The timed region of the default run is
+    tens of milliseconds, far below nvidia-smi's practical sampling period, so NVML is polled in-process
+    from a thread (ctypes calls into libdvs release the GIL); `nvidia-smi -lms` is the fallback when the
+    NVML binding is unavailable.  CUDA_VISIBLE_DEVICES remapping is resolved through the PCI bus id."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, pci_bus_id: str | None = None):
         self.index = index
+        self.pci = pci_bus_id
         self.proc = None
         self.lines = []
+        self.nvml = None
+        self.samples = []  # (sm_mhz, power_w, reasons_mask)
+        self._stop = threading.Event()
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                h = pynvml.nvmlDeviceGetHandleByPciBusId(self.pci.encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.nvml, self.h = pynvml, h
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv, h = self.nvml, self.h
+        reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                                     nv.nvmlDeviceGetPowerUsage(h) / 1000.0, int(reasons(h))))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    @staticmethod
+    def _summary(sm, mx, pw, reasons, how):
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "how": how}
+        # "under load": samples in the upper half of the observed power range
+        thr = (max(pw) + min(pw)) / 2
+        load = [s for s, p in zip(sm, pw) if p >= thr] or sm
+        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(mx), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons), "how": how}
+
     def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            nv = self.nvml
+            names = {"hw_slowdown": "nvmlClocksThrottleReasonHwSlowdown",
+                     "hw_thermal_slowdown": "nvmlClocksThrottleReasonHwThermalSlowdown",
+                     "sw_thermal_slowdown": "nvmlClocksThrottleReasonSwThermalSlowdown",
+                     "sw_power_cap": "nvmlClocksThrottleReasonSwPowerCap"}
+            seen = set()
+            for _, _, mask in self.samples:
+                for name, attr in names.items():
+                    if mask & int(getattr(nv, attr, 0)):
+                        seen.add(name)
+            out = self._summary([s[0] for s in self.samples], self.sm_max, [s[1] for s in self.samples], seen,
+                                "NVML polled in-process every ~2 ms during the timed region")
+            try:
+                nv.nvmlShutdown()
+            except Exception:
+                pass
+            return out
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"]}
         time.sleep(0.25)
         self.proc.terminate()
         try:
@@ -115,13 +178,7 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        # "under load": samples in the upper half of the observed power range
-        thr = (max(pw) + min(pw)) / 2
-        load = [s for s, p in zip(sm, pw) if p >= thr] or sm
-        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
-                "samples": len(sm), "reasons": sorted(reasons)}
+        return self._summary(sm, max(mx) if mx else None, pw, reasons, "nvidia-smi -lms 50")
 
 
 # ------------------------------------------------------------------- CPU (oracle) leg ----
@@ -295,7 +352,12 @@ def main():
 
     for _ in range(a.warmup):
         step(seqset)
-    sampler = ClockSampler(local)
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        pci = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+    except Exception:
+        pci = None
+    sampler = ClockSampler(local, pci)
     if rank == 0:
         sampler.start()
     launches0 = ctx.launch_count

@@ -19,8 +19,12 @@
 #include <algorithm>
 #include <limits>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "entropy.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace dvs {
 
@@ -501,25 +505,32 @@ __device__ __forceinline__ void stats_fast_block(const double* mdelta, const dou
     }
 }
 
+// The mutable selection state (S, member list, is_member, scalars) is read with ld.global.cg inside the
+// bodies below: the persistent kernel keeps CTAs alive across rounds, where a line cached in L1 during
+// an earlier round would be stale.  Rows of F / H / valid / order never change and use the default path.
+struct ScanScal {
+    double E, total_jsd, total_bound;
+    unsigned n, low_row;
+};
+
 // fast increases_jsd of the candidate at position `pos`; first_true / first_unsure by atomicMin
 __device__ __forceinline__ void scan_fast_body(const double* __restrict__ F, const double* __restrict__ H, uint64_t dim,
-                                               const double* __restrict__ S, const unsigned* __restrict__ members,
-                                               SelScal* sc, const uint8_t* __restrict__ valid,
+                                               const double* __restrict__ S, SelScal* sc, const ScanScal& q,
+                                               const uint8_t* __restrict__ valid,
                                                const uint8_t* __restrict__ is_member,
                                                const unsigned* __restrict__ order, unsigned pos) {
     const unsigned row = order[pos];
-    if (!valid[row] || is_member[row]) return;
-    const unsigned n = sc->n;
-    const double nd = (double)n;
-    const unsigned low_row = members[sc->lowest];
-    const double* fl = F + (size_t)low_row * dim;
+    if (!valid[row] || __ldcg(is_member + row)) return;
+    const double nd = (double)q.n;
+    const double* fl = F + (size_t)q.low_row * dim;
     const double* fc = F + (size_t)row * dim;
-    FastSum h = block_entropy_fast(dim, [&](uint64_t i) { return __ddiv_rn(__dadd_rn(__dsub_rn(S[i], fl[i]), fc[i]), nd); });
+    FastSum h = block_entropy_fast(
+        dim, [&](uint64_t i) { return __ddiv_rn(__dadd_rn(__dsub_rn(__ldcg(S + i), fl[i]), fc[i]), nd); });
     if (threadIdx.x == 0) {
-        const double mean_entropy = __ddiv_rn(__dadd_rn(__dsub_rn(sc->E, H[low_row]), H[row]), nd);
+        const double mean_entropy = __ddiv_rn(__dadd_rn(__dsub_rn(q.E, H[q.low_row]), H[row]), nd);
         const double d = h.e - mean_entropy;
         const double b = fast_bound(dim, h.a, mean_entropy);
-        const double thr = sc->total_jsd + kEps, tb = sc->total_bound + 4.0 * kEps;
+        const double thr = q.total_jsd + kEps, tb = q.total_bound + 4.0 * kEps;
         if (h.bad || !fast_total_ok(dim, h.t) || !(d == d)) {
             atomicMin(&sc->first_unsure, pos);
         } else if (d - b > thr + tb) {
@@ -530,12 +541,22 @@ __device__ __forceinline__ void scan_fast_body(const double* __restrict__ F, con
     }
 }
 
+__device__ __forceinline__ ScanScal load_scan_scal(const SelScal* sc, const unsigned* members) {
+    ScanScal q;
+    q.E = __ldcg(&sc->E);
+    q.total_jsd = __ldcg(&sc->total_jsd);
+    q.total_bound = __ldcg(&sc->total_bound);
+    q.n = __ldcg(&sc->n);
+    q.low_row = __ldcg(members + __ldcg(&sc->lowest));
+    return q;
+}
+
 // host-driven window: one CTA per position pos0 + blockIdx.x
 __global__ void __launch_bounds__(kFastThreads)
 k_sel_scan_fast(const double* __restrict__ F, const double* __restrict__ H, uint64_t dim, const double* __restrict__ S,
                 const unsigned* __restrict__ members, SelScal* sc, const uint8_t* __restrict__ valid,
                 const uint8_t* __restrict__ is_member, const unsigned* __restrict__ order, unsigned pos0) {
-    scan_fast_body(F, H, dim, S, members, sc, valid, is_member, order, pos0 + blockIdx.x);
+    scan_fast_body(F, H, dim, S, sc, load_scan_scal(sc, members), valid, is_member, order, pos0 + blockIdx.x);
 }
 
 // device-driven window: cursor / window / current buffer come from the scalar block, so the host can
@@ -551,7 +572,8 @@ k_sel_scan_dev(const double* __restrict__ F, const double* __restrict__ H, uint6
     const unsigned count = min(sc->window, num - cursor);
     if (blockIdx.x >= count) return;
     const unsigned w = sc->which;
-    scan_fast_body(F, H, dim, w ? S1 : S0, w ? M1 : M0, sc, valid, is_member, order, cursor + blockIdx.x);
+    scan_fast_body(F, H, dim, w ? S1 : S0, sc, load_scan_scal(sc, w ? M1 : M0), valid, is_member, order,
+                   cursor + blockIdx.x);
 }
 
 // fast total_jsd + get_lowest_record_index: same shape as k_sel_update.  Leaves approximate
@@ -618,16 +640,15 @@ __device__ __forceinline__ void replace_update_fast_body(
     const double* __restrict__ F, const double* __restrict__ H, uint64_t dim, const double* __restrict__ S_in,
     double* __restrict__ S_out, const unsigned* __restrict__ m_in, unsigned* __restrict__ m_out,
     uint8_t* __restrict__ is_member, double* __restrict__ mdelta, double* __restrict__ mbound, SelScal* sc,
-    unsigned cand_row, unsigned dev_pos, unsigned dev_cursor) {
+    unsigned cand_row, unsigned dev_pos, unsigned dev_cursor, unsigned j, unsigned n, unsigned low, double E_old) {
     __shared__ unsigned s_last;
-    const unsigned j = blockIdx.x, n = sc->n, low = sc->lowest;
     const double nd = (double)n;
-    const unsigned low_row = m_in[low];
+    const unsigned low_row = __ldcg(m_in + low);
     const double* fl = F + (size_t)low_row * dim;
     const double* fc = F + (size_t)cand_row * dim;
-    const double E_new = __dadd_rn(__dsub_rn(sc->E, H[low_row]), H[cand_row]);  // records.rs:101,129
+    const double E_new = __dadd_rn(__dsub_rn(E_old, H[low_row]), H[cand_row]);  // records.rs:101,129
     auto s_new = [&](uint64_t i) {
-        double s = __dsub_rn(S_in[i], fl[i]);
+        double s = __dsub_rn(__ldcg(S_in + i), fl[i]);
         if (s <= kEps) s = 0.0;
         return __dadd_rn(s, fc[i]);
     };
@@ -645,7 +666,7 @@ __device__ __forceinline__ void replace_update_fast_body(
         }
     } else {
         // member j of the list after Vec::remove(low) + push(cand)
-        const unsigned row = j < low ? m_in[j] : (j + 1 < n ? m_in[j + 1] : cand_row);
+        const unsigned row = j < low ? __ldcg(m_in + j) : (j + 1 < n ? __ldcg(m_in + j + 1) : cand_row);
         const double div = __dsub_rn(nd, 1.0);
         const double* f = F + (size_t)row * dim;
         FastSum h = block_entropy_fast(dim, [&](uint64_t i) {
@@ -667,7 +688,7 @@ __device__ __forceinline__ void replace_update_fast_body(
     if (s_last) {  // block-uniform: the whole last CTA finishes the round
         __threadfence();
         for (unsigned t = threadIdx.x; t < n; t += blockDim.x)
-            m_out[t] = t < low ? m_in[t] : (t + 1 < n ? m_in[t + 1] : cand_row);
+            m_out[t] = t < low ? __ldcg(m_in + t) : (t + 1 < n ? __ldcg(m_in + t + 1) : cand_row);
         const double total = __ldcg(&sc->total_jsd), tb = __ldcg(&sc->total_bound);
         unsigned lo2 = 0;
         const unsigned unsure = finalize_fast_block(mdelta, mbound, n, total, tb, &lo2);
@@ -684,10 +705,10 @@ __device__ __forceinline__ void replace_update_fast_body(
             sc->first_panic = kNone;
             sc->first_unsure = kNone;
             if (dev_pos != kNone) {
-                sc->window = max(64u, min(sc->window_max, 2u * (dev_pos - dev_cursor + 1u)));
+                sc->window = max(64u, min(__ldcg(&sc->window_max), 2u * (dev_pos - dev_cursor + 1u)));
                 sc->cursor = dev_pos + 1u;
-                sc->accepts += 1u;
-                sc->which ^= 1u;
+                sc->accepts = __ldcg(&sc->accepts) + 1u;
+                sc->which = __ldcg(&sc->which) ^ 1u;
             }
         }
     }
@@ -699,7 +720,8 @@ k_sel_replace_update_fast(const double* __restrict__ F, const double* __restrict
                           const unsigned* __restrict__ m_in, unsigned* __restrict__ m_out,
                           uint8_t* __restrict__ is_member, double* __restrict__ mdelta, double* __restrict__ mbound,
                           SelScal* sc, unsigned cand_row) {
-    replace_update_fast_body(F, H, dim, S_in, S_out, m_in, m_out, is_member, mdelta, mbound, sc, cand_row, kNone, 0u);
+    replace_update_fast_body(F, H, dim, S_in, S_out, m_in, m_out, is_member, mdelta, mbound, sc, cand_row, kNone, 0u,
+                             blockIdx.x, sc->n, sc->lowest, sc->E);
 }
 
 // One device-driven round after k_sel_scan_dev: every CTA takes the same decision from the scalar
@@ -720,7 +742,7 @@ k_sel_round_dev(const double* __restrict__ F, const double* __restrict__ H, uint
     if (!su && !(fu < ft) && ft != kNone) {
         const unsigned w = sc->which;
         replace_update_fast_body(F, H, dim, w ? S1 : S0, w ? S0 : S1, w ? M1 : M0, w ? M0 : M1, is_member, mdelta,
-                                 mbound, sc, order[ft], ft, cursor);
+                                 mbound, sc, order[ft], ft, cursor, blockIdx.x, n, sc->lowest, sc->E);
         return;
     }
     if (threadIdx.x == 0) {
@@ -736,6 +758,79 @@ k_sel_round_dev(const double* __restrict__ F, const double* __restrict__ H, uint
             sc->cursor = cursor + count;
             sc->window = min(window * 2u, sc->window_max);
         }
+    }
+}
+
+// All device-driven rounds in ONE cooperative launch: the CTAs stay resident, a round is
+//   scan (one candidate per CTA and pass) | grid barrier | accept: fused replace + update over n+1 member
+//   slots, or advance / halt | grid barrier
+// with the same scalar-block protocol as k_sel_scan_dev / k_sel_round_dev, so the host loop and the exact
+// fallbacks are unchanged.  Against the two-launches-per-round form this removes the launch and block
+// scheduling latency of ~2 x 350 dependent kernels per nmost run and loads the round's scalars once per
+// CTA instead of through chains of dependent global loads.
+struct RoundScal {
+    ScanScal q;
+    unsigned lowest, which, cursor, count, window, stop, ft, fu, su;
+};
+
+__global__ void __launch_bounds__(kFastThreads)
+k_sel_persist(const double* __restrict__ F, const double* __restrict__ H, uint64_t dim, double* S0, double* S1,
+              unsigned* M0, unsigned* M1, uint8_t* is_member, double* mdelta, double* mbound, SelScal* sc,
+              const uint8_t* __restrict__ valid, const unsigned* __restrict__ order, unsigned max_rounds,
+              unsigned long long* trace) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ RoundScal rs;
+    // DVS_SELECT_TRACE: CTA 0 stamps %globaltimer at the four phase boundaries of the first rounds
+    auto stamp = [&](unsigned round, int slot) {
+        if (trace && blockIdx.x == 0 && threadIdx.x == 0 && round < 512) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            trace[round * 4 + slot] = t;
+        }
+    };
+    for (unsigned round = 0; round < max_rounds; ++round) {
+        stamp(round, 0);
+        if (threadIdx.x == 0) {
+            const unsigned cursor = __ldcg(&sc->cursor), num = __ldcg(&sc->num), window = __ldcg(&sc->window);
+            rs.stop = __ldcg(&sc->halt) || cursor >= num;
+            rs.cursor = cursor;
+            rs.window = window;
+            rs.count = cursor < num ? min(window, num - cursor) : 0u;
+            rs.which = __ldcg(&sc->which);
+            rs.lowest = __ldcg(&sc->lowest);
+            rs.q = load_scan_scal(sc, rs.which ? M1 : M0);
+        }
+        __syncthreads();
+        if (rs.stop) break;  // grid-uniform: every CTA read the same scalar block
+        const unsigned which = rs.which, cursor = rs.cursor, count = rs.count, n = rs.q.n;
+        const ScanScal q = rs.q;
+        for (unsigned c = blockIdx.x; c < count; c += gridDim.x)
+            scan_fast_body(F, H, dim, which ? S1 : S0, sc, q, valid, is_member, order, cursor + c);
+        stamp(round, 1);
+        grid.sync();
+        stamp(round, 2);
+        if (threadIdx.x == 0) {
+            rs.ft = __ldcg(&sc->first_true);
+            rs.fu = __ldcg(&sc->first_unsure);
+            rs.su = __ldcg(&sc->state_unsure);
+        }
+        __syncthreads();
+        const unsigned ft = rs.ft, fu = rs.fu, su = rs.su;
+        if (!su && !(fu < ft) && ft != kNone) {
+            const unsigned cand_row = order[ft];
+            for (unsigned j = blockIdx.x; j <= n; j += gridDim.x)
+                replace_update_fast_body(F, H, dim, which ? S1 : S0, which ? S0 : S1, which ? M1 : M0, which ? M0 : M1,
+                                         is_member, mdelta, mbound, sc, cand_row, ft, cursor, j, n, rs.lowest, q.E);
+        } else if (blockIdx.x == 0 && threadIdx.x == 0) {
+            if (su || fu < ft) {
+                sc->halt = 1u;
+            } else {  // empty window
+                sc->cursor = cursor + count;
+                sc->window = min(rs.window * 2u, __ldcg(&sc->window_max));
+            }
+        }
+        stamp(round, 3);
+        grid.sync();
     }
 }
 
@@ -952,8 +1047,64 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
     const char* dev_env = getenv("DVS_SELECT_HOST_LOOP");
     const bool use_dev = use_fast && !(dev_env && dev_env[0] == '1');
     constexpr int kRoundsPerBatch = 32;
+    // DVS_SELECT_PERSIST=0 keeps the two-launches-per-round form (A/B measurements, fallback)
+    const char* per_env = getenv("DVS_SELECT_PERSIST");
+    int coop = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+    if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sel_persist, kFastThreads, 0) != cudaSuccess)
+        per_sm = 0;
+    const bool use_persist = use_dev && coop && per_sm > 0 && !(per_env && per_env[0] == '0');
+    const unsigned persist_grid = (unsigned)ctx->sm_count * (unsigned)std::min(per_sm, 2);
     while (cursor < num) {
-        if (use_dev && (!grow_mode || n == max_size)) {
+        if (use_persist && (!grow_mode || n == max_size)) {
+            // every remaining round in one cooperative launch (until done, or halted for the host)
+            k_sel_set_dev<<<1, 1, 0, st>>>(cur->sc.p, cursor, std::min(window, persist_grid), persist_grid, num, accepts,
+                                           (unsigned)cur->which);
+            DVS_LAUNCHED(ctx);
+            const double* a_F = f->freqs.p;
+            const double* a_H = f->entropy.p;
+            uint64_t a_dim = dim;
+            double *a_S0 = cur->Sbuf[0].p, *a_S1 = cur->Sbuf[1].p;
+            unsigned *a_M0 = cur->membuf[0].p, *a_M1 = cur->membuf[1].p;
+            uint8_t* a_mem = is_member.p;
+            double *a_md = cur->mdelta.p, *a_mb = cur->mbound.p;
+            SelScal* a_sc = cur->sc.p;
+            const uint8_t* a_valid = f->valid.p;
+            const unsigned* a_order = d_order.p;
+            unsigned a_rounds = 0x7fffffffu;
+            unsigned long long* a_trace = nullptr;
+            DevBuf<unsigned long long> d_trace;
+            const char* tr_env = getenv("DVS_SELECT_TRACE");
+            if (tr_env && tr_env[0]) {
+                DVS_TRY(d_trace.alloc(2048));
+                DVS_CUDA_TRY(cudaMemsetAsync(d_trace.p, 0, 2048 * sizeof(unsigned long long), st));
+                a_trace = d_trace.p;
+            }
+            void* args[] = {&a_F, &a_H, &a_dim, &a_S0, &a_S1, &a_M0, &a_M1, &a_mem, &a_md, &a_mb, &a_sc, &a_valid, &a_order, &a_rounds, &a_trace};
+            DVS_CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_sel_persist, dim3(persist_grid), dim3(kFastThreads), args, 0, st));
+            ctx->launches++;
+            DVS_TRY(sel.read(*cur));
+            if (a_trace) {  // phase timeline of CTA 0 to the file named by DVS_SELECT_TRACE
+                std::vector<unsigned long long> tr(2048);
+                DVS_CUDA_TRY(cudaMemcpy(tr.data(), a_trace, 2048 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+                if (FILE* fp = fopen(tr_env, "a")) {
+                    fprintf(fp, "# round scan_ns wait1_ns update_ns wait2_ns (CTA 0; wait = grid barrier incl. the slowest CTA)\n");
+                    for (int r = 0; r + 1 < 512 && tr[4 * (r + 1)]; ++r)
+                        fprintf(fp, "%d %llu %llu %llu %llu\n", r, tr[4 * r + 1] - tr[4 * r], tr[4 * r + 2] - tr[4 * r + 1],
+                                tr[4 * r + 3] - tr[4 * r + 2], tr[4 * (r + 1)] - tr[4 * r + 3]);
+                    fclose(fp);
+                }
+            }
+            const SelScal hd = *sel.h_sc;
+            if (hd.panic) return panic_error(hd);
+            cursor = hd.cursor;
+            window = hd.window;
+            accepts = hd.accepts;
+            cur->which = (int)hd.which;
+            if (!hd.halt) continue;  // finished
+            DVS_TRY(sel.reset_scan(*cur));
+            if (cursor >= num) break;
+        } else if (use_dev && (!grow_mode || n == max_size)) {
             // Device-driven rounds: scan + decide + replace/update are enqueued kRoundsPerBatch times
             // without any read-back; the kernels carry cursor / window / accepts in the scalar block
             // and stop doing work once they halt (undecided within the error bound) or finish.
