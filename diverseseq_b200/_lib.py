@@ -75,6 +75,7 @@ SIGNATURES = {
     "dvs_euclid_distances": (_i32, [_vp, _vp, _u32, _u32, _vp]),
     "dvs_debug_pack_host": (_i32, [_vp, _u64, _vp, _vp, _vp, _u32, C.POINTER(_u32)]),
     "dvs_debug_log2": (_i32, [_vp, _vp, _vp, _u64]),
+    "dvs_debug_fast_terms": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _u64]),
     "dvs_debug_entropy": (_i32, [_vp, _vp, _u32, _u64, _vp, _vp]),
 }
 
@@ -493,6 +494,14 @@ def debug_log2(ctx: Context, x: np.ndarray) -> np.ndarray:
     y = np.zeros_like(x)
     check(ctx._lib.dvs_debug_log2(ctx.handle, ptr(x), ptr(y), x.size))
     return y
+
+
+def debug_fast_terms(ctx: Context, a: np.ndarray, b: np.ndarray):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    m, lg, sp = np.zeros_like(a), np.zeros_like(a), np.zeros(a.size, dtype=np.int32)
+    check(ctx._lib.dvs_debug_fast_terms(ctx.handle, ptr(a), ptr(b), ptr(m), ptr(lg), ptr(sp), a.size))
+    return m, lg, sp
 
 
 def debug_entropy(ctx: Context, rows: np.ndarray):

@@ -135,3 +135,54 @@ DVS_HD double dvs_log2(double x) {
     double y = fma_(r2, p, lo);
     return add_(y, hi);
 }
+
+#if defined(__CUDACC__)
+// The table-driven path of dvs_log2 on its own, for the throughput kernels: branch-free so that several
+// evaluations interleave in one thread (FP64 latency on sm_100 is ~14 cycles), table read from a
+// shared-memory copy (`tab[i] = {1/c_i, log2 c_i}`; the __constant__ copy would serialise a warp's 32
+// different indices).  Same operations in the same order as above, hence the same bits, for every input
+// that dvs_log2 sends down this path; `special` is raised for the inputs it handles elsewhere
+// (|x - 1| small, zero, negative, subnormal, inf, nan), for which the value returned here is meaningless.
+__device__ __forceinline__ double dvs_log2_main(double x, const double2* __restrict__ tab, int& special) {
+    using namespace dvs_log2_detail;
+    constexpr double A0[6] = {DVS_LOG2_POLY_A};
+    const double InvLn2hi = DVS_LOG2_INVLN2HI;
+    const double InvLn2lo = DVS_LOG2_INVLN2LO;
+    const uint64_t ix = bits_(x);
+    const uint32_t top = (uint32_t)(ix >> 48);
+    special |= (ix - 0x3feea4af00000000ULL < 0x000210aa00000000ULL) ? 1 : 0;
+    special |= (top - 0x0010u >= 0x7ff0u - 0x0010u) ? 1 : 0;
+    const uint64_t tmp = ix - 0x3fe6000000000000ULL;
+    const int i = (int)((tmp >> 46) & 63);
+    const int k = (int)((int64_t)tmp >> 52);
+    const uint64_t iz = ix - (tmp & 0xfff0000000000000ULL);
+    const double2 ic = tab[i];
+    const double invc = ic.x, logc = ic.y;
+    const double z = dbl_(iz);
+    const double kd = (double)k;
+
+    const double t3 = add_(kd, logc);
+    const double r = fma_(z, invc, -1.0);
+    const double q01 = fma_(r, A0[1], A0[0]);
+    const double t1 = mul_(InvLn2hi, r);
+    const double u = fma_(InvLn2hi, r, -t1);
+    const double hi = add_(t1, t3);
+    double lo = sub_(t3, hi);
+    const double t2 = fma_(r, InvLn2lo, u);
+    const double r2 = mul_(r, r);
+    lo = add_(lo, t1);
+    lo = add_(lo, t2);
+    const double q23 = fma_(r, A0[3], A0[2]);
+    const double r4 = mul_(r2, r2);
+    const double q45 = fma_(r, A0[5], A0[4]);
+    const double s = fma_(q23, r2, q01);
+    const double p = fma_(q45, r4, s);
+    const double y = fma_(r2, p, lo);
+    return add_(y, hi);
+}
+// 64 x {1/c, log2 c} into shared memory (call from >= 64 threads, then __syncthreads())
+__device__ __forceinline__ void dvs_log2_stage_table(double2* tab) {
+    if (threadIdx.x < 64)
+        tab[threadIdx.x] = make_double2(dvs_log2_data_dev.tab[2 * threadIdx.x], dvs_log2_data_dev.tab[2 * threadIdx.x + 1]);
+}
+#endif

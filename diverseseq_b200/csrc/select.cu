@@ -316,8 +316,9 @@ struct FastSum {
     int bad;         // a negative / NaN frequency was seen (reference yields NaN): cannot be bounded
 };
 
+// elements [lo, hi) of a vector (the SM-replicated selection kernel splits one vector over several CTAs)
 template <class Elem>
-__device__ FastSum block_entropy_fast(uint64_t dim, Elem elem) {
+__device__ FastSum block_entropy_span(uint64_t lo, uint64_t dim, Elem elem) {
     __shared__ double s_part[3][kFastThreads / 32];
     __shared__ int s_bad[kFastThreads / 32];
     double e0 = 0.0, e1 = 0.0, t0 = 0.0, t1 = 0.0, a0 = 0.0, a1 = 0.0;
@@ -325,7 +326,7 @@ __device__ FastSum block_entropy_fast(uint64_t dim, Elem elem) {
     // 8 elements per thread per pass: all frequencies (global loads + divides) are formed before the
     // first log2 so one memory latency is exposed per pass, not one per element
     constexpr int kBatch = 8;
-    for (uint64_t base = 0; base < dim; base += (uint64_t)kBatch * kFastThreads) {
+    for (uint64_t base = lo; base < dim; base += (uint64_t)kBatch * kFastThreads) {
         double x[kBatch];
 #pragma unroll
         for (int q = 0; q < kBatch; ++q) {
@@ -366,19 +367,107 @@ __device__ FastSum block_entropy_fast(uint64_t dim, Elem elem) {
     __syncthreads();
     return r;
 }
+template <class Elem>
+__device__ __forceinline__ FastSum block_entropy_fast(uint64_t dim, Elem elem) {
+    return block_entropy_span(0, dim, elem);
+}
+
+// ---- the same sums with instruction-level parallelism (SM-replicated rounds) ----
+// block_entropy_span evaluates one element at a time: CUDA's ddiv and log2 are ~50 dependent FP64
+// instructions behind their own branches, and with 4 warps per scheduler at ~14 cycles per dependent
+// FP64 instruction the FP64 pipe idles most of the time (measured 0.47 us per element per thread).
+// Here every step is branch-free straight-line code over 8 elements per thread, so 8 chains interleave:
+//   * x / b by Markstein's sequence on a correctly rounded reciprocal — two refinement steps, the second
+//     from a faithful quotient, which rounds correctly (= __ddiv_rn bit for bit; checked on 8.2e7 random
+//     operands x all b <= 4100 on the host and in tests/test_gpu_parity.py on the device);
+//   * log2 by the table-driven path of the glibc restatement (dvs_log2_main): the reference's own bits,
+//     so a term -m*log2(m) is now IDENTICAL to the reference's, not merely within 3 ulp.
+// Inputs that the glibc algorithm sends down its other paths (m within ~4 % of 1, subnormals) or that
+// make the reference's value NaN raise `bad`, which the callers already treat as "undecided".
+struct FastDiv {
+    double b, y;  // divisor and RN(1/b)
+};
+__device__ __forceinline__ FastDiv make_fast_div(double b) { return FastDiv{b, __drcp_rn(b)}; }
+__device__ __forceinline__ double div_exact(double a, const FastDiv& d) {
+    double q = __dmul_rn(a, d.y);
+    double r = __fma_rn(-q, d.b, a);
+    q = __fma_rn(r, d.y, q);
+    r = __fma_rn(-q, d.b, a);
+    return __fma_rn(r, d.y, q);
+}
+
+template <bool CLAMP, class Num>
+__device__ FastSum block_entropy_ilp(unsigned lo, unsigned hi, Num num, const FastDiv dv,
+                                     const double2* __restrict__ ltab) {
+    __shared__ double s_part[3][kFastThreads / 32];
+    __shared__ int s_bad[kFastThreads / 32];
+    double e0 = 0.0, e1 = 0.0, t0 = 0.0, t1 = 0.0, a0 = 0.0, a1 = 0.0;
+    int bad = 0;
+    constexpr int kBatch = 8;
+    for (unsigned base = lo; base < hi; base += kBatch * kFastThreads) {
+        double x[kBatch], l[kBatch];
+        int sp[kBatch];
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) {
+            const unsigned i = base + threadIdx.x + (unsigned)q * kFastThreads;
+            x[q] = i < hi ? num(i) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) {
+            // |numerator| below 1e-280 (never a k-mer frequency) would make the remainders inexact
+            sp[q] = (x[q] != 0.0 && fabs(x[q]) < 1e-280) ? 1 : 0;
+            double m = div_exact(x[q], dv);
+            if (CLAMP) m = (m <= kEps) ? 0.0 : m;
+            x[q] = m;
+        }
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) l[q] = dvs_log2_main(x[q], ltab, sp[q]);
+#pragma unroll
+        for (int q = 0; q < kBatch; q += 2) {
+            const bool nz0 = !(x[q] == 0.0), nz1 = !(x[q + 1] == 0.0);
+            const double tm0 = nz0 ? __dmul_rn(-x[q], l[q]) : 0.0;
+            const double tm1 = nz1 ? __dmul_rn(-x[q + 1], l[q + 1]) : 0.0;
+            bad |= (nz0 && (sp[q] || !(x[q] > 0.0))) ? 1 : 0;
+            bad |= (nz1 && (sp[q + 1] || !(x[q + 1] > 0.0))) ? 1 : 0;
+            e0 += tm0; a0 += fabs(tm0); t0 += nz0 ? x[q] : 0.0;
+            e1 += tm1; a1 += fabs(tm1); t1 += nz1 ? x[q + 1] : 0.0;
+        }
+    }
+    double e = e0 + e1, t = t0 + t1, a = a0 + a1;
+    for (int o = 16; o; o >>= 1) {
+        e += __shfl_xor_sync(0xffffffffu, e, o);
+        t += __shfl_xor_sync(0xffffffffu, t, o);
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        s_part[0][w] = e; s_part[1][w] = t; s_part[2][w] = a; s_bad[w] = bad;
+    }
+    __syncthreads();
+    FastSum r{0.0, 0.0, 0.0, 0};
+    for (int q = 0; q < kFastThreads / 32; ++q) {
+        r.e += s_part[0][q]; r.t += s_part[1][q]; r.a += s_part[2][q]; r.bad |= s_bad[q];
+    }
+    __syncthreads();
+    return r;
+}
 
 // Each thread first sums dim/kFastThreads elements sequentially, then the partials are tree-summed:
 // |sum_fast - real sum| <= (dim/kFastThreads + 12) u A, the reference's sequential sum is within
 // (dim - 1) u A, and the per-term differences add 6 u A; 1.2e-16 > u = 2^-53 absorbs second-order terms.
-__device__ __forceinline__ double fast_slack(uint64_t dim) { return (double)(dim / kFastThreads) + 12.0; }
-__device__ __forceinline__ double fast_bound(uint64_t dim, double a, double extra) {
-    return ((double)dim + fast_slack(dim) + 16.0) * 1.2e-16 * (a + fabs(extra) + 1.0);
+// `depth`: additional sequential additions on top of the tree (partials of a vector split over CTAs)
+__device__ __forceinline__ double fast_slack(uint64_t dim, double depth = 0.0) {
+    return (double)(dim / kFastThreads) + 12.0 + depth;
+}
+__device__ __forceinline__ double fast_bound(uint64_t dim, double a, double extra, double depth = 0.0) {
+    return ((double)dim + fast_slack(dim, depth) + 16.0) * 1.2e-16 * (a + fabs(extra) + 1.0);
 }
 // reference check: |t_ref - 1| <= dim*EPS = 2 dim u.  |t_ref - T| <= (dim-1) u, |t - T| <= slack u (T ~ 1),
 // so the check cannot fail when |t - 1| <= (dim + 1 - slack) u; for tiny dim this is never certified
 // and the (then trivially cheap) exact kernel decides.
-__device__ __forceinline__ bool fast_total_ok(uint64_t dim, double t) {
-    const double lim = ((double)dim + 1.0 - fast_slack(dim) - 2.0) * 1.1102230246251565e-16;
+__device__ __forceinline__ bool fast_total_ok(uint64_t dim, double t, double depth = 0.0) {
+    const double lim = ((double)dim + 1.0 - fast_slack(dim, depth) - 2.0) * 1.1102230246251565e-16;
     return lim > 0.0 && fabs(t - 1.0) <= lim;
 }
 
@@ -386,8 +475,12 @@ __device__ __forceinline__ bool fast_total_ok(uint64_t dim, double t) {
 // delta_j = total - jsd_j, argmin (lowest index wins ties) and the certainty test
 // "member `low` is smaller than every other member for all admissible errors".  Returns 1 when the
 // argmin could not be certified.  (A single thread walking n global values costs n L2 latencies.)
+// GLOBAL: the arrays live in global memory and were written by other CTAs (read through L2); otherwise
+// they are this CTA's own shared-memory copies.
+template <bool GLOBAL = true>
 __device__ __forceinline__ unsigned finalize_fast_block(double* mdelta, const double* mbound, unsigned n, double total,
                                                         double total_bound, unsigned* low_out) {
+    auto ld = [](const double* p) { return GLOBAL ? __ldcg(p) : *p; };
     __shared__ double s_mn[kFastThreads / 32], s_mb[kFastThreads / 32];
     __shared__ unsigned s_ix[kFastThreads / 32];
     __shared__ double s_best, s_bestb;
@@ -395,11 +488,11 @@ __device__ __forceinline__ unsigned finalize_fast_block(double* mdelta, const do
     double mn = 1e300, mb = 0.0;
     unsigned ix = kNone;
     for (unsigned t = threadIdx.x; t < n; t += blockDim.x) {
-        const double d = total - __ldcg(&mdelta[t]);
+        const double d = total - ld(&mdelta[t]);
         mdelta[t] = d;
         if (d < mn || (d == mn && t < ix)) {
             mn = d;
-            mb = __ldcg(&mbound[t]);
+            mb = ld(&mbound[t]);
             ix = t;
         }
     }
@@ -426,7 +519,7 @@ __device__ __forceinline__ unsigned finalize_fast_block(double* mdelta, const do
     const unsigned low = s_besti;
     int unsure = 0;
     for (unsigned t = threadIdx.x; t < n; t += blockDim.x)
-        if (t != low && !(mn + mb + 2.0 * kEps < mdelta[t] - __ldcg(&mbound[t]))) unsure = 1;
+        if (t != low && !(mn + mb + 2.0 * kEps < mdelta[t] - ld(&mbound[t]))) unsure = 1;
     if (!(mn + mb + total_bound < 1e6)) unsure = 1;  // the reference's `min_delta_jsd = 1e6` initial value
     unsure = __syncthreads_or(unsure);
     *low_out = low;
@@ -834,6 +927,312 @@ k_sel_persist(const double* __restrict__ F, const double* __restrict__ H, uint64
     }
 }
 
+// ---------------------------------------------------------------- SM-replicated selection rounds ----
+// k_sel_persist still pays ~10 dependent L2 round trips per round (scalar block, member list, ticket,
+// last-CTA tail) and two cooperative-groups barriers.  For vectors that fit in shared memory (dim <= 4096,
+// i.e. k <= 6) the whole selection state is instead REPLICATED in every SM:
+//   shared memory: S, T = S - f_lowest (the first operation of both delta_jsd and replace_lowest), member
+//   rows and their entropies, per-member delta / bound;   registers: E, total_jsd, lowest, cursor, window.
+// Per round only 32-byte partial sums cross the L2:
+//   scan    CTA b scores slice p = b % P of candidate c = b / P of the window (P = 4, 2 or 1 CTAs per
+//           candidate, so a short window still uses every SM) and writes {e, t, a, bad};
+//   barrier (one release-add + acquire-spin per CTA);
+//   every CTA combines the partials in the same order and takes the SAME decision (first certain
+//   acceptance / first undecided candidate) — no atomics, no scalar block, no second barrier for an
+//   empty window;
+//   accept  CTA j computes the leave-one-out entropy of member j (CTA n: H(S'/n)) and writes its partial,
+//           every CTA forms S' = clamp(T) + f_cand in its own shared memory;
+//   barrier; every CTA forms the member deltas, the certified argmin and T' = S' - f_lowest'.
+// Arithmetic, bounds and the halt protocol are those of the kernels above (the partial sums only add
+// P - 1 sequential additions, covered by `depth`), so decisions are identical; CTA 0 writes the state
+// back to global memory when the rounds end or halt for the host.
+constexpr unsigned kSmMaxDim = 4096, kSmMaxN = 1024, kSmMaxGrid = 256;
+constexpr double kSmDepth = 4.0;
+
+struct SmPart {
+    double e, t, a;
+    unsigned bad, pad;
+};
+
+struct SmShared {
+    double S[kSmMaxDim];
+    double T[kSmMaxDim];
+    double mH[2][kSmMaxN + 1];
+    double md[kSmMaxN + 1];
+    double mb[kSmMaxN + 1];
+    unsigned members[2][kSmMaxN + 1];
+    double wH[kSmMaxGrid];
+    unsigned wrow[kSmMaxGrid];
+    unsigned char wskip[kSmMaxGrid];
+    unsigned ft, fu, unsure;
+    double2 ltab[64];  // glibc log2 table {1/c, log2 c}
+};
+
+__device__ __forceinline__ void sm_store_part(SmPart* dst, const FastSum& h) {
+    double2* d = reinterpret_cast<double2*>(dst);
+    __stcg(d, make_double2(h.e, h.t));
+    __stcg(d + 1, make_double2(h.a, __longlong_as_double((long long)(h.bad ? 1 : 0))));
+}
+__device__ __forceinline__ FastSum sm_load_part(const SmPart* src) {
+    const double2* d = reinterpret_cast<const double2*>(src);
+    const double2 x = __ldcg(d), y = __ldcg(d + 1);
+    return FastSum{x.x, x.y, y.x, __double_as_longlong(y.y) != 0 ? 1 : 0};
+}
+
+// grid barrier on a monotonic 64-bit counter (zeroed by the host before the launch)
+__device__ __forceinline__ void sm_grid_barrier(unsigned long long* ctr, unsigned long long& target, unsigned grid) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += grid;
+        asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(ctr), "l"(1ull) : "memory");
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
+        } while (v < target);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kFastThreads, 1)
+k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, unsigned dim, double* S_glob,
+                 unsigned* M_glob, uint8_t* is_member, double* mdelta_g, double* mbound_g, SelScal* sc,
+                 const uint8_t* __restrict__ valid, const unsigned* __restrict__ order, SmPart* spart, SmPart* upart,
+                 unsigned long long* bar, unsigned long long* trace) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    SmShared& sm = *reinterpret_cast<SmShared*>(sm_raw);
+    const unsigned tid = threadIdx.x, b = blockIdx.x, G = gridDim.x;
+    unsigned tr_round = 0;
+    auto stamp = [&](int slot) {
+        if (trace && b == 0 && tid == 0 && tr_round < 512) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            trace[tr_round * 4 + slot] = t;
+        }
+    };
+
+    // ---- every CTA loads the state the host / the previous kernels left in global memory ----
+    const unsigned n = sc->n, num = sc->num;
+    const double nd = (double)n, div = __dsub_rn(nd, 1.0);
+    double E = sc->E, total_jsd = sc->total_jsd, total_bound = sc->total_bound;
+    unsigned lowest = sc->lowest, cursor = sc->cursor, window = sc->window, accepts = sc->accepts;
+    unsigned state_unsure = sc->state_unsure, halt = state_unsure ? 1u : 0u, mw = 0;
+    bool touched = false;  // an acceptance happened in this launch: md / mb / total are this kernel's
+    const FastDiv div_n = make_fast_div(nd), div_n1 = make_fast_div(div);
+    dvs_log2_stage_table(sm.ltab);
+    for (unsigned i = tid; i < dim; i += kFastThreads) sm.S[i] = S_glob[i];
+    for (unsigned j = tid; j < n; j += kFastThreads) {
+        const unsigned r = M_glob[j];
+        sm.members[0][j] = r;
+        sm.mH[0][j] = H[r];
+    }
+    __syncthreads();
+    {
+        const double* fl = F + (size_t)sm.members[0][lowest] * dim;
+        for (unsigned i = tid; i < dim; i += kFastThreads) sm.T[i] = __dsub_rn(sm.S[i], fl[i]);
+    }
+    __syncthreads();
+    unsigned long long target = 0;
+    const unsigned wmin = max(1u, G / 4u);
+
+    while (!halt && cursor < num) {
+        stamp(0);
+        window = max(1u, min(window, G));
+        const unsigned P = (dim >= 2048u && window * 4u <= G) ? 4u : ((dim >= 2048u && window * 2u <= G) ? 2u : 1u);
+        const unsigned count = min(window, num - cursor);
+        // window metadata, identical in every CTA: thread c looks at candidate c
+        if (tid < count) {
+            const unsigned row = order[cursor + tid];
+            sm.wrow[tid] = row;
+            sm.wskip[tid] = (!valid[row] || __ldcg(is_member + row)) ? 1 : 0;
+            sm.wH[tid] = H[row];
+        }
+        if (tid == 0) {
+            sm.ft = kNone;
+            sm.fu = kNone;
+        }
+        // ---- scan: slice p of candidate c ----
+        const unsigned c = b / P, p = b % P;
+        if (c < count) {  // CTA-uniform
+            const unsigned row = order[cursor + c];
+            if (valid[row] && !__ldcg(is_member + row)) {
+                const double* fc = F + (size_t)row * dim;
+                const unsigned lo = (unsigned)(((uint64_t)dim * p) / P), hi = (unsigned)(((uint64_t)dim * (p + 1)) / P);
+                const FastSum h = block_entropy_ilp<false>(
+                    lo, hi, [&](unsigned i) { return __dadd_rn(sm.T[i], fc[i]); }, div_n, sm.ltab);
+                if (tid == 0) sm_store_part(spart + b, h);
+            }
+        }
+        stamp(1);
+        sm_grid_barrier(bar, target, G);
+        stamp(2);
+        // ---- decision, redundantly in every CTA ----
+        if (tid < count && !sm.wskip[tid]) {
+            FastSum h = sm_load_part(spart + tid * P);
+            for (unsigned q = 1; q < P; ++q) {
+                const FastSum g = sm_load_part(spart + tid * P + q);
+                h.e += g.e; h.t += g.t; h.a += g.a; h.bad |= g.bad;
+            }
+            const unsigned pos = cursor + tid;
+            const double mean_entropy = __ddiv_rn(__dadd_rn(__dsub_rn(E, sm.mH[mw][lowest]), sm.wH[tid]), nd);
+            const double d = h.e - mean_entropy;
+            const double depth = P > 1u ? kSmDepth : 0.0;
+            const double bd = fast_bound(dim, h.a, mean_entropy, depth);
+            const double thr = total_jsd + kEps, tb = total_bound + 4.0 * kEps;
+            if (h.bad || !fast_total_ok(dim, h.t, depth) || !(d == d)) {
+                atomicMin(&sm.fu, pos);
+            } else if (d - bd > thr + tb) {
+                atomicMin(&sm.ft, pos);
+            } else if (!(d + bd < thr - tb)) {
+                atomicMin(&sm.fu, pos);
+            }
+        }
+        __syncthreads();
+        const unsigned ft = sm.ft, fu = sm.fu;
+        __syncthreads();
+        if (fu < ft) {  // the first interesting candidate is undecided: the host resolves it exactly
+            halt = 1;
+            break;
+        }
+        if (ft == kNone) {  // empty window
+            cursor += count;
+            window = min(window * 2u, G);
+            stamp(3);
+            ++tr_round;
+            continue;
+        }
+        // ---- accept: replace_lowest + leave-one-out update ----
+        const unsigned cand = sm.wrow[ft - cursor];
+        const double Hc = sm.wH[ft - cursor];
+        const unsigned low_row = sm.members[mw][lowest];
+        const double E_new = __dadd_rn(__dsub_rn(E, sm.mH[mw][lowest]), Hc);  // records.rs:101,129
+        const double* fc = F + (size_t)cand * dim;
+        auto member_after = [&](unsigned j) {  // Vec::remove(lowest) + push(cand)
+            return j < lowest ? sm.members[mw][j] : (j + 1 < n ? sm.members[mw][j + 1] : cand);
+        };
+        auto s_new = [&](uint64_t i) {
+            double s = sm.T[i];
+            if (s <= kEps) s = 0.0;
+            return __dadd_rn(s, fc[i]);
+        };
+        bool have_S = false;
+        for (unsigned j = b; j <= n; j += G) {
+            FastSum h;
+            if (j == n) {
+                h = block_entropy_ilp<false>(0u, dim, [&](unsigned i) {
+                    const double s = have_S ? sm.S[i] : s_new(i);
+                    if (!have_S) sm.S[i] = s;
+                    return s;
+                }, div_n, sm.ltab);
+            } else {
+                const double* f = F + (size_t)member_after(j) * dim;
+                h = block_entropy_ilp<true>(0u, dim, [&](unsigned i) {
+                    const double s = have_S ? sm.S[i] : s_new(i);
+                    if (!have_S) sm.S[i] = s;
+                    return __dsub_rn(s, f[i]);
+                }, div_n1, sm.ltab);
+            }
+            if (tid == 0) sm_store_part(upart + j, h);
+            have_S = true;
+        }
+        if (!have_S)
+            for (unsigned i = tid; i < dim; i += kFastThreads) sm.S[i] = s_new(i);
+        if (b == 0 && tid == 0) {
+            is_member[low_row] = 0;
+            is_member[cand] = 1;
+        }
+        stamp(3);
+        sm_grid_barrier(bar, target, G);
+        // ---- every CTA: new member list, deltas, certified argmin, T' ----
+        for (unsigned t = tid; t < n; t += kFastThreads) {
+            sm.members[mw ^ 1][t] = member_after(t);
+            sm.mH[mw ^ 1][t] = t < lowest ? sm.mH[mw][t] : (t + 1 < n ? sm.mH[mw][t + 1] : Hc);
+        }
+        if (tid == 0) sm.unsure = 0;
+        __syncthreads();
+        mw ^= 1;
+        E = E_new;
+        {
+            const FastSum h = sm_load_part(upart + n);
+            const double me = __ddiv_rn(E, nd);
+            total_jsd = h.e - me;
+            total_bound = fast_bound(dim, h.a, me);
+            int uns = (h.bad || !fast_total_ok(dim, h.t)) ? 1 : 0;
+            for (unsigned t = tid; t < n; t += kFastThreads) {
+                const FastSum g = sm_load_part(upart + t);
+                const double mean_entropy = __ddiv_rn(__dsub_rn(E, sm.mH[mw][t]), div);
+                sm.md[t] = g.e - mean_entropy;
+                sm.mb[t] = fast_bound(dim, g.a, mean_entropy);
+                if (g.bad || !fast_total_ok(dim, g.t)) uns = 1;
+            }
+            if (uns) sm.unsure = 1;  // benign race: every writer stores 1
+        }
+        __syncthreads();
+        unsigned lo2 = 0;
+        unsigned unsure = finalize_fast_block<false>(sm.md, sm.mb, n, total_jsd, total_bound, &lo2);
+        unsure |= sm.unsure;
+        lowest = lo2;
+        touched = true;
+        window = max(wmin, min(G, 2u * (ft - cursor + 1u)));
+        cursor = ft + 1u;
+        ++accepts;
+        ++tr_round;
+        if (unsure) {  // the argmin / a sum check could not be certified: the host redoes the update exactly
+            state_unsure = 1;
+            halt = 1;
+            break;
+        }
+        const double* fl = F + (size_t)sm.members[mw][lowest] * dim;
+        for (unsigned i = tid; i < dim; i += kFastThreads) sm.T[i] = __dsub_rn(sm.S[i], fl[i]);
+        __syncthreads();
+    }
+
+    // ---- CTA 0 hands the state back in the layout the other kernels and the host loop use ----
+    if (b == 0) {
+        __syncthreads();
+        if (touched) {
+            for (unsigned i = tid; i < dim; i += kFastThreads) S_glob[i] = sm.S[i];
+            for (unsigned j = tid; j < n; j += kFastThreads) {
+                M_glob[j] = sm.members[mw][j];
+                mdelta_g[j] = sm.md[j];
+                mbound_g[j] = sm.mb[j];
+            }
+        }
+        if (tid == 0) {
+            if (touched) {
+                sc->E = E;
+                sc->total_jsd = total_jsd;
+                sc->total_bound = total_bound;
+                sc->lowest = lowest;
+                sc->exact = 0;
+            }
+            sc->state_unsure = state_unsure;
+            sc->ticket = 0;
+            sc->first_true = kNone;
+            sc->first_panic = kNone;
+            sc->first_unsure = kNone;
+            sc->cursor = cursor;
+            sc->window = window;
+            sc->accepts = accepts;
+            sc->halt = halt;
+        }
+    }
+}
+
+// test hook: the two building blocks of block_entropy_ilp on arbitrary operands
+__global__ void k_debug_fast_terms(const double* a, const double* b, double* m_out, double* l_out, int* sp_out, uint64_t n) {
+    __shared__ double2 ltab[64];
+    dvs_log2_stage_table(ltab);
+    __syncthreads();
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double m = div_exact(a[i], make_fast_div(b[i]));
+    int sp = 0;
+    const double l = dvs_log2_main(m, ltab, sp);
+    m_out[i] = m;
+    l_out[i] = l;
+    sp_out[i] = sp;
+}
+
 __global__ void k_sel_set_dev(SelScal* sc, unsigned cursor, unsigned window, unsigned window_max, unsigned num,
                               unsigned accepts, unsigned which) {
     sc->cursor = cursor;
@@ -1047,18 +1446,38 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
     const char* dev_env = getenv("DVS_SELECT_HOST_LOOP");
     const bool use_dev = use_fast && !(dev_env && dev_env[0] == '1');
     constexpr int kRoundsPerBatch = 32;
-    // DVS_SELECT_PERSIST=0 keeps the two-launches-per-round form (A/B measurements, fallback)
+    // DVS_SELECT_PERSIST=0 keeps the two-launches-per-round form, =1 the global-state persistent kernel
+    // (A/B measurements, fallbacks); default: SM-replicated rounds when the state fits in shared memory
     const char* per_env = getenv("DVS_SELECT_PERSIST");
-    int coop = 0, per_sm = 0;
+    int coop = 0, per_sm = 0, per_sm2 = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
     if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sel_persist, kFastThreads, 0) != cudaSuccess)
         per_sm = 0;
     const bool use_persist = use_dev && coop && per_sm > 0 && !(per_env && per_env[0] == '0');
     const unsigned persist_grid = (unsigned)ctx->sm_count * (unsigned)std::min(per_sm, 2);
+    bool sm_ok = use_persist && !(per_env && per_env[0] == '1') && dim <= kSmMaxDim;
+    if (sm_ok) {
+        sm_ok = cudaFuncSetAttribute(k_sel_persist_sm, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(SmShared)) == cudaSuccess &&
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_sel_persist_sm, kFastThreads,
+                                                              sizeof(SmShared)) == cudaSuccess &&
+                per_sm2 > 0;
+        (void)cudaGetLastError();
+    }
+    const unsigned sm_grid = std::min<unsigned>((unsigned)ctx->sm_count, kSmMaxGrid);
+    DevBuf<SmPart> d_spart, d_upart;
+    DevBuf<unsigned long long> d_bar;
+    if (sm_ok) {
+        DVS_TRY(d_spart.alloc(kSmMaxGrid));
+        DVS_TRY(d_upart.alloc(kSmMaxN + 1));
+        DVS_TRY(d_bar.alloc(1));
+    }
     while (cursor < num) {
         if (use_persist && (!grow_mode || n == max_size)) {
             // every remaining round in one cooperative launch (until done, or halted for the host)
-            k_sel_set_dev<<<1, 1, 0, st>>>(cur->sc.p, cursor, std::min(window, persist_grid), persist_grid, num, accepts,
+            const bool use_sm = sm_ok && n <= kSmMaxN;
+            const unsigned grid = use_sm ? sm_grid : persist_grid;
+            k_sel_set_dev<<<1, 1, 0, st>>>(cur->sc.p, cursor, std::min(window, grid), grid, num, accepts,
                                            (unsigned)cur->which);
             DVS_LAUNCHED(ctx);
             const double* a_F = f->freqs.p;
@@ -1080,8 +1499,22 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
                 DVS_CUDA_TRY(cudaMemsetAsync(d_trace.p, 0, 2048 * sizeof(unsigned long long), st));
                 a_trace = d_trace.p;
             }
-            void* args[] = {&a_F, &a_H, &a_dim, &a_S0, &a_S1, &a_M0, &a_M1, &a_mem, &a_md, &a_mb, &a_sc, &a_valid, &a_order, &a_rounds, &a_trace};
-            DVS_CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_sel_persist, dim3(persist_grid), dim3(kFastThreads), args, 0, st));
+            if (use_sm) {
+                unsigned a_dim32 = (unsigned)dim;
+                double* a_S = cur->S();
+                unsigned* a_M = cur->members();
+                SmPart *a_sp = d_spart.p, *a_up = d_upart.p;
+                unsigned long long* a_bar = d_bar.p;
+                DVS_CUDA_TRY(cudaMemsetAsync(d_bar.p, 0, sizeof(unsigned long long), st));
+                void* args[] = {&a_F, &a_H, &a_dim32, &a_S, &a_M, &a_mem, &a_md, &a_mb, &a_sc, &a_valid, &a_order,
+                                &a_sp, &a_up, &a_bar, &a_trace};
+                DVS_CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_sel_persist_sm, dim3(grid), dim3(kFastThreads), args,
+                                                         sizeof(SmShared), st));
+            } else {
+                void* args[] = {&a_F, &a_H, &a_dim, &a_S0, &a_S1, &a_M0, &a_M1, &a_mem, &a_md, &a_mb, &a_sc, &a_valid,
+                                &a_order, &a_rounds, &a_trace};
+                DVS_CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_sel_persist, dim3(grid), dim3(kFastThreads), args, 0, st));
+            }
             ctx->launches++;
             DVS_TRY(sel.read(*cur));
             if (a_trace) {  // phase timeline of CTA 0 to the file named by DVS_SELECT_TRACE
@@ -1267,6 +1700,28 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
     }
     *size_out = n;
     ctx->last_accepts = accepts;
+    return DVS_OK;
+}
+
+int dvs_debug_fast_terms(dvs_ctx* ctx, const double* a, const double* b, double* m, double* l, int32_t* special,
+                         uint64_t n) {
+    if (n == 0) return DVS_OK;
+    DVS_CUDA_TRY(dvs::enter(ctx));
+    DevBuf<double> da, db, dm, dl;
+    DevBuf<int> ds;
+    DVS_TRY(da.alloc(n));
+    DVS_TRY(db.alloc(n));
+    DVS_TRY(dm.alloc(n));
+    DVS_TRY(dl.alloc(n));
+    DVS_TRY(ds.alloc(n));
+    DVS_CUDA_TRY(cudaMemcpyAsync(da.p, a, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    DVS_CUDA_TRY(cudaMemcpyAsync(db.p, b, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    k_debug_fast_terms<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(da.p, db.p, dm.p, dl.p, ds.p, n);
+    DVS_LAUNCHED(ctx);
+    DVS_CUDA_TRY(cudaMemcpyAsync(m, dm.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    DVS_CUDA_TRY(cudaMemcpyAsync(l, dl.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    DVS_CUDA_TRY(cudaMemcpyAsync(special, ds.p, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    DVS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return DVS_OK;
 }
 

@@ -221,6 +221,11 @@ int dvs_debug_pack_host(const uint8_t* src, uint64_t n, uint8_t* packed, uint32_
                         uint32_t cap, uint32_t* nexc);
 /* device evaluation of the glibc-log2 restatement on n doubles */
 int dvs_debug_log2(dvs_ctx* ctx, const double* x, double* y, uint64_t n);
+/* building blocks of the bounded-error selection kernels: m[i] = a[i] / b[i] by the reciprocal + two
+ * fused-remainder steps (must equal IEEE division), l[i] = table path of the glibc log2 restatement,
+ * special[i] != 0 where that path does not apply (m near 1, <= 0, subnormal, inf, nan) */
+int dvs_debug_fast_terms(dvs_ctx* ctx, const double* a, const double* b, double* m, double* l, int32_t* special,
+                         uint64_t n);
 /* exact (reference-order) entropy of each host row on the device; err[r]=1 when the reference
  * would panic (sum check, src/record.rs:101-104) */
 int dvs_debug_entropy(dvs_ctx* ctx, const double* rows, uint32_t nrec, uint64_t dim, double* out, uint8_t* err);

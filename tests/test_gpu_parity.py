@@ -41,6 +41,37 @@ def test_log2_device_bit_identical_to_libm(lib, ctx, orc):
     assert same.all(), f"first mismatch at x={xs[~same][0]!r}"
 
 
+def test_fast_terms_division_and_table_log2_are_bit_exact(lib, ctx, orc):
+    """building blocks of the SM-replicated selection rounds: the reciprocal + fused-remainder division
+    must equal IEEE division and the table path of the log2 restatement must equal libm wherever it
+    applies; everything else must be flagged"""
+    rng = np.random.default_rng(2026)
+    n = 1_500_000
+    b = rng.integers(1, 4100, n).astype(np.float64)
+    a = np.empty(n)
+    third = n // 3
+    a[:third] = rng.integers(0, 200_000, third) / rng.integers(1, 5_000_000, third)      # frequency-like
+    a[third:2 * third] = np.ldexp(rng.random(third) + 1.0, rng.integers(-200, 12, third))  # any mantissa / exponent
+    a[2 * third:] = b[2 * third:] * (1.0 + (rng.random(n - 2 * third) - 0.5) * 0.12)        # quotients around 1
+    a[::97] = 0.0
+    a[1::1013] *= -1.0
+    m, lg, sp = lib.debug_fast_terms(ctx, a, b)
+    ref_m = a / b
+    nz = a != 0
+    assert np.array_equal(m[nz].view(np.uint64), ref_m[nz].view(np.uint64)) and (m[~nz] == 0).all()
+    near1 = (ref_m >= float.fromhex("0x1.ea4afp-1")) & (ref_m < float.fromhex("0x1.0b559p+0"))
+    expect_sp = near1 | ~(ref_m > 0) | (ref_m < 2.2250738585072014e-308)
+    assert np.array_equal(sp != 0, expect_sp)
+    ok = ~expect_sp
+    assert ok.sum() > n // 2
+    ref_l = lib.debug_log2(ctx, ref_m[ok])  # = libm bit for bit (test_log2_device_bit_identical_to_libm)
+    assert np.array_equal(lg[ok].view(np.uint64), ref_l.view(np.uint64))
+    xs, ys = orc.log2_samples(7, 200_000)
+    m2, lg2, sp2 = lib.debug_fast_terms(ctx, xs, np.ones_like(xs))
+    good = sp2 == 0
+    assert good.sum() > 50_000 and np.array_equal(lg2[good].view(np.uint64), ys[good].view(np.uint64))
+
+
 @pytest.mark.parametrize("dim", [1, 2, 4, 5, 63, 64, 511, 512, 513, 1024, 4096, 5000])
 def test_entropy_device_matches_reference_order(lib, ctx, orc, dim):
     rng = np.random.default_rng(dim)
@@ -267,15 +298,43 @@ def test_select_fast_path_equals_exact_only(lib, ctx, orc, monkeypatch):
         i0, d0, s0 = kf.select(order, mode, lo, hi)
         assert ctx._lib.dvs_select_last_exact_evals(ctx.handle) == 0
         monkeypatch.setenv("DVS_SELECT_EXACT_ONLY", "0")
-        for host_loop in ("1", "0"):  # host-driven fast rounds, then device-driven rounds
+        # host-driven fast rounds, two launches per device-driven round, the global-state persistent
+        # kernel, the SM-replicated persistent kernel (default)
+        for host_loop, persist in (("1", "0"), ("0", "0"), ("0", "1"), ("0", "2")):
             monkeypatch.setenv("DVS_SELECT_HOST_LOOP", host_loop)
+            monkeypatch.setenv("DVS_SELECT_PERSIST", persist)
             i1, d1, s1 = kf.select(order, mode, lo, hi)
             assert i0.tolist() == i1.tolist() and np.array_equal(d0, d1) and np.array_equal(s0, s1)
             assert ctx._lib.dvs_select_last_exact_evals(ctx.handle) <= 5  # decisions are far from ties here
+    monkeypatch.delenv("DVS_SELECT_PERSIST")
     _, of, oe, ov = orc.count_batch(flat, off, 5)
     exp = orc.select_rows(of, oe, order, "nmost", 40, valid=ov)
     i1, d1, s1 = kf.select(order, lib.MODE_NMOST, 40)
     assert i1.tolist() == exp.ids.tolist() and np.array_equal(d1, exp.delta_jsd)
+
+
+@pytest.mark.parametrize("n", [3, 30, 160])
+def test_select_sm_replicated_rounds_k6(lib, ctx, orc, monkeypatch, n):
+    """k=6 (4096-element vectors): the SM-replicated kernel splits one candidate over 4 / 2 / 1 CTAs and
+    loops member tasks when n + 1 exceeds the grid; decisions must equal the oracle's and the other forms'"""
+    flat, off = lib.synth_host(4242 + n, 1300, 9, 20_000)
+    kf = lib.KFreqs.count(ctx, lib.SeqSet.upload(ctx, flat, off), 6)
+    _, of, oe, ov = orc.count_batch(flat, off, 6)
+    order = np.random.default_rng(n).permutation(1300).astype(np.uint32)
+    exp = orc.select_rows(of, oe, order, "nmost", n, valid=ov)
+    res = {}
+    for persist in ("2", "1", "0"):
+        monkeypatch.setenv("DVS_SELECT_PERSIST", persist)
+        idx, delta, stats = kf.select(order, lib.MODE_NMOST, n)
+        res[persist] = (idx.tolist(), delta.tolist(), stats.tolist(), int(ctx._lib.dvs_select_last_accepts(ctx.handle)))
+        assert idx.tolist() == exp.ids.tolist() and np.array_equal(delta, exp.delta_jsd)
+        assert stats[0] == exp.total_jsd and stats[4] == exp.summed_entropies
+    assert res["2"] == res["1"] == res["0"]
+    assert res["2"][3] > 5  # the rounds actually accepted candidates
+    monkeypatch.setenv("DVS_SELECT_PERSIST", "2")
+    m_idx, m_delta, m_stats = kf.select(order, lib.MODE_MAX_COV, 10, 40)
+    mexp = orc.select_rows(of, oe, order, "cov", 10, 40, valid=ov)
+    assert m_idx.tolist() == mexp.ids.tolist() and np.array_equal(m_delta, mexp.delta_jsd)
 
 
 def test_select_large_sets_match_oracle(lib, ctx, orc):
