@@ -148,17 +148,18 @@ __device__ __forceinline__ double dvs_log2_main(double x, const double2* __restr
     constexpr double A0[6] = {DVS_LOG2_POLY_A};
     const double InvLn2hi = DVS_LOG2_INVLN2HI;
     const double InvLn2lo = DVS_LOG2_INVLN2LO;
-    const uint64_t ix = bits_(x);
-    const uint32_t top = (uint32_t)(ix >> 48);
-    special |= (ix - 0x3feea4af00000000ULL < 0x000210aa00000000ULL) ? 1 : 0;
+    // all constants of the reference code have zero low words, so the integer part only needs the high
+    // word of x (the exponent and the top 20 mantissa bits)
+    const uint32_t hi32 = (uint32_t)__double2hiint(x);
+    const uint32_t top = hi32 >> 16;
+    special |= (hi32 - 0x3feea4afu < 0x000210aau) ? 1 : 0;
     special |= (top - 0x0010u >= 0x7ff0u - 0x0010u) ? 1 : 0;
-    const uint64_t tmp = ix - 0x3fe6000000000000ULL;
-    const int i = (int)((tmp >> 46) & 63);
-    const int k = (int)((int64_t)tmp >> 52);
-    const uint64_t iz = ix - (tmp & 0xfff0000000000000ULL);
+    const uint32_t tmp = hi32 - 0x3fe60000u;
+    const int i = (int)((tmp >> 14) & 63u);
+    const int k = (int)tmp >> 20;
+    const double z = __hiloint2double((int)(hi32 - (tmp & 0xfff00000u)), __double2loint(x));
     const double2 ic = tab[i];
     const double invc = ic.x, logc = ic.y;
-    const double z = dbl_(iz);
     const double kd = (double)k;
 
     const double t3 = add_(kd, logc);

@@ -396,53 +396,61 @@ __device__ __forceinline__ double div_exact(double a, const FastDiv& d) {
     return __fma_rn(r, d.y, q);
 }
 
-template <bool CLAMP, class Num>
+// m is usable by the table path (and was divided exactly) iff 2^-900 <= m < 0x1.ea4afp-1: one unsigned
+// compare on its high word; negative, NaN, inf, zero, subnormal and "near 1 or above" all fall outside.
+// (Below 2^-900 the fused remainders of div_exact could underflow; k-mer frequencies are >= ~1e-10.)
+__device__ __forceinline__ bool fast_term_ok(double m) {
+    return (uint32_t)__double2hiint(m) - 0x07b00000u < 0x3feea4afu - 0x07b00000u;
+}
+
+template <bool CLAMP, int BATCH, class Num>
 __device__ FastSum block_entropy_ilp(unsigned lo, unsigned hi, Num num, const FastDiv dv,
                                      const double2* __restrict__ ltab) {
     __shared__ double s_part[3][kFastThreads / 32];
     __shared__ int s_bad[kFastThreads / 32];
     double e0 = 0.0, e1 = 0.0, t0 = 0.0, t1 = 0.0, a0 = 0.0, a1 = 0.0;
-    int bad = 0;
-    constexpr int kBatch = 8;
-    for (unsigned base = lo; base < hi; base += kBatch * kFastThreads) {
-        double x[kBatch], l[kBatch];
-        int sp[kBatch];
+    bool bad = false;
+    for (unsigned base = lo; base < hi; base += BATCH * kFastThreads) {
+        double x[BATCH], l[BATCH];
 #pragma unroll
-        for (int q = 0; q < kBatch; ++q) {
+        for (int q = 0; q < BATCH; ++q) {
             const unsigned i = base + threadIdx.x + (unsigned)q * kFastThreads;
             x[q] = i < hi ? num(i) : 0.0;
         }
 #pragma unroll
-        for (int q = 0; q < kBatch; ++q) {
-            // |numerator| below 1e-280 (never a k-mer frequency) would make the remainders inexact
-            sp[q] = (x[q] != 0.0 && fabs(x[q]) < 1e-280) ? 1 : 0;
+        for (int q = 0; q < BATCH; ++q) {
             double m = div_exact(x[q], dv);
             if (CLAMP) m = (m <= kEps) ? 0.0 : m;
             x[q] = m;
         }
 #pragma unroll
-        for (int q = 0; q < kBatch; ++q) l[q] = dvs_log2_main(x[q], ltab, sp[q]);
+        for (int q = 0; q < BATCH; ++q) {
+            int ignored = 0;
+            l[q] = dvs_log2_main(x[q], ltab, ignored);
+        }
 #pragma unroll
-        for (int q = 0; q < kBatch; q += 2) {
-            const bool nz0 = !(x[q] == 0.0), nz1 = !(x[q + 1] == 0.0);
-            const double tm0 = nz0 ? __dmul_rn(-x[q], l[q]) : 0.0;
-            const double tm1 = nz1 ? __dmul_rn(-x[q + 1], l[q + 1]) : 0.0;
-            bad |= (nz0 && (sp[q] || !(x[q] > 0.0))) ? 1 : 0;
-            bad |= (nz1 && (sp[q + 1] || !(x[q + 1] > 0.0))) ? 1 : 0;
-            e0 += tm0; a0 += fabs(tm0); t0 += nz0 ? x[q] : 0.0;
-            e1 += tm1; a1 += fabs(tm1); t1 += nz1 ? x[q + 1] : 0.0;
+        for (int q = 0; q < BATCH; ++q) {
+            const bool ok = fast_term_ok(x[q]);
+            bad |= !ok && !(x[q] == 0.0);
+            const double tm = ok ? __dmul_rn(-x[q], l[q]) : 0.0;
+            if (q & 1) {
+                e1 += tm; a1 += fabs(tm); t1 += x[q];
+            } else {
+                e0 += tm; a0 += fabs(tm); t0 += x[q];
+            }
         }
     }
     double e = e0 + e1, t = t0 + t1, a = a0 + a1;
+    int badi = bad ? 1 : 0;
     for (int o = 16; o; o >>= 1) {
         e += __shfl_xor_sync(0xffffffffu, e, o);
         t += __shfl_xor_sync(0xffffffffu, t, o);
         a += __shfl_xor_sync(0xffffffffu, a, o);
-        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+        badi |= __shfl_xor_sync(0xffffffffu, badi, o);
     }
     const int w = threadIdx.x >> 5;
     if ((threadIdx.x & 31) == 0) {
-        s_part[0][w] = e; s_part[1][w] = t; s_part[2][w] = a; s_bad[w] = bad;
+        s_part[0][w] = e; s_part[1][w] = t; s_part[2][w] = a; s_bad[w] = badi;
     }
     __syncthreads();
     FastSum r{0.0, 0.0, 0.0, 0};
@@ -931,93 +939,145 @@ k_sel_persist(const double* __restrict__ F, const double* __restrict__ H, uint64
 // k_sel_persist still pays ~10 dependent L2 round trips per round (scalar block, member list, ticket,
 // last-CTA tail) and two cooperative-groups barriers.  For vectors that fit in shared memory (dim <= 4096,
 // i.e. k <= 6) the whole selection state is instead REPLICATED in every SM:
-//   shared memory: S, T = S - f_lowest (the first operation of both delta_jsd and replace_lowest), member
-//   rows and their entropies, per-member delta / bound;   registers: E, total_jsd, lowest, cursor, window.
-// Per round only 32-byte partial sums cross the L2:
+//   shared memory: S, member rows and their entropies, per-member delta / bound, and the (row, valid,
+//   entropy) of the next 512 positions of `order` (their rows are prefetched into L2 when the chunk is
+//   staged);   registers: E, total_jsd, lowest, cursor, window.  (The global is_member map is only
+//   brought up to date when the kernel ends.)
+// Per round only 32-byte partial sums cross the L2, and they carry their own arrival flag, so there is no
+// grid barrier at all:
 //   scan    CTA b scores slice p = b % P of candidate c = b / P of the window (P = 4, 2 or 1 CTAs per
-//           candidate, so a short window still uses every SM) and writes {e, t, a, bad};
-//   barrier (one release-add + acquire-spin per CTA);
-//   every CTA combines the partials in the same order and takes the SAME decision (first certain
-//   acceptance / first undecided candidate) — no atomics, no scalar block, no second barrier for an
-//   empty window;
-//   accept  CTA j computes the leave-one-out entropy of member j (CTA n: H(S'/n)) and writes its partial,
-//           every CTA forms S' = clamp(T) + f_cand in its own shared memory;
-//   barrier; every CTA forms the member deltas, the certified argmin and T' = S' - f_lowest'.
+//           candidate, so a short window still uses every SM) and publishes {e, t, a, bad | tag} as two
+//           self-validating 128-bit stores (tag = number of the exchange);
+//   gather  every CTA polls the window's slots until their tags match (one L2 round trip after the last
+//           writer), combines the partials in the same order and takes the SAME decision (first certain
+//           acceptance / first undecided candidate) — no atomics, no scalar block;
+//   accept  CTA j computes the leave-one-out entropy of member j (CTA n: H(S'/n)) and publishes its partial,
+//           every CTA forms S' = clamp(S - f_lowest) + f_cand in its own shared memory;
+//   gather  every CTA forms the member deltas and the certified argmin.
+// Slot reuse is safe without resets: a CTA can only publish exchange x+2 of a kind after it has gathered
+// x+1, which needs every CTA to have published x+1, i.e. to have finished gathering x; scan exchanges can
+// follow each other directly (empty window), so their slots are double buffered.
 // Arithmetic, bounds and the halt protocol are those of the kernels above (the partial sums only add
-// P - 1 sequential additions, covered by `depth`), so decisions are identical; CTA 0 writes the state
-// back to global memory when the rounds end or halt for the host.
-constexpr unsigned kSmMaxDim = 4096, kSmMaxN = 1024, kSmMaxGrid = 256;
+// P - 1 sequential additions, covered by `depth`; `a` travels as a float rounded UP, which only widens a
+// bound), so decisions are identical; CTA 0 writes the state back to global memory when the rounds end or
+// halt for the host.
+constexpr unsigned kSmMaxDim = 4096, kSmMaxN = 1024, kSmMaxGrid = 256, kSmChunk = kFastThreads;
 constexpr double kSmDepth = 4.0;
 
-struct SmPart {
-    double e, t, a;
-    unsigned bad, pad;
+struct __align__(16) SmPart {
+    unsigned long long w[4];  // {e, bad<<32 | tag}, {t, float_ru(a)<<32 | tag}
 };
 
 struct SmShared {
     double S[kSmMaxDim];
-    double T[kSmMaxDim];
     double mH[2][kSmMaxN + 1];
     double md[kSmMaxN + 1];
     double mb[kSmMaxN + 1];
     unsigned members[2][kSmMaxN + 1];
-    double wH[kSmMaxGrid];
-    unsigned wrow[kSmMaxGrid];
-    unsigned char wskip[kSmMaxGrid];
+    double cH[kSmChunk];
+    unsigned crow[kSmChunk];
+    unsigned char cvalid[kSmChunk];
+    double pe[kSmMaxGrid], pt[kSmMaxGrid], pa[kSmMaxGrid];
+    unsigned char pbad[kSmMaxGrid], wskip[kSmMaxGrid];
     unsigned ft, fu, unsure;
     double2 ltab[64];  // glibc log2 table {1/c, log2 c}
 };
 
-__device__ __forceinline__ void sm_store_part(SmPart* dst, const FastSum& h) {
-    double2* d = reinterpret_cast<double2*>(dst);
-    __stcg(d, make_double2(h.e, h.t));
-    __stcg(d + 1, make_double2(h.a, __longlong_as_double((long long)(h.bad ? 1 : 0))));
+__device__ __forceinline__ void sm_st128(void* p, unsigned long long lo, unsigned long long hi) {
+    asm volatile("{ .reg .b128 v; mov.b128 v, {%1, %2}; st.relaxed.gpu.global.b128 [%0], v; }" ::"l"(p), "l"(lo), "l"(hi)
+                 : "memory");
 }
-__device__ __forceinline__ FastSum sm_load_part(const SmPart* src) {
-    const double2* d = reinterpret_cast<const double2*>(src);
-    const double2 x = __ldcg(d), y = __ldcg(d + 1);
-    return FastSum{x.x, x.y, y.x, __double_as_longlong(y.y) != 0 ? 1 : 0};
+__device__ __forceinline__ void sm_ld128(const void* p, unsigned long long& lo, unsigned long long& hi) {
+    asm volatile("{ .reg .b128 v; ld.relaxed.gpu.global.b128 v, [%2]; mov.b128 {%0, %1}, v; }"
+                 : "=l"(lo), "=l"(hi)
+                 : "l"(p)
+                 : "memory");
+}
+__device__ __forceinline__ void sm_publish(SmPart* slot, const FastSum& h, unsigned tag) {
+    sm_st128(&slot->w[0], (unsigned long long)__double_as_longlong(h.e), ((unsigned long long)(h.bad ? 1u : 0u) << 32) | tag);
+    sm_st128(&slot->w[2], (unsigned long long)__double_as_longlong(h.t),
+             ((unsigned long long)__float_as_uint(__double2float_ru(h.a)) << 32) | tag);
+}
+__device__ __forceinline__ FastSum sm_gather(const SmPart* slot, unsigned tag) {
+    unsigned long long w0, w1, w2, w3;
+    do sm_ld128(&slot->w[0], w0, w1); while ((unsigned)w1 != tag);
+    do sm_ld128(&slot->w[2], w2, w3); while ((unsigned)w3 != tag);
+    return FastSum{__longlong_as_double((long long)w0), __longlong_as_double((long long)w2),
+                   (double)__uint_as_float((unsigned)(w3 >> 32)), (int)(w1 >> 32)};
 }
 
-// grid barrier on a monotonic 64-bit counter (zeroed by the host before the launch)
-__device__ __forceinline__ void sm_grid_barrier(unsigned long long* ctr, unsigned long long& target, unsigned grid) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        target += grid;
-        asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(ctr), "l"(1ull) : "memory");
-        unsigned long long v;
-        do {
-            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
-        } while (v < target);
+// finalize_fast_block on this CTA's shared-memory copies, with the cross-warp step done redundantly by
+// every thread (one barrier less, no serial tail on thread 0)
+__device__ __forceinline__ unsigned sm_finalize(double* md, const double* mb_, unsigned n, double total,
+                                                double total_bound, unsigned* low_out) {
+    __shared__ double s_mn[kFastThreads / 32], s_mb[kFastThreads / 32];
+    __shared__ unsigned s_ix[kFastThreads / 32];
+    double mn = 1e300, mb = 0.0;
+    unsigned ix = kNone;
+    for (unsigned t = threadIdx.x; t < n; t += blockDim.x) {
+        const double d = total - md[t];
+        md[t] = d;
+        if (d < mn || (d == mn && t < ix)) {
+            mn = d; mb = mb_[t]; ix = t;
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        const double omn = __shfl_xor_sync(0xffffffffu, mn, o), omb = __shfl_xor_sync(0xffffffffu, mb, o);
+        const unsigned oix = __shfl_xor_sync(0xffffffffu, ix, o);
+        if (omn < mn || (omn == mn && oix < ix)) {
+            mn = omn; mb = omb; ix = oix;
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_mn[threadIdx.x >> 5] = mn; s_mb[threadIdx.x >> 5] = mb; s_ix[threadIdx.x >> 5] = ix;
     }
     __syncthreads();
+    mn = s_mn[0]; mb = s_mb[0]; ix = s_ix[0];
+#pragma unroll
+    for (unsigned w = 1; w < kFastThreads / 32; ++w) {
+        const double wmn = s_mn[w];
+        const unsigned wix = s_ix[w];
+        if (wmn < mn || (wmn == mn && wix < ix)) {
+            mn = wmn; mb = s_mb[w]; ix = wix;
+        }
+    }
+    const unsigned low = (ix == kNone) ? 0u : ix;
+    int unsure = 0;
+    for (unsigned t = threadIdx.x; t < n; t += blockDim.x)
+        if (t != low && !(mn + mb + 2.0 * kEps < md[t] - mb_[t])) unsure = 1;
+    if (!(mn + mb + total_bound < 1e6)) unsure = 1;  // the reference's `min_delta_jsd = 1e6` initial value
+    unsure = __syncthreads_or(unsure);  // (also fences s_mn / s_mb / s_ix for the next call)
+    *low_out = low;
+    return (unsigned)unsure;
 }
+
+constexpr int kSmTraceSlots = 8;
 
 __global__ void __launch_bounds__(kFastThreads, 1)
 k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, unsigned dim, double* S_glob,
                  unsigned* M_glob, uint8_t* is_member, double* mdelta_g, double* mbound_g, SelScal* sc,
                  const uint8_t* __restrict__ valid, const unsigned* __restrict__ order, SmPart* spart, SmPart* upart,
-                 unsigned long long* bar, unsigned long long* trace) {
+                 unsigned long long* trace) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     SmShared& sm = *reinterpret_cast<SmShared*>(sm_raw);
     const unsigned tid = threadIdx.x, b = blockIdx.x, G = gridDim.x;
     unsigned tr_round = 0;
-    auto stamp = [&](int slot) {
-        if (trace && b == 0 && tid == 0 && tr_round < 512) {
+    auto stamp = [&](int slot) {  // DVS_SELECT_TRACE: CTA 0's timeline of the first 256 rounds
+        if (trace && b == 0 && tid == 0 && tr_round < 256) {
             unsigned long long t;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-            trace[tr_round * 4 + slot] = t;
+            trace[tr_round * kSmTraceSlots + slot] = t;
         }
     };
 
     // ---- every CTA loads the state the host / the previous kernels left in global memory ----
     const unsigned n = sc->n, num = sc->num;
     const double nd = (double)n, div = __dsub_rn(nd, 1.0);
+    const FastDiv div_n = make_fast_div(nd), div_n1 = make_fast_div(div);
     double E = sc->E, total_jsd = sc->total_jsd, total_bound = sc->total_bound;
     unsigned lowest = sc->lowest, cursor = sc->cursor, window = sc->window, accepts = sc->accepts;
     unsigned state_unsure = sc->state_unsure, halt = state_unsure ? 1u : 0u, mw = 0;
     bool touched = false;  // an acceptance happened in this launch: md / mb / total are this kernel's
-    const FastDiv div_n = make_fast_div(nd), div_n1 = make_fast_div(div);
     dvs_log2_stage_table(sm.ltab);
     for (unsigned i = tid; i < dim; i += kFastThreads) sm.S[i] = S_glob[i];
     for (unsigned j = tid; j < n; j += kFastThreads) {
@@ -1026,59 +1086,89 @@ k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, uns
         sm.mH[0][j] = H[r];
     }
     __syncthreads();
-    {
-        const double* fl = F + (size_t)sm.members[0][lowest] * dim;
-        for (unsigned i = tid; i < dim; i += kFastThreads) sm.T[i] = __dsub_rn(sm.S[i], fl[i]);
-    }
-    __syncthreads();
-    unsigned long long target = 0;
     const unsigned wmin = max(1u, G / 4u);
+    // loop-invariant factors of fast_bound / fast_total_ok (same expressions, same rounding)
+    const double kb0 = ((double)dim + fast_slack(dim) + 16.0) * 1.2e-16;
+    const double kb4 = ((double)dim + fast_slack(dim, kSmDepth) + 16.0) * 1.2e-16;
+    const double lim0 = ((double)dim + 1.0 - fast_slack(dim) - 2.0) * 1.1102230246251565e-16;
+    const double lim4 = ((double)dim + 1.0 - fast_slack(dim, kSmDepth) - 2.0) * 1.1102230246251565e-16;
+    auto total_ok = [](double t, double lim) { return lim > 0.0 && fabs(t - 1.0) <= lim; };
+    unsigned xs = 0, xu = 0;       // scan / update exchanges so far (= tags)
+    unsigned cbase = 0, cend = 0;  // positions [cbase, cend) of `order` are staged in shared memory
 
     while (!halt && cursor < num) {
         stamp(0);
         window = max(1u, min(window, G));
         const unsigned P = (dim >= 2048u && window * 4u <= G) ? 4u : ((dim >= 2048u && window * 2u <= G) ? 2u : 1u);
         const unsigned count = min(window, num - cursor);
-        // window metadata, identical in every CTA: thread c looks at candidate c
-        if (tid < count) {
-            const unsigned row = order[cursor + tid];
-            sm.wrow[tid] = row;
-            sm.wskip[tid] = (!valid[row] || __ldcg(is_member + row)) ? 1 : 0;
-            sm.wH[tid] = H[row];
+        if (cursor < cbase || cursor + count > cend) {  // stage the next chunk of positions (CTA-uniform)
+            __syncthreads();
+            cbase = cursor;
+            cend = min(num, cbase + kSmChunk);
+            if (cbase + tid < cend) {
+                const unsigned row = order[cbase + tid];
+                sm.crow[tid] = row;
+                sm.cvalid[tid] = valid[row];
+                sm.cH[tid] = H[row];
+            }
+            // ... and pull their rows towards L2, one 128-byte line per prefetch, rows dealt over the CTAs
+            for (unsigned r = b; r < cend - cbase; r += G) {
+                const double* fr = F + (size_t)order[cbase + r] * dim;
+                for (unsigned l = tid * 16u; l < dim; l += kFastThreads * 16u)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(fr + l));
+            }
+            __syncthreads();
         }
+        const unsigned coff = cursor - cbase;
         if (tid == 0) {
             sm.ft = kNone;
             sm.fu = kNone;
         }
+        if (tid < count) sm.wskip[tid] = sm.cvalid[coff + tid] ? 0 : 1;
         // ---- scan: slice p of candidate c ----
+        ++xs;
+        SmPart* const sbuf = spart + (xs & 1u) * kSmMaxGrid;
         const unsigned c = b / P, p = b % P;
-        if (c < count) {  // CTA-uniform
-            const unsigned row = order[cursor + c];
-            if (valid[row] && !__ldcg(is_member + row)) {
-                const double* fc = F + (size_t)row * dim;
-                const unsigned lo = (unsigned)(((uint64_t)dim * p) / P), hi = (unsigned)(((uint64_t)dim * (p + 1)) / P);
-                const FastSum h = block_entropy_ilp<false>(
-                    lo, hi, [&](unsigned i) { return __dadd_rn(sm.T[i], fc[i]); }, div_n, sm.ltab);
-                if (tid == 0) sm_store_part(spart + b, h);
-            }
+        const double* fl = F + (size_t)sm.members[mw][lowest] * dim;
+        if (c < count && sm.cvalid[coff + c]) {  // CTA-uniform (a member's score is published but never read)
+            const double* fc = F + (size_t)sm.crow[coff + c] * dim;
+            const unsigned lo = (unsigned)(((uint64_t)dim * p) / P), hi = (unsigned)(((uint64_t)dim * (p + 1)) / P);
+            auto num = [&](unsigned i) { return __dadd_rn(__dsub_rn(sm.S[i], fl[i]), fc[i]); };
+            const FastSum h = P == 4u   ? block_entropy_ilp<false, 2>(lo, hi, num, div_n, sm.ltab)
+                              : P == 2u ? block_entropy_ilp<false, 4>(lo, hi, num, div_n, sm.ltab)
+                                        : block_entropy_ilp<false, 8>(lo, hi, num, div_n, sm.ltab);
+            if (tid == 0) sm_publish(sbuf + b, h, xs);
         }
         stamp(1);
-        sm_grid_barrier(bar, target, G);
+        // a candidate that is already a member is skipped (records.rs:76-78): the replicated member list is
+        // the ground truth, searched while the other CTAs' partials are still in flight (thread j holds
+        // member j and walks the window)
+        __syncthreads();  // wskip initialised (a CTA without a candidate has not passed a barrier yet)
+        for (unsigned j = tid; j < n; j += kFastThreads) {
+            const unsigned r = sm.members[mw][j];
+            for (unsigned cc = 0; cc < count; ++cc)
+                if (sm.crow[coff + cc] == r) sm.wskip[cc] = 1;
+        }
+        __syncthreads();
+        // ---- gather + decision, redundantly in every CTA ----
+        if (tid < count * P && !sm.wskip[tid / P]) {
+            const FastSum g = sm_gather(sbuf + tid, xs);
+            sm.pe[tid] = g.e; sm.pt[tid] = g.t; sm.pa[tid] = g.a; sm.pbad[tid] = (unsigned char)g.bad;
+        }
+        __syncthreads();
         stamp(2);
-        // ---- decision, redundantly in every CTA ----
         if (tid < count && !sm.wskip[tid]) {
-            FastSum h = sm_load_part(spart + tid * P);
+            FastSum h{sm.pe[tid * P], sm.pt[tid * P], sm.pa[tid * P], sm.pbad[tid * P]};
             for (unsigned q = 1; q < P; ++q) {
-                const FastSum g = sm_load_part(spart + tid * P + q);
-                h.e += g.e; h.t += g.t; h.a += g.a; h.bad |= g.bad;
+                h.e += sm.pe[tid * P + q]; h.t += sm.pt[tid * P + q]; h.a += sm.pa[tid * P + q];
+                h.bad |= sm.pbad[tid * P + q];
             }
             const unsigned pos = cursor + tid;
-            const double mean_entropy = __ddiv_rn(__dadd_rn(__dsub_rn(E, sm.mH[mw][lowest]), sm.wH[tid]), nd);
+            const double mean_entropy = div_exact(__dadd_rn(__dsub_rn(E, sm.mH[mw][lowest]), sm.cH[coff + tid]), div_n);
             const double d = h.e - mean_entropy;
-            const double depth = P > 1u ? kSmDepth : 0.0;
-            const double bd = fast_bound(dim, h.a, mean_entropy, depth);
+            const double bd = (P > 1u ? kb4 : kb0) * (h.a + fabs(mean_entropy) + 1.0);
             const double thr = total_jsd + kEps, tb = total_bound + 4.0 * kEps;
-            if (h.bad || !fast_total_ok(dim, h.t, depth) || !(d == d)) {
+            if (h.bad || !total_ok(h.t, P > 1u ? lim4 : lim0) || !(d == d)) {
                 atomicMin(&sm.fu, pos);
             } else if (d - bd > thr + tb) {
                 atomicMin(&sm.ft, pos);
@@ -1089,6 +1179,7 @@ k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, uns
         __syncthreads();
         const unsigned ft = sm.ft, fu = sm.fu;
         __syncthreads();
+        stamp(3);
         if (fu < ft) {  // the first interesting candidate is undecided: the host resolves it exactly
             halt = 1;
             break;
@@ -1096,53 +1187,48 @@ k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, uns
         if (ft == kNone) {  // empty window
             cursor += count;
             window = min(window * 2u, G);
-            stamp(3);
+            stamp(4); stamp(5); stamp(6);
             ++tr_round;
             continue;
         }
         // ---- accept: replace_lowest + leave-one-out update ----
-        const unsigned cand = sm.wrow[ft - cursor];
-        const double Hc = sm.wH[ft - cursor];
-        const unsigned low_row = sm.members[mw][lowest];
+        const unsigned cand = sm.crow[ft - cbase];
+        const double Hc = sm.cH[ft - cbase];
         const double E_new = __dadd_rn(__dsub_rn(E, sm.mH[mw][lowest]), Hc);  // records.rs:101,129
         const double* fc = F + (size_t)cand * dim;
         auto member_after = [&](unsigned j) {  // Vec::remove(lowest) + push(cand)
             return j < lowest ? sm.members[mw][j] : (j + 1 < n ? sm.members[mw][j + 1] : cand);
         };
-        auto s_new = [&](uint64_t i) {
-            double s = sm.T[i];
+        auto s_new = [&](unsigned i) {
+            double s = __dsub_rn(sm.S[i], fl[i]);
             if (s <= kEps) s = 0.0;
             return __dadd_rn(s, fc[i]);
         };
+        ++xu;
         bool have_S = false;
         for (unsigned j = b; j <= n; j += G) {
             FastSum h;
             if (j == n) {
-                h = block_entropy_ilp<false>(0u, dim, [&](unsigned i) {
+                h = block_entropy_ilp<false, 8>(0u, dim, [&](unsigned i) {
                     const double s = have_S ? sm.S[i] : s_new(i);
                     if (!have_S) sm.S[i] = s;
                     return s;
                 }, div_n, sm.ltab);
             } else {
                 const double* f = F + (size_t)member_after(j) * dim;
-                h = block_entropy_ilp<true>(0u, dim, [&](unsigned i) {
+                h = block_entropy_ilp<true, 8>(0u, dim, [&](unsigned i) {
                     const double s = have_S ? sm.S[i] : s_new(i);
                     if (!have_S) sm.S[i] = s;
                     return __dsub_rn(s, f[i]);
                 }, div_n1, sm.ltab);
             }
-            if (tid == 0) sm_store_part(upart + j, h);
+            if (tid == 0) sm_publish(upart + j, h, xu);
             have_S = true;
         }
         if (!have_S)
             for (unsigned i = tid; i < dim; i += kFastThreads) sm.S[i] = s_new(i);
-        if (b == 0 && tid == 0) {
-            is_member[low_row] = 0;
-            is_member[cand] = 1;
-        }
-        stamp(3);
-        sm_grid_barrier(bar, target, G);
-        // ---- every CTA: new member list, deltas, certified argmin, T' ----
+        stamp(4);
+        // ---- every CTA: new member list, deltas, certified argmin ----
         for (unsigned t = tid; t < n; t += kFastThreads) {
             sm.members[mw ^ 1][t] = member_after(t);
             sm.mH[mw ^ 1][t] = t < lowest ? sm.mH[mw][t] : (t + 1 < n ? sm.mH[mw][t + 1] : Hc);
@@ -1152,47 +1238,56 @@ k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, uns
         mw ^= 1;
         E = E_new;
         {
-            const FastSum h = sm_load_part(upart + n);
-            const double me = __ddiv_rn(E, nd);
-            total_jsd = h.e - me;
-            total_bound = fast_bound(dim, h.a, me);
-            int uns = (h.bad || !fast_total_ok(dim, h.t)) ? 1 : 0;
-            for (unsigned t = tid; t < n; t += kFastThreads) {
-                const FastSum g = sm_load_part(upart + t);
-                const double mean_entropy = __ddiv_rn(__dsub_rn(E, sm.mH[mw][t]), div);
-                sm.md[t] = g.e - mean_entropy;
-                sm.mb[t] = fast_bound(dim, g.a, mean_entropy);
-                if (g.bad || !fast_total_ok(dim, g.t)) uns = 1;
+            int uns = 0;
+            for (unsigned t = tid; t <= n; t += kFastThreads) {
+                const FastSum g = sm_gather(upart + t, xu);
+                if (t == n) {
+                    sm.pe[0] = g.e; sm.pa[0] = g.a;  // (scan staging is free again)
+                } else {
+                    const double mean_entropy = div_exact(__dsub_rn(E, sm.mH[mw][t]), div_n1);
+                    sm.md[t] = g.e - mean_entropy;
+                    sm.mb[t] = kb0 * (g.a + fabs(mean_entropy) + 1.0);
+                }
+                if (g.bad || !total_ok(g.t, lim0)) uns = 1;
             }
             if (uns) sm.unsure = 1;  // benign race: every writer stores 1
         }
         __syncthreads();
+        stamp(5);
+        {
+            const double me = div_exact(E, div_n);
+            total_jsd = sm.pe[0] - me;
+            total_bound = kb0 * (sm.pa[0] + fabs(me) + 1.0);
+        }
         unsigned lo2 = 0;
-        unsigned unsure = finalize_fast_block<false>(sm.md, sm.mb, n, total_jsd, total_bound, &lo2);
+        unsigned unsure = sm_finalize(sm.md, sm.mb, n, total_jsd, total_bound, &lo2);
         unsure |= sm.unsure;
         lowest = lo2;
         touched = true;
         window = max(wmin, min(G, 2u * (ft - cursor + 1u)));
         cursor = ft + 1u;
         ++accepts;
+        stamp(6);
         ++tr_round;
         if (unsure) {  // the argmin / a sum check could not be certified: the host redoes the update exactly
             state_unsure = 1;
             halt = 1;
             break;
         }
-        const double* fl = F + (size_t)sm.members[mw][lowest] * dim;
-        for (unsigned i = tid; i < dim; i += kFastThreads) sm.T[i] = __dsub_rn(sm.S[i], fl[i]);
-        __syncthreads();
     }
+    stamp(0);
 
     // ---- CTA 0 hands the state back in the layout the other kernels and the host loop use ----
     if (b == 0) {
         __syncthreads();
         if (touched) {
             for (unsigned i = tid; i < dim; i += kFastThreads) S_glob[i] = sm.S[i];
+            for (unsigned j = tid; j < n; j += kFastThreads) is_member[M_glob[j]] = 0;  // the set at entry
+            __syncthreads();
             for (unsigned j = tid; j < n; j += kFastThreads) {
-                M_glob[j] = sm.members[mw][j];
+                const unsigned r = sm.members[mw][j];
+                M_glob[j] = r;
+                is_member[r] = 1;
                 mdelta_g[j] = sm.md[j];
                 mbound_g[j] = sm.mb[j];
             }
@@ -1466,11 +1561,9 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
     }
     const unsigned sm_grid = std::min<unsigned>((unsigned)ctx->sm_count, kSmMaxGrid);
     DevBuf<SmPart> d_spart, d_upart;
-    DevBuf<unsigned long long> d_bar;
     if (sm_ok) {
-        DVS_TRY(d_spart.alloc(kSmMaxGrid));
+        DVS_TRY(d_spart.alloc(2 * kSmMaxGrid));
         DVS_TRY(d_upart.alloc(kSmMaxN + 1));
-        DVS_TRY(d_bar.alloc(1));
     }
     while (cursor < num) {
         if (use_persist && (!grow_mode || n == max_size)) {
@@ -1504,10 +1597,11 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
                 double* a_S = cur->S();
                 unsigned* a_M = cur->members();
                 SmPart *a_sp = d_spart.p, *a_up = d_upart.p;
-                unsigned long long* a_bar = d_bar.p;
-                DVS_CUDA_TRY(cudaMemsetAsync(d_bar.p, 0, sizeof(unsigned long long), st));
+                // exchange tags restart at 1 in every launch
+                DVS_CUDA_TRY(cudaMemsetAsync(d_spart.p, 0, 2 * kSmMaxGrid * sizeof(SmPart), st));
+                DVS_CUDA_TRY(cudaMemsetAsync(d_upart.p, 0, (kSmMaxN + 1) * sizeof(SmPart), st));
                 void* args[] = {&a_F, &a_H, &a_dim32, &a_S, &a_M, &a_mem, &a_md, &a_mb, &a_sc, &a_valid, &a_order,
-                                &a_sp, &a_up, &a_bar, &a_trace};
+                                &a_sp, &a_up, &a_trace};
                 DVS_CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_sel_persist_sm, dim3(grid), dim3(kFastThreads), args,
                                                          sizeof(SmShared), st));
             } else {
@@ -1521,10 +1615,14 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
                 std::vector<unsigned long long> tr(2048);
                 DVS_CUDA_TRY(cudaMemcpy(tr.data(), a_trace, 2048 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
                 if (FILE* fp = fopen(tr_env, "a")) {
-                    fprintf(fp, "# round scan_ns wait1_ns update_ns wait2_ns (CTA 0; wait = grid barrier incl. the slowest CTA)\n");
-                    for (int r = 0; r + 1 < 512 && tr[4 * (r + 1)]; ++r)
-                        fprintf(fp, "%d %llu %llu %llu %llu\n", r, tr[4 * r + 1] - tr[4 * r], tr[4 * r + 2] - tr[4 * r + 1],
-                                tr[4 * r + 3] - tr[4 * r + 2], tr[4 * (r + 1)] - tr[4 * r + 3]);
+                    const int slots = use_sm ? kSmTraceSlots : 4, used = use_sm ? 7 : 4;
+                    fprintf(fp, use_sm ? "# round scan_ns gather_ns decide_ns update_ns gather2_ns finalize_ns next_ns (CTA 0)\n"
+                                       : "# round scan_ns wait1_ns update_ns wait2_ns (CTA 0; wait = grid barrier incl. the slowest CTA)\n");
+                    for (int r = 0; (r + 1) * slots < 2048 && tr[slots * (r + 1)]; ++r) {
+                        fprintf(fp, "%d", r);
+                        for (int q = 0; q + 1 < used; ++q) fprintf(fp, " %llu", tr[slots * r + q + 1] - tr[slots * r + q]);
+                        fprintf(fp, " %llu\n", tr[slots * (r + 1)] - tr[slots * r + used - 1]);
+                    }
                     fclose(fp);
                 }
             }

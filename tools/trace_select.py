@@ -57,10 +57,14 @@ def main() -> int:
         os.environ.pop("DVS_SELECT_TRACE", None)
         rows = np.loadtxt(out, comments="#", ndmin=2)
         if rows.size:
-            r = rows[1:, 1:5]
+            r = rows[1:, 1:]
             r = r[(r < 1e6).all(axis=1)]
-            print(f"  rounds traced {len(r)}: mean ns scan/wait1/update/wait2 = {np.round(r.mean(axis=0), 0).tolist()} "
-                  f"median = {np.median(r, axis=0).tolist()} sum/round = {r.sum(axis=1).mean():.0f}", flush=True)
+            print(f"  {out.read_text().splitlines()[0]}", flush=True)
+            print(f"  rounds traced {len(r)}: mean ns {np.round(r.mean(axis=0), 0).tolist()} "
+                  f"median {np.median(r, axis=0).tolist()} sum/round = {r.sum(axis=1).mean():.0f}", flush=True)
+            acc = r[r[:, 3] > 0] if r.shape[1] > 4 else r
+            print(f"  accepting rounds {len(acc)}: median {np.median(acc, axis=0).tolist()} sum = {acc.sum(axis=1).mean():.0f}",
+                  flush=True)
     return 0
 
 
