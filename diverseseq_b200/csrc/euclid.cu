@@ -8,7 +8,8 @@
 // register tile (64 FP64 accumulators); the frequency rows are staged through double-buffered
 // shared memory in 16-column slabs, stored [column][row] so that the inner loop reads its operands
 // with conflict-free 16-byte LDS (thread (ty,tx) owns rows {2ty,2ty+1}+32j and columns
-// {2tx,2tx+1}+32j).  The distance is accumulated in difference form sum((a-b)^2) — one DADD + one
+// {2tx,2tx+1}+32j); global loads are whole 128-byte lines (8 lanes x 16 bytes per row segment).  The
+// distance is accumulated in difference form sum((a-b)^2) — one DADD + one
 // DFMA per pair-element, FP64-pipe bound — which has no cancellation (the Gram form
 // ||a||^2+||b||^2-2ab loses all digits once d^2 << ||a||^2).  Only tiles on or
 // below the diagonal are computed when both row ranges are in the shard; results are mirrored.
@@ -35,12 +36,25 @@ k_euclid_tiles(const double* __restrict__ F, uint64_t dim, uint32_t n, uint32_t 
     const bool mirror_in_range = (row_begin % kEuT == 0) && (j0 >= row_begin) && (j0 < row_end);
     if (mirror_in_range && j0 > i0) return;
     const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
-    // loader mapping: thread -> (row lr of the tile, 8-column half lh of the slab)
-    const int lr = t & 127, lh = t >> 7;
-    const uint32_t ra = i0 + lr, rb = j0 + lr;
-    const bool va = ra < row_end, vb = rb < n;
-    const double* pa = F + (size_t)(va ? ra : 0) * dim;
-    const double* pb = F + (size_t)(vb ? rb : 0) * dim;
+    // loader mapping: a slab row segment is 16 doubles = one 128-byte line; chunk = 16 bytes (2 columns).
+    // Thread t moves chunks t, t+256, t+512, t+768 of each operand: 8 consecutive lanes read one whole
+    // line of one row (4 lines per warp-wide LDG.128).  (The first version gave each thread 8 consecutive
+    // doubles of its own row: 32 rows per warp instruction, 16x the L1 wavefronts, and the kernel sat
+    // on long-scoreboard stalls at 60 % FP64-pipe utilisation.)
+    const bool vec_ok = (dim % 2 == 0);  // 16-byte alignment of every row
+    const int lc2 = t & 7;               // chunk within the row segment -> columns 2*lc2, 2*lc2+1
+    const double* parow[4];
+    const double* pbrow[4];
+    bool varow[4], vbrow[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int lr = (t >> 3) + 32 * q;
+        const uint32_t ra = i0 + lr, rb = j0 + lr;
+        varow[q] = ra < row_end;
+        vbrow[q] = rb < n;
+        parow[q] = F + (size_t)(varow[q] ? ra : 0) * dim;
+        pbrow[q] = F + (size_t)(vbrow[q] ? rb : 0) * dim;
+    }
 
     double acc[8][8];
 #pragma unroll
@@ -48,21 +62,30 @@ k_euclid_tiles(const double* __restrict__ F, uint64_t dim, uint32_t n, uint32_t 
 #pragma unroll
         for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
 
-    double ga[8], gb[8];
+    double2 ga[4], gb[4];
     auto gload = [&](uint64_t c0) {
+        const uint64_t col = c0 + 2 * lc2;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const uint64_t col = c0 + lh * 8 + q;
-            const bool vc = col < dim;
-            ga[q] = (va && vc) ? pa[col] : 0.0;
-            gb[q] = (vb && vc) ? pb[col] : 0.0;
+        for (int q = 0; q < 4; ++q) {
+            if (vec_ok && col + 1 < dim) {
+                ga[q] = varow[q] ? *reinterpret_cast<const double2*>(parow[q] + col) : make_double2(0.0, 0.0);
+                gb[q] = vbrow[q] ? *reinterpret_cast<const double2*>(pbrow[q] + col) : make_double2(0.0, 0.0);
+            } else {
+                ga[q].x = (varow[q] && col < dim) ? parow[q][col] : 0.0;
+                ga[q].y = (varow[q] && col + 1 < dim) ? parow[q][col + 1] : 0.0;
+                gb[q].x = (vbrow[q] && col < dim) ? pbrow[q][col] : 0.0;
+                gb[q].y = (vbrow[q] && col + 1 < dim) ? pbrow[q][col + 1] : 0.0;
+            }
         }
     };
     auto sstore = [&](int buf) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            sa[buf][lh * 8 + q][lr] = ga[q];
-            sb[buf][lh * 8 + q][lr] = gb[q];
+        for (int q = 0; q < 4; ++q) {
+            const int lr = (t >> 3) + 32 * q;
+            sa[buf][2 * lc2][lr] = ga[q].x;
+            sa[buf][2 * lc2 + 1][lr] = ga[q].y;
+            sb[buf][2 * lc2][lr] = gb[q].x;
+            sb[buf][2 * lc2 + 1][lr] = gb[q].y;
         }
     };
     const uint64_t nslab = (dim + kEuK - 1) / kEuK;
