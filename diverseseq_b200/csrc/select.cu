@@ -944,19 +944,23 @@ k_sel_persist(const double* __restrict__ F, const double* __restrict__ H, uint64
 //   staged);   registers: E, total_jsd, lowest, cursor, window.  (The global is_member map is only
 //   brought up to date when the kernel ends.)
 // Per round only 32-byte partial sums cross the L2, and they carry their own arrival flag, so there is no
-// grid barrier at all:
+// separate grid barrier:
 //   scan    CTA b scores slice p = b % P of candidate c = b / P of the window (P = 4, 2 or 1 CTAs per
 //           candidate, so a short window still uses every SM) and publishes {e, t, a, bad | tag} as two
-//           self-validating 128-bit stores (tag = number of the exchange);
-//   gather  every CTA polls the window's slots until their tags match (one L2 round trip after the last
-//           writer), combines the partials in the same order and takes the SAME decision (first certain
-//           acceptance / first undecided candidate) — no atomics, no scalar block;
+//           self-validating 128-bit stores (tag = number of the exchange); CTAs without a candidate
+//           publish an empty slot;
+//   decide  the leader (CTA 0) polls all G slots until their tags match (one one-way latency after the
+//           last writer), combines the partials in order, finds the first certain acceptance / first
+//           undecided candidate and broadcasts them in one tagged 128-bit store that every other CTA polls;
 //   accept  CTA j computes the leave-one-out entropy of member j (CTA n: H(S'/n)) and publishes its partial,
-//           every CTA forms S' = clamp(S - f_lowest) + f_cand in its own shared memory;
-//   gather  every CTA forms the member deltas and the certified argmin.
-// Slot reuse is safe without resets: a CTA can only publish exchange x+2 of a kind after it has gathered
-// x+1, which needs every CTA to have published x+1, i.e. to have finished gathering x; scan exchanges can
-// follow each other directly (empty window), so their slots are double buffered.
+//           every CTA forms S' = clamp(S - f_lowest) + f_cand and the new member list in shared memory;
+//   final   the leader gathers the n + 1 partials, forms the member deltas and the certified argmin and
+//           broadcasts {total_jsd, total_bound, lowest, unsure}.
+// (Letting every CTA poll every slot and decide redundantly was measured at 2.2 us per exchange against
+// 1.3 us for the leader form — 148 x 148 pollers — tools/microbench/gridsync_bench.cu.)
+// Slot reuse is safe without resets: the leader only broadcasts scan decision x after EVERY CTA has
+// published its slot of exchange x, i.e. after every CTA has consumed all earlier broadcasts, and two
+// update exchanges are always separated by a scan exchange; scan slots are double buffered.
 // Arithmetic, bounds and the halt protocol are those of the kernels above (the partial sums only add
 // P - 1 sequential additions, covered by `depth`; `a` travels as a float rounded UP, which only widens a
 // bound), so decisions are identical; CTA 0 writes the state back to global memory when the rounds end or
@@ -1057,16 +1061,20 @@ __global__ void __launch_bounds__(kFastThreads, 1)
 k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, unsigned dim, double* S_glob,
                  unsigned* M_glob, uint8_t* is_member, double* mdelta_g, double* mbound_g, SelScal* sc,
                  const uint8_t* __restrict__ valid, const unsigned* __restrict__ order, SmPart* spart, SmPart* upart,
-                 unsigned long long* trace) {
+                 SmPart* dpart, unsigned long long* trace, int trace_all) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     SmShared& sm = *reinterpret_cast<SmShared*>(sm_raw);
     const unsigned tid = threadIdx.x, b = blockIdx.x, G = gridDim.x;
     unsigned tr_round = 0;
-    auto stamp = [&](int slot) {  // DVS_SELECT_TRACE: CTA 0's timeline of the first 256 rounds
-        if (trace && b == 0 && tid == 0 && tr_round < 256) {
+    // DVS_SELECT_TRACE: CTA 0's timeline of the first 256 rounds; DVS_SELECT_TRACE_ALL: every CTA's
+    auto stamp = [&](int slot) {
+        if (trace && tid == 0 && tr_round < 256 && (b == 0 || trace_all)) {
             unsigned long long t;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-            trace[tr_round * kSmTraceSlots + slot] = t;
+            if (trace_all)
+                trace[((size_t)tr_round * kSmTraceSlots + slot) * kSmMaxGrid + b] = t;
+            else
+                trace[tr_round * kSmTraceSlots + slot] = t;
         }
     };
 
@@ -1138,45 +1146,67 @@ k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, uns
                               : P == 2u ? block_entropy_ilp<false, 4>(lo, hi, num, div_n, sm.ltab)
                                         : block_entropy_ilp<false, 8>(lo, hi, num, div_n, sm.ltab);
             if (tid == 0) sm_publish(sbuf + b, h, xs);
+        } else if (tid == 0) {
+            // every CTA publishes in every scan exchange: the leader's wait for all G slots is what bounds
+            // how far any CTA can lag, i.e. what makes the reuse of all exchange slots safe
+            sm_publish(sbuf + b, FastSum{0.0, 0.0, 0.0, 0}, xs);
         }
         stamp(1);
-        // a candidate that is already a member is skipped (records.rs:76-78): the replicated member list is
-        // the ground truth, searched while the other CTAs' partials are still in flight (thread j holds
-        // member j and walks the window)
-        __syncthreads();  // wskip initialised (a CTA without a candidate has not passed a barrier yet)
-        for (unsigned j = tid; j < n; j += kFastThreads) {
-            const unsigned r = sm.members[mw][j];
-            for (unsigned cc = 0; cc < count; ++cc)
-                if (sm.crow[coff + cc] == r) sm.wskip[cc] = 1;
-        }
-        __syncthreads();
-        // ---- gather + decision, redundantly in every CTA ----
-        if (tid < count * P && !sm.wskip[tid / P]) {
-            const FastSum g = sm_gather(sbuf + tid, xs);
-            sm.pe[tid] = g.e; sm.pt[tid] = g.t; sm.pa[tid] = g.a; sm.pbad[tid] = (unsigned char)g.bad;
-        }
-        __syncthreads();
-        stamp(2);
-        if (tid < count && !sm.wskip[tid]) {
-            FastSum h{sm.pe[tid * P], sm.pt[tid * P], sm.pa[tid * P], sm.pbad[tid * P]};
-            for (unsigned q = 1; q < P; ++q) {
-                h.e += sm.pe[tid * P + q]; h.t += sm.pt[tid * P + q]; h.a += sm.pa[tid * P + q];
-                h.bad |= sm.pbad[tid * P + q];
+        // ---- gather + decision by the leader (CTA 0), broadcast of {first_true, first_unsure} ----
+        // (an all-to-all gather — every CTA polling every slot — costs 2.2 us per exchange on 148 SMs, the
+        // leader form 1.3 us: tools/microbench/gridsync_bench.cu)
+        SmPart* const dslot = dpart + (xs & 1u);
+        if (b == 0) {
+            // a candidate that is already a member is skipped (records.rs:76-78): the replicated member list
+            // is the ground truth, searched while the partials are still in flight (thread j holds member j
+            // and walks the window)
+            __syncthreads();  // wskip initialised (a CTA without a candidate has not passed a barrier yet)
+            for (unsigned j = tid; j < n; j += kFastThreads) {
+                const unsigned r = sm.members[mw][j];
+                for (unsigned cc = 0; cc < count; ++cc)
+                    if (sm.crow[coff + cc] == r) sm.wskip[cc] = 1;
             }
-            const unsigned pos = cursor + tid;
-            const double mean_entropy = div_exact(__dadd_rn(__dsub_rn(E, sm.mH[mw][lowest]), sm.cH[coff + tid]), div_n);
-            const double d = h.e - mean_entropy;
-            const double bd = (P > 1u ? kb4 : kb0) * (h.a + fabs(mean_entropy) + 1.0);
-            const double thr = total_jsd + kEps, tb = total_bound + 4.0 * kEps;
-            if (h.bad || !total_ok(h.t, P > 1u ? lim4 : lim0) || !(d == d)) {
-                atomicMin(&sm.fu, pos);
-            } else if (d - bd > thr + tb) {
-                atomicMin(&sm.ft, pos);
-            } else if (!(d + bd < thr - tb)) {
-                atomicMin(&sm.fu, pos);
+            __syncthreads();
+            if (tid < G) {
+                const FastSum g = sm_gather(sbuf + tid, xs);
+                if (tid < count * P && !sm.wskip[tid / P]) {
+                    sm.pe[tid] = g.e; sm.pt[tid] = g.t; sm.pa[tid] = g.a; sm.pbad[tid] = (unsigned char)g.bad;
+                }
             }
+            __syncthreads();
+            stamp(2);
+            if (tid < count && !sm.wskip[tid]) {
+                FastSum h{sm.pe[tid * P], sm.pt[tid * P], sm.pa[tid * P], sm.pbad[tid * P]};
+                for (unsigned q = 1; q < P; ++q) {
+                    h.e += sm.pe[tid * P + q]; h.t += sm.pt[tid * P + q]; h.a += sm.pa[tid * P + q];
+                    h.bad |= sm.pbad[tid * P + q];
+                }
+                const unsigned pos = cursor + tid;
+                const double mean_entropy =
+                    div_exact(__dadd_rn(__dsub_rn(E, sm.mH[mw][lowest]), sm.cH[coff + tid]), div_n);
+                const double d = h.e - mean_entropy;
+                const double bd = (P > 1u ? kb4 : kb0) * (h.a + fabs(mean_entropy) + 1.0);
+                const double thr = total_jsd + kEps, tb = total_bound + 4.0 * kEps;
+                if (h.bad || !total_ok(h.t, P > 1u ? lim4 : lim0) || !(d == d)) {
+                    atomicMin(&sm.fu, pos);
+                } else if (d - bd > thr + tb) {
+                    atomicMin(&sm.ft, pos);
+                } else if (!(d + bd < thr - tb)) {
+                    atomicMin(&sm.fu, pos);
+                }
+            }
+            __syncthreads();
+            if (tid == 0) sm_st128(&dslot->w[0], ((unsigned long long)sm.fu << 32) | sm.ft, xs);
+        } else {
+            if (tid == 0) {
+                unsigned long long w0, w1;
+                do sm_ld128(&dslot->w[0], w0, w1); while ((unsigned)w1 != xs);
+                sm.ft = (unsigned)w0;
+                sm.fu = (unsigned)(w0 >> 32);
+            }
+            stamp(2);
+            __syncthreads();
         }
-        __syncthreads();
         const unsigned ft = sm.ft, fu = sm.fu;
         __syncthreads();
         stamp(3);
@@ -1228,7 +1258,7 @@ k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, uns
         if (!have_S)
             for (unsigned i = tid; i < dim; i += kFastThreads) sm.S[i] = s_new(i);
         stamp(4);
-        // ---- every CTA: new member list, deltas, certified argmin ----
+        // ---- every CTA: new member list; the leader: deltas + certified argmin, broadcast ----
         for (unsigned t = tid; t < n; t += kFastThreads) {
             sm.members[mw ^ 1][t] = member_after(t);
             sm.mH[mw ^ 1][t] = t < lowest ? sm.mH[mw][t] : (t + 1 < n ? sm.mH[mw][t + 1] : Hc);
@@ -1237,7 +1267,9 @@ k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, uns
         __syncthreads();
         mw ^= 1;
         E = E_new;
-        {
+        unsigned lo2 = 0, unsure = 0;
+        SmPart* const fslot = dpart + 2;
+        if (b == 0) {
             int uns = 0;
             for (unsigned t = tid; t <= n; t += kFastThreads) {
                 const FastSum g = sm_gather(upart + t, xu);
@@ -1251,17 +1283,36 @@ k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, uns
                 if (g.bad || !total_ok(g.t, lim0)) uns = 1;
             }
             if (uns) sm.unsure = 1;  // benign race: every writer stores 1
-        }
-        __syncthreads();
-        stamp(5);
-        {
+            __syncthreads();
+            stamp(5);
             const double me = div_exact(E, div_n);
             total_jsd = sm.pe[0] - me;
             total_bound = kb0 * (sm.pa[0] + fabs(me) + 1.0);
+            unsure = sm_finalize(sm.md, sm.mb, n, total_jsd, total_bound, &lo2);
+            unsure |= sm.unsure;
+            if (tid == 0) {
+                sm_st128(&fslot->w[0], (unsigned long long)__double_as_longlong(total_jsd), ((unsigned long long)lo2 << 32) | xu);
+                sm_st128(&fslot->w[2], (unsigned long long)__double_as_longlong(total_bound),
+                         ((unsigned long long)unsure << 32) | xu);
+            }
+        } else {
+            if (tid == 0) {
+                unsigned long long w0, w1, w2, w3;
+                do sm_ld128(&fslot->w[0], w0, w1); while ((unsigned)w1 != xu);
+                do sm_ld128(&fslot->w[2], w2, w3); while ((unsigned)w3 != xu);
+                sm.pe[0] = __longlong_as_double((long long)w0);
+                sm.pa[0] = __longlong_as_double((long long)w2);
+                sm.ft = (unsigned)(w1 >> 32);
+                sm.unsure = (unsigned)(w3 >> 32);
+            }
+            __syncthreads();
+            stamp(5);
+            total_jsd = sm.pe[0];
+            total_bound = sm.pa[0];
+            lo2 = sm.ft;
+            unsure = sm.unsure;
+            __syncthreads();
         }
-        unsigned lo2 = 0;
-        unsigned unsure = sm_finalize(sm.md, sm.mb, n, total_jsd, total_bound, &lo2);
-        unsure |= sm.unsure;
         lowest = lo2;
         touched = true;
         window = max(wmin, min(G, 2u * (ft - cursor + 1u)));
@@ -1560,10 +1611,11 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
         (void)cudaGetLastError();
     }
     const unsigned sm_grid = std::min<unsigned>((unsigned)ctx->sm_count, kSmMaxGrid);
-    DevBuf<SmPart> d_spart, d_upart;
+    DevBuf<SmPart> d_spart, d_upart, d_dpart;
     if (sm_ok) {
         DVS_TRY(d_spart.alloc(2 * kSmMaxGrid));
         DVS_TRY(d_upart.alloc(kSmMaxN + 1));
+        DVS_TRY(d_dpart.alloc(3));  // the leader's broadcasts: scan decision (double buffered), update result
     }
     while (cursor < num) {
         if (use_persist && (!grow_mode || n == max_size)) {
@@ -1587,21 +1639,26 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
             unsigned long long* a_trace = nullptr;
             DevBuf<unsigned long long> d_trace;
             const char* tr_env = getenv("DVS_SELECT_TRACE");
-            if (tr_env && tr_env[0]) {
-                DVS_TRY(d_trace.alloc(2048));
-                DVS_CUDA_TRY(cudaMemsetAsync(d_trace.p, 0, 2048 * sizeof(unsigned long long), st));
+            const char* tra_env = getenv("DVS_SELECT_TRACE_ALL");  // raw u64 [256 rounds][8 slots][256 CTAs]
+            int a_trace_all = (use_sm && tra_env && tra_env[0]) ? 1 : 0;
+            const size_t trace_len = a_trace_all ? (size_t)256 * kSmTraceSlots * kSmMaxGrid : 2048;
+            if (a_trace_all) tr_env = nullptr;
+            if ((tr_env && tr_env[0]) || a_trace_all) {
+                DVS_TRY(d_trace.alloc(trace_len));
+                DVS_CUDA_TRY(cudaMemsetAsync(d_trace.p, 0, trace_len * sizeof(unsigned long long), st));
                 a_trace = d_trace.p;
             }
             if (use_sm) {
                 unsigned a_dim32 = (unsigned)dim;
                 double* a_S = cur->S();
                 unsigned* a_M = cur->members();
-                SmPart *a_sp = d_spart.p, *a_up = d_upart.p;
+                SmPart *a_sp = d_spart.p, *a_up = d_upart.p, *a_dp = d_dpart.p;
+                DVS_CUDA_TRY(cudaMemsetAsync(d_dpart.p, 0, 3 * sizeof(SmPart), st));
                 // exchange tags restart at 1 in every launch
                 DVS_CUDA_TRY(cudaMemsetAsync(d_spart.p, 0, 2 * kSmMaxGrid * sizeof(SmPart), st));
                 DVS_CUDA_TRY(cudaMemsetAsync(d_upart.p, 0, (kSmMaxN + 1) * sizeof(SmPart), st));
                 void* args[] = {&a_F, &a_H, &a_dim32, &a_S, &a_M, &a_mem, &a_md, &a_mb, &a_sc, &a_valid, &a_order,
-                                &a_sp, &a_up, &a_trace};
+                                &a_sp, &a_up, &a_dp, &a_trace, &a_trace_all};
                 DVS_CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_sel_persist_sm, dim3(grid), dim3(kFastThreads), args,
                                                          sizeof(SmShared), st));
             } else {
@@ -1611,7 +1668,14 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
             }
             ctx->launches++;
             DVS_TRY(sel.read(*cur));
-            if (a_trace) {  // phase timeline of CTA 0 to the file named by DVS_SELECT_TRACE
+            if (a_trace && a_trace_all) {
+                std::vector<unsigned long long> tr(trace_len);
+                DVS_CUDA_TRY(cudaMemcpy(tr.data(), a_trace, trace_len * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+                if (FILE* fp = fopen(tra_env, "wb")) {
+                    fwrite(tr.data(), sizeof(unsigned long long), trace_len, fp);
+                    fclose(fp);
+                }
+            } else if (a_trace) {  // phase timeline of CTA 0 to the file named by DVS_SELECT_TRACE
                 std::vector<unsigned long long> tr(2048);
                 DVS_CUDA_TRY(cudaMemcpy(tr.data(), a_trace, 2048 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
                 if (FILE* fp = fopen(tr_env, "a")) {
