@@ -532,8 +532,8 @@ k_freq_entropy(const uint32_t* __restrict__ counts, uint64_t dim, double* __rest
     __syncthreads();
     const unsigned long long total_u = s_total;
     const double total = (double)total_u;  // `sum::<usize>() as f64`
-    for (uint64_t i = threadIdx.x; i < dim; i += blockDim.x) f[i] = __ddiv_rn((double)c[i], total);  // NaN row if 0
     if (total_u == 0ULL) {
+        for (uint64_t i = threadIdx.x; i < dim; i += blockDim.x) f[i] = __ddiv_rn((double)c[i], total);  // NaN row
         if (threadIdx.x == 0) {
             totals[r] = 0;
             entropy[r] = 0.0;
@@ -543,7 +543,13 @@ k_freq_entropy(const uint32_t* __restrict__ counts, uint64_t dim, double* __rest
         }
         return;
     }
-    EntropyResult h = block_entropy_exact(dim, [&](uint64_t i) { return __ddiv_rn((double)c[i], total); }, ent_smem);
+    // count / total by div_exact (= IEEE division, entropy.cuh); the row is stored by the same pass
+    const FastDiv dv = make_fast_div(total);
+    EntropyResult h = block_entropy_exact(dim, [&](uint64_t i) {
+        const double x = div_exact((double)c[i], dv);
+        f[i] = x;
+        return x;
+    }, ent_smem);
     if (threadIdx.x == 0) {
         totals[r] = total_u;
         entropy[r] = h.e;

@@ -40,11 +40,35 @@ __device__ __forceinline__ bool entropy_total_bad(double t, uint64_t len) {
 // All kEntThreads threads of the block must call this.  `elem(i)` returns element i of the
 // frequency vector (any thread may be asked for any i).  `smem` must hold kEntSmemBytes.
 // The result is returned to every thread.
+// x / b through a correctly rounded reciprocal and two fused-remainder steps (Markstein): the second
+// step starts from a faithful quotient and therefore rounds correctly, i.e. the result equals IEEE
+// division (__ddiv_rn) bit for bit — checked on the host for 8.2e7 random numerators x every integer
+// divisor <= 4100 and for 1.5e8 count/total pairs incl. all-ones significands, and on the device in
+// tests/test_gpu_parity.py — without __ddiv_rn's ~20 instructions and slow-path branch.  Requires a
+// normal quotient well above the subnormal range (callers: k-mer frequencies, or guarded by fast_term_ok).
+struct FastDiv {
+    double b, y;  // divisor and RN(1/b)
+};
+__device__ __forceinline__ FastDiv make_fast_div(double b) { return FastDiv{b, __drcp_rn(b)}; }
+__device__ __forceinline__ double div_exact(double a, const FastDiv& d) {
+    double q = __dmul_rn(a, d.y);
+    double r = __fma_rn(-q, d.b, a);
+    q = __fma_rn(r, d.y, q);
+    r = __fma_rn(-q, d.b, a);
+    return __fma_rn(r, d.y, q);
+}
+
 template <class Elem>
 __device__ EntropyResult block_entropy_exact(uint64_t dim, Elem elem, double* smem) {
     double* term[2] = {smem, smem + 2 * kEntTile};
     double* val[2] = {smem + kEntTile, smem + 3 * kEntTile};
     __shared__ double s_res[2];
+    // log2 goes through the branch-free table path of the restatement (table in shared memory, one
+    // lookup per lane) and only falls back to the full dvs_log2 for the inputs that path does not cover
+    // (|x - 1| small, subnormal, <= 0, inf, nan): same bits, about a third of the instructions
+    __shared__ double2 s_ltab[64];
+    dvs_log2_stage_table(s_ltab);
+    __syncthreads();
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const uint64_t ntiles = (dim + kEntTile - 1) / kEntTile;
@@ -58,7 +82,10 @@ __device__ EntropyResult block_entropy_exact(uint64_t dim, Elem elem, double* sm
             double x = elem(base + j);
             double tm = 0.0, v = 0.0;
             if (!(x == 0.0)) {  // NaN is not skipped, like `*freq == 0.0` in Rust
-                tm = __dmul_rn(-x, dvs_log2(x));
+                int special = 0;
+                double l = dvs_log2_main(x, s_ltab, special);
+                if (special) l = dvs_log2(x);
+                tm = __dmul_rn(-x, l);
                 v = x;
             }
             tb[j] = tm;

@@ -377,25 +377,11 @@ __device__ __forceinline__ FastSum block_entropy_fast(uint64_t dim, Elem elem) {
 // instructions behind their own branches, and with 4 warps per scheduler at ~14 cycles per dependent
 // FP64 instruction the FP64 pipe idles most of the time (measured 0.47 us per element per thread).
 // Here every step is branch-free straight-line code over 8 elements per thread, so 8 chains interleave:
-//   * x / b by Markstein's sequence on a correctly rounded reciprocal — two refinement steps, the second
-//     from a faithful quotient, which rounds correctly (= __ddiv_rn bit for bit; checked on 8.2e7 random
-//     operands x all b <= 4100 on the host and in tests/test_gpu_parity.py on the device);
+//   * x / b by div_exact (entropy.cuh): reciprocal + two fused-remainder steps, = __ddiv_rn bit for bit;
 //   * log2 by the table-driven path of the glibc restatement (dvs_log2_main): the reference's own bits,
 //     so a term -m*log2(m) is now IDENTICAL to the reference's, not merely within 3 ulp.
 // Inputs that the glibc algorithm sends down its other paths (m within ~4 % of 1, subnormals) or that
 // make the reference's value NaN raise `bad`, which the callers already treat as "undecided".
-struct FastDiv {
-    double b, y;  // divisor and RN(1/b)
-};
-__device__ __forceinline__ FastDiv make_fast_div(double b) { return FastDiv{b, __drcp_rn(b)}; }
-__device__ __forceinline__ double div_exact(double a, const FastDiv& d) {
-    double q = __dmul_rn(a, d.y);
-    double r = __fma_rn(-q, d.b, a);
-    q = __fma_rn(r, d.y, q);
-    r = __fma_rn(-q, d.b, a);
-    return __fma_rn(r, d.y, q);
-}
-
 // m is usable by the table path (and was divided exactly) iff 2^-900 <= m < 0x1.ea4afp-1: one unsigned
 // compare on its high word; negative, NaN, inf, zero, subnormal and "near 1 or above" all fall outside.
 // (Below 2^-900 the fused remainders of div_exact could underflow; k-mer frequencies are >= ~1e-10.)
