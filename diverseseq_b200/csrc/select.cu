@@ -921,6 +921,113 @@ k_sel_persist(const double* __restrict__ F, const double* __restrict__ H, uint64
     }
 }
 
+// ------------------------------------------------------------------ batched grow attempts (max) ----
+// While a `max` selection is below max_size every candidate that increases the JSD costs the reference a
+// `clone()` + `push` and a comparison of std / cov (records.rs:434-451), and the candidate is DISCARDED
+// when the statistic does not improve — the state is unchanged.  On the benchmark set almost every
+// candidate is of that kind (stdev 5..10 over 10.5k genomes: 4 adoptions), and one host-driven attempt
+// costs ~210 us.  As with the windowed scan, a window of candidates is therefore evaluated concurrently
+// against the same state: for each candidate the scan predicate and, for the grown set, H(S'/(n+1)) and the
+// n+1 leave-one-out entropies (one CTA each, same operations as k_sel_sum + k_sel_update_fast), then the
+// bounded statistic.  A candidate is skipped only if it CERTAINLY does not increase the JSD or CERTAINLY
+// does not improve the statistic; the first candidate that is anything else is handed to the existing
+// host path (which adopts it, or decides it exactly).  Decisions are unchanged, only certain discards
+// are taken in bulk.
+__global__ void __launch_bounds__(kFastThreads)
+k_grow_eval(const double* __restrict__ F, uint64_t dim, const double* __restrict__ S_cur,
+            const unsigned* __restrict__ members, const SelScal* __restrict__ sc_cur,
+            const double* __restrict__ S_fresh, const uint8_t* __restrict__ valid,
+            const uint8_t* __restrict__ is_member, const unsigned* __restrict__ order, unsigned cursor,
+            FastSum* __restrict__ parts) {
+    const unsigned c = blockIdx.y, t = blockIdx.x, n = sc_cur->n;
+    const unsigned row = order[cursor + c];
+    if (!valid[row] || is_member[row]) return;
+    const double* fc = F + (size_t)row * dim;
+    const double nd = (double)n;
+    FastSum h;
+    if (t == 0) {  // increases_jsd against the current state (records.rs:70-92)
+        const double* fl = F + (size_t)members[sc_cur->lowest] * dim;
+        h = block_entropy_fast(dim, [&](uint64_t i) { return __ddiv_rn(__dadd_rn(__dsub_rn(S_cur[i], fl[i]), fc[i]), nd); });
+    } else if (t == 1) {  // total of the grown set: clone() re-sums in member order, push adds the candidate
+        const double nd1 = __dadd_rn(nd, 1.0);
+        h = block_entropy_fast(dim, [&](uint64_t i) { return __ddiv_rn(__dadd_rn(S_fresh[i], fc[i]), nd1); });
+    } else {  // leave-one-out of member j of the grown set (j == n: the candidate itself)
+        const unsigned j = t - 2;
+        const double* f = j < n ? F + (size_t)members[j] * dim : fc;
+        h = block_entropy_fast(dim, [&](uint64_t i) {
+            const double m = __ddiv_rn(__dsub_rn(__dadd_rn(S_fresh[i], fc[i]), f[i]), nd);
+            return (m <= kEps) ? 0.0 : m;
+        });
+    }
+    if (threadIdx.x == 0) parts[(size_t)c * (n + 3) + t] = h;
+}
+
+__global__ void __launch_bounds__(kFastThreads)
+k_grow_decide(const double* __restrict__ H, uint64_t dim, const unsigned* __restrict__ members,
+              const SelScal* __restrict__ sc_cur, const SelScal* __restrict__ sc_fresh,
+              const uint8_t* __restrict__ valid, const uint8_t* __restrict__ is_member,
+              const unsigned* __restrict__ order, unsigned cursor, const FastSum* __restrict__ parts,
+              double* __restrict__ md, double* __restrict__ mb, unsigned cap, SelScal* __restrict__ scratch,
+              unsigned* __restrict__ first_interesting, int use_cov) {
+    __shared__ int s_dec;
+    const unsigned c = blockIdx.x, pos = cursor + c, n = sc_cur->n;
+    const unsigned row = order[pos];
+    if (!valid[row] || is_member[row]) return;  // skipped silently, like the scan
+    const FastSum* P = parts + (size_t)c * (n + 3);
+    const double nd = (double)n;
+    if (threadIdx.x == 0) {
+        const FastSum h = P[0];
+        const unsigned low_row = members[sc_cur->lowest];
+        const double me = __ddiv_rn(__dadd_rn(__dsub_rn(sc_cur->E, H[low_row]), H[row]), nd);
+        const double d = h.e - me, b = fast_bound(dim, h.a, me);
+        const double thr = sc_cur->total_jsd + kEps, tb = sc_cur->total_bound + 4.0 * kEps;
+        int dec = 2;  // 0: certainly not increasing, 1: certainly increasing, 2: undecided
+        if (!sc_cur->state_unsure && !h.bad && fast_total_ok(dim, h.t) && d == d) {
+            if (d - b > thr + tb) dec = 1;
+            else if (d + b < thr - tb) dec = 0;
+        }
+        s_dec = dec;
+    }
+    __syncthreads();
+    const int dec = s_dec;
+    if (dec == 0) return;
+    if (dec == 2) {
+        if (threadIdx.x == 0) atomicMin(first_interesting, pos);
+        return;
+    }
+    // the grown set's total, member deltas and statistic (same forms as k_sel_update_fast)
+    const double nd1 = __dadd_rn(nd, 1.0);
+    const double E_try = __dadd_rn(sc_fresh->E, H[row]);
+    const FastSum tot = P[1];
+    const double me_t = __ddiv_rn(E_try, nd1);
+    const double total_try = tot.e - me_t, tbound = fast_bound(dim, tot.a, me_t);
+    int unsure = (tot.bad || !fast_total_ok(dim, tot.t)) ? 1 : 0;
+    double* mdc = md + (size_t)c * cap;
+    double* mbc = mb + (size_t)c * cap;
+    for (unsigned j = threadIdx.x; j <= n; j += blockDim.x) {
+        const FastSum hj = P[2 + j];
+        const double Hj = j < n ? H[members[j]] : H[row];
+        const double me = __ddiv_rn(__dsub_rn(E_try, Hj), nd);
+        mdc[j] = total_try - (hj.e - me);
+        mbc[j] = fast_bound(dim, hj.a, me);
+        if (hj.bad || !fast_total_ok(dim, hj.t)) unsure = 1;
+    }
+    unsure = __syncthreads_or(unsure);
+    if (unsure) {
+        if (threadIdx.x == 0) atomicMin(first_interesting, pos);
+        return;
+    }
+    stats_fast_block(mdc, mbc, n + 1, tbound, scratch + c);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const SelScal* g = scratch + c;
+        const double sa = use_cov ? sc_cur->cov : sc_cur->stdv;
+        const double ba = sc_cur->exact ? 0.0 : (use_cov ? sc_cur->cov_bound : sc_cur->std_bound);
+        const double sb = use_cov ? g->cov : g->stdv, bb = use_cov ? g->cov_bound : g->std_bound;
+        if (!(sb + bb < sa - ba)) atomicMin(first_interesting, pos);  // not a certain discard (NaN included)
+    }
+}
+
 // ---------------------------------------------------------------- SM-replicated selection rounds ----
 // k_sel_persist still pays ~10 dependent L2 round trips per round (scalar block, member list, ticket,
 // last-CTA tail) and two cooperative-groups barriers.  For vectors that fit in shared memory (dim <= 4096,
@@ -1603,7 +1710,78 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
         DVS_TRY(d_upart.alloc(kSmMaxN + 1));
         DVS_TRY(d_dpart.alloc(3));  // the leader's broadcasts: scan decision (double buffered), update result
     }
+    // batched grow attempts (see k_grow_eval): scratch for a window of candidates; DVS_SELECT_GROW_BATCH=0
+    // keeps one host-driven attempt per candidate
+    const char* gb_env = getenv("DVS_SELECT_GROW_BATCH");
+    const bool use_grow_batch = use_fast && grow_mode && !(gb_env && gb_env[0] == '0');
+    constexpr unsigned kGrowWindowMax = 64;
+    SelState fresh;  // clone(): the members re-summed in order (S, E), refreshed whenever the set changes
+    DevBuf<FastSum> d_gparts;
+    DevBuf<double> d_gmd, d_gmb;
+    DevBuf<SelScal> d_gscratch;
+    DevBuf<unsigned> d_ginteresting;
+    bool fresh_valid = false;
+    unsigned grow_window = 16;
+    if (use_grow_batch && n < max_size) {
+        DVS_TRY(fresh.alloc(dim, cap));
+        DVS_TRY(d_gparts.alloc((size_t)kGrowWindowMax * (cap + 3)));
+        DVS_TRY(d_gmd.alloc((size_t)kGrowWindowMax * cap));
+        DVS_TRY(d_gmb.alloc((size_t)kGrowWindowMax * cap));
+        DVS_TRY(d_gscratch.alloc(kGrowWindowMax));
+        DVS_TRY(d_ginteresting.alloc(1));
+    }
+    unsigned fresh_n = 0;
+    const SelState* fresh_of = nullptr;
+    int fresh_which = -1;
+    bool single_candidate = false;  // the grow filter has already isolated the candidate at `cursor`
+    // while the set grows at almost every candidate (e.g. cov right after the start) the filter skips
+    // nothing: after two such windows in a row it is bypassed for 1, 2, 4, 8 candidates
+    unsigned filter_streak = 0, filter_bypass = 0;
     while (cursor < num) {
+        if (use_grow_batch && n < max_size && !single_candidate && filter_bypass > 0) {
+            --filter_bypass;
+            single_candidate = true;  // straight to the host path for this candidate
+            continue;
+        }
+        if (use_grow_batch && n < max_size && !single_candidate) {
+            if (!fresh_valid || fresh_n != n || fresh_of != cur || fresh_which != cur->which) {
+                k_sel_sum<<<sel.vec_grid(), 256, 0, st>>>(f->freqs.p, f->entropy.p, dim, cur->members(), n, -1, fresh.S(),
+                                                          fresh.members(), fresh.sc.p);
+                DVS_LAUNCHED(ctx);
+                fresh_valid = true;
+                fresh_n = n;
+                fresh_of = cur;
+                fresh_which = cur->which;
+            }
+            const unsigned W = std::min(grow_window, num - cursor);
+            DVS_CUDA_TRY(cudaMemsetAsync(d_ginteresting.p, 0xFF, sizeof(unsigned), st));
+            k_grow_eval<<<dim3(n + 3, W), kFastThreads, 0, st>>>(f->freqs.p, dim, cur->S(), cur->members(), cur->sc.p,
+                                                                 fresh.S(), f->valid.p, is_member.p, d_order.p, cursor,
+                                                                 d_gparts.p);
+            DVS_LAUNCHED(ctx);
+            k_grow_decide<<<W, kFastThreads, 0, st>>>(f->entropy.p, dim, cur->members(), cur->sc.p, fresh.sc.p, f->valid.p,
+                                                      is_member.p, d_order.p, cursor, d_gparts.p, d_gmd.p, d_gmb.p, cap,
+                                                      d_gscratch.p, d_ginteresting.p, mode == DVS_MODE_MAX_COV ? 1 : 0);
+            DVS_LAUNCHED(ctx);
+            unsigned* h_fi = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ctx->pinned) + sizeof(SelScal));
+            DVS_CUDA_TRY(cudaMemcpyAsync(h_fi, d_ginteresting.p, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            DVS_CUDA_TRY(cudaStreamSynchronize(st));
+            const unsigned fi = *h_fi;
+            if (fi == kNone) {  // the whole window was certainly rejected
+                cursor += W;
+                grow_window = std::min(grow_window * 2u, kGrowWindowMax);
+                continue;
+            }
+            grow_window = std::max(4u, std::min(kGrowWindowMax, 2u * (fi - cursor + 1u)));
+            if (fi == cursor) {
+                if (++filter_streak >= 2) filter_bypass = 1u << std::min(filter_streak - 2u, 3u);
+            } else {
+                filter_streak = 0;
+            }
+            cursor = fi;  // everything before it is certainly rejected; the host path below takes this one
+            single_candidate = true;
+            continue;
+        }
         if (use_persist && (!grow_mode || n == max_size)) {
             // every remaining round in one cooperative launch (until done, or halted for the host)
             const bool use_sm = sm_ok && n <= kSmMaxN;
@@ -1714,7 +1892,8 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
             DVS_TRY(sel.reset_scan(*cur));
             if (cursor >= num) break;
         }
-        const unsigned count = std::min(window, num - cursor);
+        const unsigned count = single_candidate ? 1u : std::min(window, num - cursor);
+        single_candidate = false;
         SelScal h;
         unsigned pos = kNone;
         if (use_fast) {

@@ -307,6 +307,13 @@ def test_select_fast_path_equals_exact_only(lib, ctx, orc, monkeypatch):
             assert i0.tolist() == i1.tolist() and np.array_equal(d0, d1) and np.array_equal(s0, s1)
             assert ctx._lib.dvs_select_last_exact_evals(ctx.handle) <= 5  # decisions are far from ties here
     monkeypatch.delenv("DVS_SELECT_PERSIST")
+    # max modes: batched grow attempts (default) against one host-driven attempt per candidate
+    for mode, lo, hi in ((lib.MODE_MAX_STDEV, 10, 30), (lib.MODE_MAX_COV, 10, 60), (lib.MODE_MAX_STDEV, 3, 1500)):
+        monkeypatch.setenv("DVS_SELECT_GROW_BATCH", "0")
+        i0, d0, s0 = kf.select(order, mode, lo, hi)
+        monkeypatch.delenv("DVS_SELECT_GROW_BATCH")
+        i1, d1, s1 = kf.select(order, mode, lo, hi)
+        assert i0.tolist() == i1.tolist() and np.array_equal(d0, d1) and np.array_equal(s0, s1)
     _, of, oe, ov = orc.count_batch(flat, off, 5)
     exp = orc.select_rows(of, oe, order, "nmost", 40, valid=ov)
     i1, d1, s1 = kf.select(order, lib.MODE_NMOST, 40)
