@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(kEntThreads)
 k_freq_entropy(const uint32_t* __restrict__ counts, uint64_t dim, double* __restrict__ freqs,
                uint64_t* __restrict__ totals, double* __restrict__ entropy, uint8_t* __restrict__ valid,
                uint8_t* __restrict__ err, double* __restrict__ err_total) {
-    extern __shared__ double ent_smem[];
+    extern __shared__ __align__(16) double ent_smem[];
     __shared__ unsigned long long s_total;
     const uint32_t r = blockIdx.x;
     const uint32_t* c = counts + (size_t)r * dim;
@@ -564,7 +564,7 @@ k_freq_entropy(const uint32_t* __restrict__ counts, uint64_t dim, double* __rest
 __global__ void __launch_bounds__(kEntThreads)
 k_rows_entropy(const double* __restrict__ freqs, uint64_t dim, double* __restrict__ entropy,
                uint8_t* __restrict__ err, double* __restrict__ err_total, int write_entropy) {
-    extern __shared__ double ent_smem[];
+    extern __shared__ __align__(16) double ent_smem[];
     const uint32_t r = blockIdx.x;
     const double* f = freqs + (size_t)r * dim;
     EntropyResult h = block_entropy_exact(dim, [&](uint64_t i) { return f[i]; }, ent_smem);

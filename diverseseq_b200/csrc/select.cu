@@ -180,7 +180,7 @@ __global__ void k_sel_replace_vec(const double* __restrict__ F, const double* __
 __global__ void __launch_bounds__(kEntThreads)
 k_sel_update(const double* __restrict__ F, const double* __restrict__ H, uint64_t dim, const double* __restrict__ S,
              const unsigned* __restrict__ members, double* __restrict__ mdelta, SelScal* sc) {
-    extern __shared__ double ent_smem[];
+    extern __shared__ __align__(16) double ent_smem[];
     __shared__ unsigned s_last;
     const unsigned j = blockIdx.x, n = sc->n;
     const double nd = (double)n;
@@ -273,7 +273,7 @@ k_sel_scan(const double* __restrict__ F, const double* __restrict__ H, uint64_t 
            const double* __restrict__ candH, const uint8_t* __restrict__ cand_valid,
            const uint8_t* __restrict__ is_member, const unsigned* __restrict__ order, unsigned pos0,
            double* __restrict__ delta_out) {
-    extern __shared__ double ent_smem[];
+    extern __shared__ __align__(16) double ent_smem[];
     const unsigned pos = pos0 + blockIdx.x;
     const unsigned row = order ? order[pos] : pos;
     if (cand_valid && !cand_valid[row]) return;     // Err("No valid k-mers") -> skipped
