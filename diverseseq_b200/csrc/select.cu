@@ -447,6 +447,25 @@ __device__ FastSum block_entropy_ilp(unsigned lo, unsigned hi, Num num, const Fa
     return r;
 }
 
+// The same evaluation for the kernels that keep their state in global memory (host-driven and
+// device-driven rounds, the cooperative kernel, the batched grow attempts — the k >= 7 paths): m_i =
+// num(i) / divisor, optionally clamped (<= EPS -> 0).  Stages the log2 table itself; divisors beyond the
+// range the exact division was verified for, and vectors longer than 2^30, take the one-element-at-a-time
+// form with __ddiv_rn (same values either way).
+template <bool CLAMP, class Num>
+__device__ FastSum block_entropy_div(uint64_t dim, Num num, double divisor) {
+    if (dim > (1ull << 30) || !(divisor >= 1.0 && divisor <= 4096.0)) {  // block-uniform
+        return block_entropy_fast(dim, [&](uint64_t i) {
+            const double m = __ddiv_rn(num(i), divisor);
+            return (CLAMP && m <= kEps) ? 0.0 : m;
+        });
+    }
+    __shared__ double2 s_ltab_div[64];
+    dvs_log2_stage_table(s_ltab_div);
+    __syncthreads();
+    return block_entropy_ilp<CLAMP, 8>(0u, (unsigned)dim, num, make_fast_div(divisor), s_ltab_div);
+}
+
 // Each thread first sums dim/kFastThreads elements sequentially, then the partials are tree-summed:
 // |sum_fast - real sum| <= (dim/kFastThreads + 12) u A, the reference's sequential sum is within
 // (dim - 1) u A, and the per-term differences add 6 u A; 1.2e-16 > u = 2^-53 absorbs second-order terms.
@@ -611,8 +630,8 @@ __device__ __forceinline__ void scan_fast_body(const double* __restrict__ F, con
     const double nd = (double)q.n;
     const double* fl = F + (size_t)q.low_row * dim;
     const double* fc = F + (size_t)row * dim;
-    FastSum h = block_entropy_fast(
-        dim, [&](uint64_t i) { return __ddiv_rn(__dadd_rn(__dsub_rn(__ldcg(S + i), fl[i]), fc[i]), nd); });
+    FastSum h = block_entropy_div<false>(
+        dim, [&](uint64_t i) { return __dadd_rn(__dsub_rn(__ldcg(S + i), fl[i]), fc[i]); }, nd);
     if (threadIdx.x == 0) {
         const double mean_entropy = __ddiv_rn(__dadd_rn(__dsub_rn(q.E, H[q.low_row]), H[row]), nd);
         const double d = h.e - mean_entropy;
@@ -673,7 +692,7 @@ k_sel_update_fast(const double* __restrict__ F, const double* __restrict__ H, ui
     const unsigned j = blockIdx.x, n = sc->n;
     const double nd = (double)n;
     if (j == n) {
-        FastSum h = block_entropy_fast(dim, [&](uint64_t i) { return __ddiv_rn(S[i], nd); });
+        FastSum h = block_entropy_div<false>(dim, [&](uint64_t i) { return S[i]; }, nd);
         if (threadIdx.x == 0) {
             const double me = __ddiv_rn(sc->E, nd);
             sc->total_jsd = h.e - me;
@@ -684,10 +703,7 @@ k_sel_update_fast(const double* __restrict__ F, const double* __restrict__ H, ui
         const unsigned row = members[j];
         const double div = __dsub_rn(nd, 1.0);
         const double* f = F + (size_t)row * dim;
-        FastSum h = block_entropy_fast(dim, [&](uint64_t i) {
-            double m = __ddiv_rn(__dsub_rn(S[i], f[i]), div);
-            return (m <= kEps) ? 0.0 : m;
-        });
+        FastSum h = block_entropy_div<true>(dim, [&](uint64_t i) { return __dsub_rn(S[i], f[i]); }, div);
         if (threadIdx.x == 0) {
             const double mean_entropy = __ddiv_rn(__dsub_rn(sc->E, H[row]), div);
             mdelta[j] = h.e - mean_entropy;
@@ -740,11 +756,11 @@ __device__ __forceinline__ void replace_update_fast_body(
         return __dadd_rn(s, fc[i]);
     };
     if (j == n) {
-        FastSum h = block_entropy_fast(dim, [&](uint64_t i) {
+        FastSum h = block_entropy_div<false>(dim, [&](uint64_t i) {
             const double s = s_new(i);
             S_out[i] = s;
-            return __ddiv_rn(s, nd);
-        });
+            return s;
+        }, nd);
         if (threadIdx.x == 0) {
             const double me = __ddiv_rn(E_new, nd);
             sc->total_jsd = h.e - me;
@@ -756,10 +772,7 @@ __device__ __forceinline__ void replace_update_fast_body(
         const unsigned row = j < low ? __ldcg(m_in + j) : (j + 1 < n ? __ldcg(m_in + j + 1) : cand_row);
         const double div = __dsub_rn(nd, 1.0);
         const double* f = F + (size_t)row * dim;
-        FastSum h = block_entropy_fast(dim, [&](uint64_t i) {
-            double m = __ddiv_rn(__dsub_rn(s_new(i), f[i]), div);
-            return (m <= kEps) ? 0.0 : m;
-        });
+        FastSum h = block_entropy_div<true>(dim, [&](uint64_t i) { return __dsub_rn(s_new(i), f[i]); }, div);
         if (threadIdx.x == 0) {
             const double mean_entropy = __ddiv_rn(__dsub_rn(E_new, H[row]), div);
             mdelta[j] = h.e - mean_entropy;
@@ -947,17 +960,14 @@ k_grow_eval(const double* __restrict__ F, uint64_t dim, const double* __restrict
     FastSum h;
     if (t == 0) {  // increases_jsd against the current state (records.rs:70-92)
         const double* fl = F + (size_t)members[sc_cur->lowest] * dim;
-        h = block_entropy_fast(dim, [&](uint64_t i) { return __ddiv_rn(__dadd_rn(__dsub_rn(S_cur[i], fl[i]), fc[i]), nd); });
+        h = block_entropy_div<false>(dim, [&](uint64_t i) { return __dadd_rn(__dsub_rn(S_cur[i], fl[i]), fc[i]); }, nd);
     } else if (t == 1) {  // total of the grown set: clone() re-sums in member order, push adds the candidate
         const double nd1 = __dadd_rn(nd, 1.0);
-        h = block_entropy_fast(dim, [&](uint64_t i) { return __ddiv_rn(__dadd_rn(S_fresh[i], fc[i]), nd1); });
+        h = block_entropy_div<false>(dim, [&](uint64_t i) { return __dadd_rn(S_fresh[i], fc[i]); }, nd1);
     } else {  // leave-one-out of member j of the grown set (j == n: the candidate itself)
         const unsigned j = t - 2;
         const double* f = j < n ? F + (size_t)members[j] * dim : fc;
-        h = block_entropy_fast(dim, [&](uint64_t i) {
-            const double m = __ddiv_rn(__dsub_rn(__dadd_rn(S_fresh[i], fc[i]), f[i]), nd);
-            return (m <= kEps) ? 0.0 : m;
-        });
+        h = block_entropy_div<true>(dim, [&](uint64_t i) { return __dsub_rn(__dadd_rn(S_fresh[i], fc[i]), f[i]); }, nd);
     }
     if (threadIdx.x == 0) parts[(size_t)c * (n + 3) + t] = h;
 }
