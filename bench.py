@@ -369,7 +369,7 @@ def main():
         return r
 
     ms_step, (idx, delta, stats) = timed(step_resident, a.steps)
-    launches = (ctx.launch_count - launches0) // max(a.steps, 1)
+    launches = ctx.launch_count - launches0  # kernels of libdvs_b200.so launched inside the timed region (all K steps)
     clocks = sampler.stop() if rank == 0 else None
     accepts = int(ctx._lib.dvs_select_last_accepts(ctx.handle))
     value = total_bases / (ms_step * 1e-3) / 1e9
@@ -501,7 +501,8 @@ def main():
                 "dtype": "u8 bases -> u32 counts -> f64 frequencies/entropy/JSD", "data": "synthetic",
                 "config": workload_config(a, world), "roofline": roofline, "cpu_baseline": base, "e2e": e2e,
                 "gpu_launches": int(launches), "clocks": clocks,
-                "extra": {"count_kernel_gbp_per_s": bases / (kc_ms * 1e-3) / 1e9, "count_kernel_ms": kc_ms,
+                "extra": {"gpu_launches_per_step": int(launches) // max(a.steps, 1),
+                          "count_kernel_gbp_per_s": bases / (kc_ms * 1e-3) / 1e9, "count_kernel_ms": kc_ms,
                           "freq_entropy_ms": float(np.mean(fe_ms)), "nmost_wall_s": float(np.mean(sel_ms)) * 1e-3,
                           "nmost_accepts": accepts, "total_gbp": total_bases / 1e9,
                           "selected_head": idx[:8].tolist(), "total_jsd": float(stats[0]),
