@@ -9,8 +9,9 @@ Metric = whole-step throughput in Gbp/s (bases consumed / step time).
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 N>1 is launched by torchrun (one rank per GPU, NCCL); each rank counts its own 10.5k-genome
-shard (weak scaling), the rows are all-gathered and every rank replays the same selection over
-the union.  `value` times the step with inputs already in HBM; `e2e` times the same step through
+shard (weak scaling) and selects from it, the N x n winning rows are all-gathered and merged with
+final_nmost on every rank (the reference's -np semantics; --multi union replays one selection over
+all rows instead).  `value` times the step with inputs already in HBM; `e2e` times the same step through
 the public host-buffer API (pinned host -> device copy + result read-back inside the timed region).
 `--impl reference` times the CPU restatement of the reference (oracle/) on the host cores.
 """
