@@ -217,9 +217,7 @@ def _select_from_store(store, seqids, k, num_states, mode, min_size, max_size) -
         raise ValueError(f"The number of sequences {len(seqids)} is < n {min_size}")
     kf = _lib.KFreqs.count(ctx, seqset, k, num_states)
     idx, delta, stats = kf.select(order, mode, min_size, max_size)
-    rows = np.zeros((len(idx), kf.dim), dtype=np.float64)
-    for j, r in enumerate(idx):
-        rows[j] = kf.download(int(r), 1, counts=False)[1][0]
+    rows = kf.download_rows(idx)
     return _make_result([names[r] for r in idx], rows, delta, stats, k, num_states)
 
 
@@ -318,7 +316,7 @@ class SummedRecordsWrapper:
 
     def get_result(self) -> SummedRecordsResult:
         idx, delta, stats, _low = self._summed.result()
-        rows = np.stack([self._kf.download(int(r), 1, counts=False)[1][0] for r in idx])
+        rows = self._kf.download_rows(idx)
         return _make_result([self._names[r] for r in idx], rows, delta, stats, self._k, self._num_states)
 
 

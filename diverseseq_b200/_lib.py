@@ -333,6 +333,17 @@ class KFreqs(_Handle):
                                                  rows.size, C.byref(h)))
         return KFreqs(self.ctx, h)
 
+    def download_rows(self, rows) -> np.ndarray:
+        """frequency rows `rows` as one [len(rows), dim] f64 array: one device gather + one copy (the
+        records of a SummedRecordsResult) instead of one round trip per row"""
+        rows = np.ascontiguousarray(rows, dtype=np.uint32)
+        if rows.size == 0:
+            return np.zeros((0, self.dim), dtype=np.float64)
+        taken = self.take_rows(rows)
+        out = taken.download(counts=False)[1]
+        taken.close()
+        return out
+
     def device_ptrs(self) -> tuple[int, int, int]:
         a, b, c = _vp(), _vp(), _vp()
         check(self.ctx._lib.dvs_kfreqs_device_ptrs(self.handle, C.byref(a), C.byref(b), C.byref(c)))
@@ -360,6 +371,8 @@ class KFreqs(_Handle):
         """nmost / max selection; returns (row indices, delta_jsd, stats5)"""
         order = np.ascontiguousarray(order, dtype=np.uint32)
         cap = max(int(min_size), int(max_size), 1) + 1
+        if int(mode) != MODE_NMOST and int(max_size) < int(min_size):
+            cap = order.size + 1  # the set can grow without bound (dvs_b200.h, dvs_select)
         idx = np.zeros(cap, dtype=np.uint32)
         delta = np.zeros(cap, dtype=np.float64)
         stats = np.zeros(5, dtype=np.float64)

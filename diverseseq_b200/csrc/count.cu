@@ -656,6 +656,14 @@ int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dv
         set_error("dvs_count_kmers: num_states^k = %d^%d does not fit a dense u32-indexed table", num_states, k);
         return DVS_ERR_ARG;
     }
+    // per-bin counters are u32 (the reference counts in usize): a bin cannot exceed the number of k-mers
+    // of its record, so records below 2^32 bases can never wrap; longer ones are refused, not miscounted
+    for (uint32_t r = 0; r < s->nrec; ++r)
+        if (s->h_offsets[r + 1] - s->h_offsets[r] >= (1ULL << 32)) {
+            set_error("dvs_count_kmers: record %u has %llu bases; records of 2^32 bases or more are not supported "
+                      "(32-bit bin counters)", r, (unsigned long long)(s->h_offsets[r + 1] - s->h_offsets[r]));
+            return DVS_ERR_ARG;
+        }
     DVS_CUDA_TRY(dvs::enter(ctx));
     size_t free_b = 0, total_b = 0;
     const double need = (double)s->nrec * (double)dim * 12.0;

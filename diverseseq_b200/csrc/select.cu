@@ -491,10 +491,14 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
     {   // duplicates in the initial set: the reference's Vec keeps both rows; keep that behaviour
     }
 
-    const unsigned cap = std::max<unsigned>(std::max(min_size, max_size), (unsigned)init.size()) + 1;
+    const bool grow_mode = (mode != DVS_MODE_NMOST);
+    // max modes with max_size below the initial size (e.g. max_size < min_size, which only the reference's
+    // CLI rejects, cli.py:311): `size == max_size` never holds, so the set keeps growing as in
+    // records.rs:427-451 - every buffer is then sized for all `num` records
+    const bool unbounded = grow_mode && max_size < (uint32_t)init.size();
+    const unsigned cap = (unbounded ? num : std::max<unsigned>(std::max(min_size, max_size), (unsigned)init.size())) + 1;
     SelState A, B;
     DVS_TRY(A.alloc(dim, cap));
-    const bool grow_mode = (mode != DVS_MODE_NMOST);
     if (grow_mode) DVS_TRY(B.alloc(dim, cap));
     DevBuf<uint8_t> is_member;
     DevBuf<unsigned> d_order, d_init;
@@ -563,7 +567,7 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
     DevBuf<unsigned> d_ginteresting;
     bool fresh_valid = false;
     unsigned grow_window = 16;
-    if (use_grow_batch && n < max_size) {
+    if (use_grow_batch && n != max_size) {
         DVS_TRY(fresh.alloc(dim, cap));
         DVS_TRY(d_gparts.alloc((size_t)kGrowWindowMax * (cap + 3)));
         DVS_TRY(d_gmd.alloc((size_t)kGrowWindowMax * cap));
@@ -579,12 +583,12 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
     // nothing: after two such windows in a row it is bypassed for 1, 2, 4, 8 candidates
     unsigned filter_streak = 0, filter_bypass = 0;
     while (cursor < num) {
-        if (use_grow_batch && n < max_size && !single_candidate && filter_bypass > 0) {
+        if (use_grow_batch && n != max_size && !single_candidate && filter_bypass > 0) {
             --filter_bypass;
             single_candidate = true;  // straight to the host path for this candidate
             continue;
         }
-        if (use_grow_batch && n < max_size && !single_candidate) {
+        if (use_grow_batch && n != max_size && !single_candidate) {
             if (!fresh_valid || fresh_n != n || fresh_of != cur || fresh_which != cur->which) {
                 k_sel_sum<<<sel.vec_grid(), 256, 0, st>>>(f->freqs.p, f->entropy.p, dim, cur->members(), n, -1, fresh.S(),
                                                           fresh.members(), fresh.sc.p);

@@ -236,13 +236,19 @@ class DvseqszStore:
         if list(meta["chunk_grid"]["configuration"]["chunk_shape"]) != [n]:
             raise RuntimeError(f"{seqid}: expected a single chunk")
         sep = meta.get("chunk_key_encoding", {}).get("configuration", {}).get("separator", "/")
-        frame = ((d / "c" / "0") if sep == "/" else (d / "c.0")).read_bytes()
+        chunk = (d / "c" / "0") if sep == "/" else (d / "c.0")
+        if not chunk.exists():
+            # zarrs does not store a chunk that consists of the fill value only (a record of code 0 = 'T')
+            out[:n] = int(meta.get("fill_value", 0))
+            return n
+        frame = chunk.read_bytes()
         codecs = [c["name"] for c in meta.get("codecs", [])]
         if "zstd" in codecs:
             got = zstd_decompress_into(frame, out[:n])
         else:
-            out[:n] = np.frombuffer(frame, dtype=np.uint8)
-            got = n
+            got = len(frame)
+            if got == n:
+                out[:n] = np.frombuffer(frame, dtype=np.uint8)
         if got != n:
             raise RuntimeError(f"{seqid}: decoded {got} bytes, expected {n}")
         return n

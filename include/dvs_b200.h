@@ -113,7 +113,8 @@ int dvs_prep_fasta(dvs_ctx* ctx, const uint8_t* text, const uint64_t* file_offse
  * SeqRecord::to_kcounts / to_kmerseq / entropy  (src/record.rs:41-84, 124-141, 86-106).
  * Result rows stay in HBM.  A record with no valid k-mer is marked valid=0 (the reference
  * returns Err and callers skip it, src/records.rs:302,333).  Entropy is evaluated in the
- * reference's sequential order with glibc's log2 algorithm, so it is bit-identical. */
+ * reference's sequential order with glibc's log2 algorithm, so it is bit-identical.  Bin counters are 32-bit:
+ * a record of 2^32 bases or more is refused with DVS_ERR_ARG (the reference counts in usize). */
 int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dvs_kfreqs** out);
 /* rows already computed elsewhere, e.g. SummedRecordsResult.records of per-chunk results fed to
  * final_nmost / final_max (src/records.rs:344-360): entropy is recomputed from the stored
@@ -148,7 +149,9 @@ int dvs_count_kmers_host(dvs_ctx* ctx, const uint8_t* seqs, const uint64_t* offs
  * the record identity, i.e. stands in for seqid).  Single-pass, order-dependent semantics of the
  * reference with numprocs=1.  Outputs, in the reference's final Vec order: sel_idx[size],
  * sel_delta[size] (delta_jsd per record), stats = {total_jsd, mean_delta_jsd, std_delta_jsd,
- * cov_delta_jsd, summed_entropies}.  sel_idx/sel_delta need capacity max(min_size, max_size). */
+ * cov_delta_jsd, summed_entropies}.  sel_idx/sel_delta need capacity max(min_size, max_size); in the max modes
+ * with max_size < min_size (rejected only by the reference's CLI, cli.py:311) `size == max_size` never holds and the
+ * set may grow to `num` records as in records.rs:427-451, so the capacity must then be `num`. */
 int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_t num, int mode,
                uint32_t min_size, uint32_t max_size, uint32_t* sel_idx, double* sel_delta, double* stats5,
                uint32_t* size_out);

@@ -67,3 +67,23 @@ def test_store_layout_roundtrip_and_dedup(tmp_path, brca1):
         ro.write("x", b"\x00\x01")
     with pytest.raises(FileNotFoundError):
         _dvs.make_zarr_store(str(tmp_path / "absent.dvseqsz"))
+
+
+def test_all_fill_value_record_without_chunk_file_reads_as_zeros(tmp_path):
+    """zarrs omits a chunk made only of the fill value (0 = 'T'): the reader must return zeros, not raise"""
+    path = tmp_path / "t.dvseqsz"
+    st = _dvs.make_zarr_store(str(path), mode="w")
+    st.write("polyT", bytes(1000))
+    st.write("other", bytes([0, 1, 2, 3] * 10))
+    import xxhash
+    hexd = xxhash.xxh3_64_hexdigest(bytes(1000))
+    (path / "seqdata" / hexd / "c" / "0").unlink()  # what a reference-written store looks like for this record
+    ro = _dvs.make_zarr_store(str(path))
+    assert ro.read("polyT") == bytes(1000) and ro.read("other") == bytes([0, 1, 2, 3] * 10)
+    # a raw (codec-less) frame of the wrong length is an error, not a silent short read
+    meta_p = path / "seqdata" / xxhash.xxh3_64_hexdigest(bytes([0, 1, 2, 3] * 10)) / "zarr.json"
+    meta = json.loads(meta_p.read_text())
+    meta["codecs"] = [c for c in meta["codecs"] if c["name"] != "zstd"]
+    meta_p.write_text(json.dumps(meta))
+    with pytest.raises(RuntimeError):
+        _dvs.make_zarr_store(str(path)).read("other")

@@ -1,18 +1,12 @@
 """Full-size parity for BASELINE.json configs[2..4] against oracle-only goldens
-(tests/golden/make_fullsize_golden_ctree_max.py).
-
-NOT YET RUN ON A GPU: the goldens were generated after round 1's GPU budget was spent, so these tests are
-opt-in (DVS_RUN_UNVALIDATED=1) until a round has run them once; the k=6 / nmost counterpart
-(test_gpu_fullsize.py) is validated and always on.  What could be compared without a GPU run already agrees:
-the mash matrix's mean distance and the sizes of the `max` selections printed by tools/bench_configs.py."""
-import os
+(tests/golden/make_fullsize_golden_ctree_max.py): configs[3] = mash k=16 s=3000 on 1,000 genomes,
+configs[2] = `max` sweeps at k=8 over the 10,500-genome set, configs[4] = Euclidean k=8 on the same set."""
 import pathlib
 
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("DVS_RUN_UNVALIDATED") != "1", reason="opt-in until validated on a GPU")]
+pytestmark = pytest.mark.gpu
 
 SEED, NFAM, MEAN_LEN = 20261017, 64, 4_000_000
 GOLD = pathlib.Path(__file__).resolve().parent / "golden"
