@@ -81,6 +81,19 @@ SIGNATURES = {
 
 _lib = None
 _lock = threading.Lock()
+_shutdown = False
+
+
+def _at_exit() -> None:
+    """interpreter shutdown: objects finalised from here on must not call into the CUDA runtime any more
+    (its own teardown may already be under way); the process exit releases everything"""
+    global _shutdown
+    _shutdown = True
+
+
+import atexit  # noqa: E402
+
+atexit.register(_at_exit)
 
 
 def load() -> C.CDLL:
@@ -138,9 +151,9 @@ class Context:
         self.device = int(device)
 
     def close(self) -> None:
-        if getattr(self, "handle", None):
+        if getattr(self, "handle", None) and not _shutdown:
             self._lib.dvs_ctx_destroy(self.handle)
-            self.handle = None
+        self.handle = None
 
     def __del__(self):
         try:
@@ -193,9 +206,10 @@ class _Handle:
         self.handle = handle
 
     def close(self) -> None:
-        if getattr(self, "handle", None):
+        # a handle that outlives its context (or the interpreter) is left to the process exit
+        if getattr(self, "handle", None) and not _shutdown and getattr(self.ctx, "handle", None):
             getattr(self.ctx._lib, self._free)(self.handle)
-            self.handle = None
+        self.handle = None
 
     def __del__(self):
         try:

@@ -366,6 +366,13 @@ k_count_s3(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offset
             if (SCR) off ^= (off >> 5) & ~3u;
             atomicAdd(reinterpret_cast<uint32_t*>(hist_b + off), 1u << ((y & 1u) << 4));
         };
+        // same, from v = y << 1 with garbage above bit 2kk (fast path: 3-4 instructions per atomic)
+        const uint32_t offmask = mask << 1 & ~3u;
+        auto bump_v = [&](uint32_t v) {
+            uint32_t off = v & offmask;
+            if (SCR) off ^= (off >> 5) & ~3u;
+            atomicAdd(reinterpret_cast<uint32_t*>(hist_b + off), (v & 2u) ? 0x10000u : 1u);
+        };
 
         const uint32_t item_len = (uint32_t)(w.end - w.begin);
         const uint32_t rs = start > w.begin ? (uint32_t)min(start - w.begin, (uint64_t)item_len) : 0u;
@@ -376,6 +383,7 @@ k_count_s3(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offset
         const uint32_t r0 = min(item_len, (uint32_t)warp * span);
         const uint32_t r1 = min(item_len, r0 + span);
         const uint8_t* base = seqs + w.begin;
+        const uint32_t safe_hi = min(min(re, r1), tail_a);
         uint32_t carry_pc = 0;
         bool carry_ok = false;
         // phase of the lane's block start (absolute position mod 3); 16 == 1 and 512 == 2 (mod 3)
@@ -399,8 +407,10 @@ k_count_s3(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offset
             if (r >= r1) break;  // warp-uniform
             const uint32_t a = r + 16 * lane;
             const uint4 cur = ring[u];
-            const bool ok = (((cur.x | cur.y | cur.z | cur.w) & 0xFCFCFCFCu) == 0) && (a >= rs) && (a + 16 <= re) &&
-                            (a < r1) && (a != tail_a);
+            // interior steps (warp-uniform test): all 512 bytes lie inside the record, the span and before
+            // the tail block, so only the bytes themselves can invalidate a block
+            bool ok = ((cur.x | cur.y | cur.z | cur.w) & 0xFCFCFCFCu) == 0;
+            if (!(r >= rs && r + 512u <= safe_hi)) ok = ok && (a >= rs) && (a + 16 <= re) && (a < r1) && (a != tail_a);
             const uint32_t pc = pack16p(cur);
             // refill the slot only now: in the common path `cur` is dead from here on, so the load lands in
             // the same registers without a copy (the per-byte path re-reads its 32 bytes)
@@ -409,16 +419,22 @@ k_count_s3(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offset
             if (lane == 0) pp = carry_pc;
             const uint32_t okmask = __ballot_sync(kFull, ok);
             const bool prev_ok = lane == 0 ? carry_ok : ((okmask >> (lane - 1)) & 1u) != 0;
-            if (ok && prev_ok) {
-                // (k+2)-mers ending at j = j0, j0+3, ... (< 16), j0 = 2 - ph
-                uint32_t sh = 2u * (13u + ph);  // 2 * (15 - j0)
+            // (k+2)-mers ending at j = j0, j0+3, ... (< 16), j0 = 2 - ph.  The 64-bit window pp:pc is
+            // aligned once by the lane's phase (W = pp:pc >> 2 ph), after which the five words sit at
+            // compile-time shifts: v_i = W >> (25 - 6 i) holds (k+2)-mer i in bits [2kk:1], i.e. the byte
+            // offset of its counter word in bits [2kk:2] and the half selector in bit 1.
+            auto fast_block = [&]() {
+                const uint32_t sa = 2u * ph;
+                const uint32_t wlo = __funnelshift_r(pc, pp, sa), whi = pp >> sa;
 #pragma unroll
-                for (int t = 0; t < 5; ++t) {
-                    bump(__funnelshift_r(pc, pp, sh) & mask);
-                    sh -= 6u;
-                }
-                if (ph == 2) bump(pc & mask);  // j0 = 0: a sixth one ends at j = 15
+                for (int t = 0; t < 5; ++t) bump_v(__funnelshift_r(wlo, whi, 25 - 6 * t));
+                if (ph == 2) bump_v(pc << 1);  // j0 = 0: a sixth one ends at j = 15
                 n_inc += 5u + (ph == 2 ? 1u : 0u);
+            };
+            if (okmask == kFull && carry_ok) {  // warp-uniform: the common case
+                fast_block();
+            } else if (ok && prev_ok) {
+                fast_block();
             } else if (a < r1) {
                 const uint4 prev = ldg16(base + a - 16), cur2 = ldg16(base + a);
                 const uint32_t wv[8] = {prev.x, prev.y, prev.z, prev.w, cur2.x, cur2.y, cur2.z, cur2.w};
@@ -815,7 +831,10 @@ int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dv
             e = cudaSuccess;
             if (d_retry.alloc(n_work) != DVS_OK || d_rc.alloc(2) != DVS_OK) return fail(DVS_ERR_CUDA);
             TRY_F(cudaMemsetAsync(d_rc.p, 0, 2 * sizeof(uint32_t), st));
-            auto s3 = scramble ? k_count_s3<true, 1024> : k_count_s3<false, 1024>;
+            // the 8-mer table spreads over 32,768 words: bank scrambling costs two instructions per atomic and
+            // buys nothing here unless asked for (DVS_COUNT_SCRAMBLE=1)
+            const bool scr3 = scr_env && scr_env[0] == '1';
+            auto s3 = scr3 ? k_count_s3<true, 1024> : k_count_s3<false, 1024>;
             auto rk = scramble ? k_count<MODE_SUPER, true, 512> : k_count<MODE_SUPER, false, 512>;
             TRY_F(cudaFuncSetAttribute(s3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
             const size_t retry_bytes = (size_t)dim * 20;
