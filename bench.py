@@ -8,10 +8,13 @@ Metric = whole-step throughput in Gbp/s (bases consumed / step time).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-N>1 is launched by torchrun (one rank per GPU, NCCL); each rank counts its own 10.5k-genome
-shard (weak scaling) and selects from it, the N x n winning rows are all-gathered and merged with
-final_nmost on every rank (the reference's -np semantics; --multi union replays one selection over
-all rows instead).  `value` times the step with inputs already in HBM; `e2e` times the same step through
+N>1 is launched by torchrun (one rank per GPU); each rank counts its own 10.5k-genome shard (weak
+scaling) and pushes its frequency rows to every peer over NVLink while it is still counting; the nmost
+selection is then ONE single pass over all N x 10.5k records (numprocs=1 semantics) with every window of
+candidates scored candidate-sharded and a 16-byte all-reduce(min) per round through the library's peer
+windows (no NCCL in the data path; torch.distributed only carries the timing reductions).  --multi chunked
+runs the reference's -np semantics instead (select per GPU, final_nmost merge of the winners).
+`value` times the step with inputs already in HBM; `e2e` times the same step through
 the public host-buffer API (pinned host -> device copy + result read-back inside the timed region).
 `--impl reference` times the CPU restatement of the reference (oracle/) on the host cores.
 """
@@ -47,9 +50,10 @@ def parse_args():
     ap.add_argument("--nfam", type=int, default=64)
     ap.add_argument("--k", type=int, default=6)
     ap.add_argument("--n", type=int, default=100)
-    ap.add_argument("--multi", default="chunked", choices=["chunked", "union"],
-                    help="N>1 selection: 'chunked' = the reference's -np N semantics (select per GPU, merge with "
-                         "final_nmost); 'union' = single-pass selection over all records on every GPU")
+    ap.add_argument("--multi", default="sharded", choices=["sharded", "chunked"],
+                    help="N>1 selection: 'sharded' = ONE single-pass selection over all records, candidate-sharded "
+                         "with a per-round all-reduce(min) over NVLink; 'chunked' = the reference's -np N semantics "
+                         "(select per GPU, merge with final_nmost)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ctree", action="store_true", help="skip the ctree pairs/s side measurements (N=1 only)")
@@ -66,9 +70,34 @@ def workload_config(a, world):
         "parallelism": ("1 GPU" if world == 1 else
                         f"records sharded x{world}; nmost per GPU then final_nmost merge of the {world}x{a.n} winners "
                         "(reference -np semantics, records.py:206-251)" if a.multi == "chunked" else
-                        f"records sharded x{world}, rows all-gathered, single-pass selection replicated"),
+                        f"records sharded x{world} (rows pushed to all peers during counting); ONE single-pass nmost "
+                        f"over all {world}x{a.nrec} records, candidate-sharded, all-reduce(min) per round over NVLink"),
         "l2": "inputs (~42 GB/GPU) are far larger than the 126 MB L2, no flush needed",
     }
+
+
+# ------------------------------------------------- timing plumbing (torch.distributed only) ----
+def max_over_ranks(value: float, device=None) -> float:
+    """timing rule: a multi-GPU duration is the max over ranks"""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value: float, device=None) -> float:
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
 
 
 # --------------------------------------------------------------------------- clocks ----
@@ -266,6 +295,114 @@ def run_reference(a):
     return 0
 
 
+
+# ------------------------------------------------------------- side metrics (configs[2..4], k=12) ----
+FP64_PEAK_TFLOPS = 40.0   # B200 nominal FP64 (vector = tensor); MEASURED_PEAKS.json carries no FP64 figure
+INT32_PEAK_TOPS = 148 * 128 * 1.965e9 / 1e12  # 128 INT32 lanes per SM and clock (nominal issue rate)
+
+
+def side_metrics(a, ctx, comm, rank, world, device, barrier, hbm_peak):
+    import torch
+
+    from diverseseq_b200 import _lib, shard
+
+    def wall(fn):
+        barrier()
+        t0 = time.perf_counter()
+        out = fn()
+        ctx.sync()
+        barrier()
+        return max_over_ranks(time.perf_counter() - t0, device), out
+
+    out = {"scaling": "strong: one record set split over the ranks", "n_gpus": world}
+    # ---- configs[3]: mash k=16 s=3000 on 1,000 genomes ----
+    n_m = 1000
+    b, e = shard.shard_bounds(n_m, world, rank)
+    ss = _lib.SeqSet.synth(ctx, SEED, e - b, a.nfam, a.mean_len, first=b)
+    _lib.Sketches.sketch(ctx, ss, 16, 3000, 4, True).close()
+    sk_wall, sk = wall(lambda: _lib.Sketches.sketch(ctx, ss, 16, 3000, 4, True))
+    sk_ms = max_over_ranks(ctx.phase_ms(_lib.PHASE_SKETCH), device)
+    mash_bases = sum_over_ranks(ss.total_bases, device)
+    npm = n_m * (n_m - 1) // 2
+    dmat = _lib.DeviceBuffer(ctx, n_m * n_m * 8)
+    if world > 1:
+        meta = comm.rv.allgather((int(sk.nrec), int(sk.stride)))
+        allsk = sk.allgather(comm, [m[0] for m in meta], max(m[1] for m in meta))
+        allsk.distances_sharded(comm, 16, 3000, dmat.ptr)
+        pairs_wall, _ = wall(lambda: allsk.distances_sharded(comm, 16, 3000, dmat.ptr))
+        allsk.close()
+    else:
+        sk.distances_into(dmat.ptr, 16, 3000)
+        pairs_wall, _ = wall(lambda: sk.distances_into(dmat.ptr, 16, 3000))
+    pairs_ms = max_over_ranks(ctx.phase_ms(_lib.PHASE_MASH_PAIRS), device)
+    int_ops = (6 * 16 + 8) * mash_bases  # ~(6k+8) integer ops per window
+    out["mash_k16_s3000_1k_genomes"] = {
+        "sketch_ms": sk_ms, "sketch_gbp_per_s": mash_bases / sk_ms / 1e6, "pairs": npm, "pairs_kernel_ms": pairs_ms,
+        "pairs_per_s": npm / pairs_ms * 1e3, "pairs_per_s_wall": npm / pairs_wall,
+        "roofline_sketch": {"bound": "int32-alu", "achieved": int_ops / sk_ms / 1e9, "peak": INT32_PEAK_TOPS * world,
+                            "unit": "Tint-op/s", "frac": int_ops / sk_ms / 1e9 / (INT32_PEAK_TOPS * world),
+                            "note": "(6k+8) integer ops per window (SURVEY 8d) vs 128 INT32 lanes/SM/clk nominal"},
+        "roofline_pairs": {"bound": "latency (L2-resident sketches)", "achieved": npm * 8 * 3000 / pairs_ms / 1e6,
+                           "unit": "GB/s nominal (8 s bytes per pair)", "peak": None, "frac": None}}
+    sk.close(); dmat.close(); ss.close()
+
+    # ---- configs[4] / configs[2]: 10.5k genomes at k=8 (rows depend on nrec x 4^8 only: 400 kbp genomes) ----
+    n_e = a.nrec
+    b, e = shard.shard_bounds(n_e, world, rank)
+    ss = _lib.SeqSet.synth(ctx, SEED, e - b, a.nfam, 400_000, first=b)
+    if world > 1:
+        kf8, _ = shard.count_sharded(ctx, comm, ss, 8)
+    else:
+        kf8 = _lib.KFreqs.count(ctx, ss, 8)
+    npe = n_e * (n_e - 1) // 2
+    dmat = _lib.DeviceBuffer(ctx, n_e * n_e * 8)
+    if world > 1:
+        eu_wall, _ = wall(lambda: kf8.euclidean_sharded(comm, dmat.ptr))
+    else:
+        eu_wall, _ = wall(lambda: kf8.euclidean_into(dmat.ptr))
+    eu_ms = max_over_ranks(ctx.phase_ms(_lib.PHASE_EUCLID), device)
+    tf = 2.0 * 65536 * npe / eu_ms / 1e9
+    entry = {"pairs": npe, "kernel_ms": eu_ms, "pairs_per_s": npe / eu_ms * 1e3, "pairs_per_s_wall": npe / eu_wall,
+             "roofline": {"bound": "fp64", "achieved": tf, "peak": FP64_PEAK_TFLOPS * world, "unit": "TFLOP/s",
+                          "frac": tf / (FP64_PEAK_TFLOPS * world),
+                          "note": "useful flops 2 D per pair (the difference form issues 3 D); nominal FP64 peak"}}
+    if rank == 0:
+        t0 = time.perf_counter()
+        children, _, _ = _lib.linkage_average(ctx, n=n_e, device_ptr=dmat.ptr)
+        entry["average_linkage"] = {"device_ms": ctx.phase_ms(_lib.PHASE_CLUSTER), "wall_ms": (time.perf_counter() - t0) * 1e3,
+                                    "merges": int(children.shape[0]), "note": "replicas only: rank 0 builds the tree"}
+    out[f"euclid_k8_{n_e}_genomes"] = entry
+    dmat.close()
+    order8 = shard.global_order(SEED, n_e)
+    sweeps = {}
+    for name, mode, lo, hi in (("stdev_5_10", _lib.MODE_MAX_STDEV, 5, 10), ("stdev_10_100", _lib.MODE_MAX_STDEV, 10, 100),
+                               ("cov_10_100", _lib.MODE_MAX_COV, 10, 100), ("nmost_100", _lib.MODE_NMOST, 100, 100)):
+        sel = (lambda m=mode, l=lo, h=hi: kf8.select_sharded(comm, order8, m, l, h)) if world > 1 else \
+              (lambda m=mode, l=lo, h=hi: kf8.select(order8, m, l, h))
+        sel()
+        w, (idx, _d, st) = wall(sel)
+        sweeps[name] = {"wall_s": w, "device_ms": max_over_ranks(ctx.phase_ms(_lib.PHASE_SELECT), device),
+                        "size": int(idx.size), "total_jsd": float(st[0]), "head": idx[:4].tolist(),
+                        "scan_bytes_per_pass": n_e * 65536 * 8}
+    out[f"max_k8_{n_e}_genomes"] = sweeps
+    kf8.close(); ss.close()
+
+    # ---- north star: k=12 counting (dense u32 rows, global RED.ADD), records sharded, no collective ----
+    n12 = 64
+    b, e = shard.shard_bounds(n12 * world, world, rank)
+    ss = _lib.SeqSet.synth(ctx, SEED + 12 + rank, n12, a.nfam, a.mean_len)
+    _lib.KFreqs.count(ctx, ss, 12).close()
+    w12, kf12 = wall(lambda: _lib.KFreqs.count(ctx, ss, 12))
+    ms12 = max_over_ranks(ctx.phase_ms(_lib.PHASE_COUNT_KERNEL), device)
+    b12 = sum_over_ranks(ss.total_bases, device)
+    dense_bytes = b12 + n12 * world * 4 * 4 ** 12
+    out["count_k12"] = {"genomes": n12 * world, "gbp": b12 / 1e9, "kernel_ms": ms12, "gbp_per_s": b12 / ms12 / 1e6,
+                        "roofline": {"bound": "hbm", "achieved": dense_bytes / ms12 / 1e6, "peak": hbm_peak * world,
+                                     "unit": "GB/s", "frac": dense_bytes / ms12 / 1e6 / (hbm_peak * world),
+                                     "note": "dense u32 rows: L + 4*4^k bytes per record (17.8 B/bp)"}}
+    kf12.close(); ss.close()
+    return out
+
 # ------------------------------------------------------------------------ B200 leg ----
 _REAL_STDOUT = None
 
@@ -303,17 +440,27 @@ def main():
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+        dist.init_process_group("nccl", device_id=device)  # timing reductions / barriers only
     ctx = _lib.Context(local)
     ctx.enable_timing(True)
     stream = torch.cuda.ExternalStream(ctx.stream, device=device)
+    comm = None
+    if world > 1:
+        # the library's own peer windows: rows of all ranks at k (headline) and, for the side metrics, the
+        # 10.5k x 4^8 rows + the n x n matrix of the ctree configs
+        rv = shard.Rendezvous()
+        need = max(shard.window_bytes_for(a.nrec * world, 4 ** a.k),
+                   0 if a.no_ctree else shard.window_bytes_for(a.nrec, 4 ** 8, a.nrec * a.nrec * 8))
+        comm = shard.connect(ctx, rv, need)
 
     # ---- synthetic inputs, resident in HBM (rank r holds records of seed SEED+r) ----
     seqset = _lib.SeqSet.synth(ctx, SEED + rank, a.nrec, a.nfam, a.mean_len)
     bases = seqset.total_bases
-    total_bases = shard.sum_over_ranks(bases, device)
-    order = shard.global_order(SEED, a.nrec * world)
+    total_bases = sum_over_ranks(bases, device)
+    order = shard.global_order(SEED, a.nrec)
     local_order = shard.global_order(SEED + rank, a.nrec)
+    if world > 1:  # position-interleaved global order over the rank-major rows of all ranks
+        order = shard.interleaved_order([shard.global_order(SEED + r, a.nrec) for r in range(world)], [a.nrec] * world)
 
     def barrier():
         if world > 1:
@@ -324,20 +471,24 @@ def main():
 
     def step(ss):
         t0 = time.perf_counter()
-        kf = _lib.KFreqs.count(ctx, ss, a.k)
-        t1 = time.perf_counter()
+        if world > 1 and a.multi == "sharded":
+            kf, _ = shard.count_sharded(ctx, comm, ss, a.k)
+            t1 = time.perf_counter()
+            idx, delta, stats = shard.select_sharded(ctx, comm, kf, order, _lib.MODE_NMOST, a.n)
+            kf.close()
+        else:
+            kf = _lib.KFreqs.count(ctx, ss, a.k)
+            t1 = time.perf_counter()
+            if world > 1:
+                idx, delta, stats = shard.chunked_select(ctx, comm, kf, local_order, _lib.MODE_NMOST, a.n, a.n)
+                idx = np.array([r * a.nrec + i for r, i in idx], dtype=np.uint32)
+            else:
+                idx, delta, stats = kf.select(order, _lib.MODE_NMOST, a.n)
+        t3 = time.perf_counter()
         phase["count_ms"] = ctx.phase_ms(_lib.PHASE_COUNT_KERNEL)
         phase["freq_entropy_ms"] = ctx.phase_ms(_lib.PHASE_FREQ_ENTROPY)
-        if world > 1 and a.multi == "chunked":
-            t2 = t1
-            idx, delta, stats = shard.chunked_select(ctx, kf, local_order, _lib.MODE_NMOST, a.n, a.n, device)
-        else:
-            allf = shard.all_gather_kfreqs(ctx, kf, device) if world > 1 else kf
-            t2 = time.perf_counter()
-            idx, delta, stats = allf.select(order, _lib.MODE_NMOST, a.n)
-        t3 = time.perf_counter()
         phase["select_ms"] = ctx.phase_ms(_lib.PHASE_SELECT)
-        phase["host_wall_ms"] = {"count_call": (t1 - t0) * 1e3, "gather": (t2 - t1) * 1e3, "select_call": (t3 - t2) * 1e3}
+        phase["host_wall_ms"] = {"count_call": (t1 - t0) * 1e3, "select_call": (t3 - t1) * 1e3}
         return idx, delta, stats
 
     def timed(fn, steps):
@@ -349,7 +500,7 @@ def main():
             out = fn()
         e1.record(stream)
         barrier()
-        return shard.max_over_ranks(e0.elapsed_time(e1), device) / steps, out
+        return max_over_ranks(e0.elapsed_time(e1), device) / steps, out
 
     for _ in range(a.warmup):
         step(seqset)
@@ -416,7 +567,7 @@ def main():
             pinned = torch.empty(int(bases) + 64, dtype=torch.uint8, pin_memory=True)
         except Exception as exc:
             why = f"{type(exc).__name__}: {exc}"
-        all_ok = shard.sum_over_ranks(0.0 if why is None else 1.0, device) == 0.0
+        all_ok = sum_over_ranks(0.0 if why is None else 1.0, device) == 0.0
         if not all_ok:
             e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                    "error": why or "another rank could not pin its input"}
@@ -435,7 +586,7 @@ def main():
                 return r
 
             step_e2e()
-            ms_e2e, (idx2, _d2, _s2) = timed(step_e2e, max(1, min(a.steps, 2)))
+            ms_e2e, (idx2, _d2, _s2) = timed(step_e2e, a.steps)
             assert idx2.tolist() == idx.tolist(), "e2e selection differs from the resident-input run"
             d2h = idx.nbytes + delta.nbytes + 5 * 8 + 4
             e2e = {"value": total_bases / (ms_e2e * 1e-3) / 1e9, "unit": UNIT,
@@ -453,46 +604,16 @@ def main():
         base = cpu_baseline(a, seqset, a.cpu_seconds)
         base = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
-    # BASELINE.json's third metric, "ctree distance pairs/s" (configs[3] and configs[4]); outside the timed step
+    # BASELINE.json's other configs as side metrics, outside the timed step, at every N (strong scaling: the SAME
+    # record sets split over the ranks): configs[2] `max` sweeps at k=8 (candidate-sharded), configs[3] mash k=16
+    # s=3000 on 1,000 genomes (pairs dealt over the GPUs), configs[4] Euclidean k=8 on 10.5k genomes (tiles dealt
+    # over the GPUs), the north star's k=12 counting, each with the roofline that bounds it
     ctree = None
-    if rank == 0 and world == 1 and not a.no_ctree:
+    if not a.no_ctree:
         try:
             del seqset
             seqset = None
-            ss = _lib.SeqSet.synth(ctx, SEED, 1000, a.nfam, a.mean_len)
-            sk = _lib.Sketches.sketch(ctx, ss, 16, 3000, 4, True)
-            sk = _lib.Sketches.sketch(ctx, ss, 16, 3000, 4, True)
-            sk_ms = ctx.phase_ms(_lib.PHASE_SKETCH)
-            t0 = time.perf_counter()
-            sk.distances(16, 3000)
-            mash_wall = time.perf_counter() - t0
-            mash_ms = ctx.phase_ms(_lib.PHASE_MASH_PAIRS)
-            mash_bases = ss.total_bases
-            del sk, ss
-            ss = _lib.SeqSet.synth(ctx, SEED, a.nrec, a.nfam, 400_000)  # rows depend on nrec x 4^8 only
-            kf8 = _lib.KFreqs.count(ctx, ss, 8)
-            t0 = time.perf_counter()
-            kf8.euclidean()
-            eu_wall = time.perf_counter() - t0
-            eu_ms = ctx.phase_ms(_lib.PHASE_EUCLID)
-            # ctree tail: the matrix stays on the device and the average-linkage tree is built there
-            import torch
-            dmat = torch.empty((a.nrec, a.nrec), dtype=torch.float64, device=torch.device("cuda", local))
-            kf8.euclidean_into(dmat.data_ptr())
-            t0 = time.perf_counter()
-            children, _, _ = _lib.linkage_average(ctx, n=a.nrec, device_ptr=dmat.data_ptr())
-            link_wall = time.perf_counter() - t0
-            link_ms = ctx.phase_ms(_lib.PHASE_CLUSTER)
-            del kf8, ss, dmat
-            npm, npe = 1000 * 999 // 2, a.nrec * (a.nrec - 1) // 2
-            ctree = {"mash_k16_s3000_1k_genomes": {"sketch_ms": sk_ms, "sketch_gbp_per_s": mash_bases / sk_ms / 1e6,
-                                                   "pairs": npm, "pairs_kernel_ms": mash_ms,
-                                                   "pairs_per_s": npm / mash_ms * 1e3, "pairs_per_s_with_d2h": npm / mash_wall},
-                     f"euclid_k8_{a.nrec}_genomes": {"pairs": npe, "kernel_ms": eu_ms, "pairs_per_s": npe / eu_ms * 1e3,
-                                                     "pairs_per_s_with_d2h": npe / eu_wall,
-                                                     "fp64_tflops": 2.0 * 65536 * npe / eu_ms / 1e9},
-                     f"average_linkage_{a.nrec}_genomes": {"device_ms": link_ms, "wall_ms": link_wall * 1e3,
-                                                           "merges": int(children.shape[0])}}
+            ctree = side_metrics(a, ctx, comm, rank, world, device, barrier, peak)
         except Exception as exc:
             ctree = {"error": f"{type(exc).__name__}: {exc}"}
 

@@ -35,8 +35,14 @@ SIGNATURES = {
     "dvs_ctx_last_upload_wire_bytes": (_u64, [_vp]),
     "dvs_ctx_enable_timing": (_i32, [_vp, _i32]),
     "dvs_ctx_phase_ms": (_f64, [_vp, _i32]),
+    "dvs_device_malloc": (_i32, [_vp, _u64, C.POINTER(_vp)]),
+    "dvs_device_free": (None, [_vp, _vp]),
+    "dvs_device_memcpy": (_i32, [_vp, _vp, _vp, _u64]),
+    "dvs_host_malloc_pinned": (_i32, [_u64, C.POINTER(_vp)]),
+    "dvs_host_free_pinned": (None, [_vp]),
     "dvs_seqset_upload": (_i32, [_vp, _vp, _vp, _u32, C.POINTER(_vp)]),
     "dvs_seqset_synth": (_i32, [_vp, _u64, _u32, _u32, _u64, C.POINTER(_vp)]),
+    "dvs_seqset_synth_range": (_i32, [_vp, _u64, _u32, _u32, _u32, _u64, C.POINTER(_vp)]),
     "dvs_synth_host": (_i32, [_u64, _u32, _u32, _u64, _u32, _u32, _vp, _vp]),
     "dvs_synth_lengths": (_i32, [_u64, _u32, _u64, _vp]),
     "dvs_seqset_nrec": (_u32, [_vp]),
@@ -73,6 +79,19 @@ SIGNATURES = {
     "dvs_mash_distances": (_i32, [_vp, _vp, _i32, _u64, _u32, _u32, _vp, _vp, _vp]),
     "dvs_mash_sketch_host": (_i32, [_vp, _vp, _u64, _i32, _u64, _i32, _i32, _vp, _u64, C.POINTER(_u64)]),
     "dvs_euclid_distances": (_i32, [_vp, _vp, _u32, _u32, _vp]),
+    "dvs_comm_create": (_i32, [_vp, _i32, _i32, _u64, C.POINTER(_vp), _vp]),
+    "dvs_comm_connect": (_i32, [_vp, _vp, _vp]),
+    "dvs_comm_rank": (_i32, [_vp]),
+    "dvs_comm_world": (_i32, [_vp]),
+    "dvs_comm_barrier": (_i32, [_vp, _vp]),
+    "dvs_comm_allgatherv": (_i32, [_vp, _vp, _vp, _vp, _vp]),
+    "dvs_comm_destroy": (None, [_vp]),
+    "dvs_count_kmers_sharded": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, C.POINTER(_vp)]),
+    "dvs_kfreqs_allgather": (_i32, [_vp, _vp, _vp, _vp, C.POINTER(_vp)]),
+    "dvs_sketches_allgather": (_i32, [_vp, _vp, _vp, _vp, _u32, C.POINTER(_vp)]),
+    "dvs_mash_distances_sharded": (_i32, [_vp, _vp, _vp, _i32, _u64, _vp]),
+    "dvs_euclid_distances_sharded": (_i32, [_vp, _vp, _vp, _vp]),
+    "dvs_select_sharded": (_i32, [_vp, _vp, _vp, _vp, _u32, _i32, _u32, _u32, _vp, _vp, _vp, C.POINTER(_u32)]),
     "dvs_debug_pack_host": (_i32, [_vp, _u64, _vp, _vp, _vp, _u32, C.POINTER(_u32)]),
     "dvs_debug_log2": (_i32, [_vp, _vp, _vp, _u64]),
     "dvs_debug_fast_terms": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _u64]),
@@ -183,6 +202,65 @@ class Context:
         return int(self._lib.dvs_ctx_launch_count(self.handle))
 
 
+class DeviceBuffer:
+    """plain device memory owned by the library (dvs_device_malloc); `.ptr` is the raw device pointer"""
+
+    def __init__(self, ctx: Context, nbytes: int):
+        self.ctx, self.nbytes = ctx, int(nbytes)
+        p = _vp()
+        check(ctx._lib.dvs_device_malloc(ctx.handle, self.nbytes, C.byref(p)))
+        self.ptr = int(p.value)
+
+    def to_host(self, dtype, shape) -> np.ndarray:
+        out = np.empty(shape, dtype=dtype)
+        assert out.nbytes <= self.nbytes
+        check(self.ctx._lib.dvs_device_memcpy(self.ctx.handle, ptr(out), _vp(self.ptr), out.nbytes))
+        return out
+
+    def from_host(self, a: np.ndarray) -> None:
+        a = np.ascontiguousarray(a)
+        assert a.nbytes <= self.nbytes
+        check(self.ctx._lib.dvs_device_memcpy(self.ctx.handle, _vp(self.ptr), ptr(a), a.nbytes))
+
+    def close(self) -> None:
+        if getattr(self, "ptr", 0) and not _shutdown and getattr(self.ctx, "handle", None):
+            self.ctx._lib.dvs_device_free(self.ctx.handle, _vp(self.ptr))
+        self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _Pinned:
+    def __init__(self, lib, p):
+        self.lib, self.p = lib, p
+
+    def __del__(self):
+        try:
+            if self.p and not _shutdown:
+                self.lib.dvs_host_free_pinned(self.p)
+        except Exception:
+            pass
+
+
+def pinned_array(nbytes: int) -> np.ndarray:
+    """uint8 numpy array over page-locked host memory (dvs_host_malloc_pinned); freed with the array"""
+    lib = load()
+    p = _vp()
+    check(lib.dvs_host_malloc_pinned(int(max(nbytes, 1)), C.byref(p)))
+    owner = _Pinned(lib, p)
+    buf = (C.c_uint8 * int(max(nbytes, 1))).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=np.uint8)
+    _PINNED_OWNERS[id(buf)] = owner  # the ctypes buffer (kept alive by arr.base) keeps the allocation alive
+    import weakref
+    weakref.finalize(buf, _PINNED_OWNERS.pop, id(buf), None)
+    return arr
+
+
+_PINNED_OWNERS: dict = {}
 _default_ctx: dict[int, Context] = {}
 
 
@@ -252,9 +330,10 @@ class SeqSet(_Handle):
         return cls.upload(ctx, *concat(seqs))
 
     @classmethod
-    def synth(cls, ctx: Context, seed: int, nrec: int, nfam: int, mean_len: int) -> "SeqSet":
+    def synth(cls, ctx: Context, seed: int, nrec: int, nfam: int, mean_len: int, first: int = 0) -> "SeqSet":
+        """`nrec` synthetic records starting at record `first` of the generator keyed by `seed`"""
         h = _vp()
-        check(ctx._lib.dvs_seqset_synth(ctx.handle, seed, nrec, nfam, mean_len, C.byref(h)))
+        check(ctx._lib.dvs_seqset_synth_range(ctx.handle, seed, first, nrec, nfam, mean_len, C.byref(h)))
         return cls(ctx, h)
 
     @classmethod
@@ -320,6 +399,41 @@ class KFreqs(_Handle):
         h = _vp()
         check(ctx._lib.dvs_count_kmers(ctx.handle, seqset.handle, int(k), int(num_states), C.byref(h)))
         return cls(ctx, h)
+
+    @classmethod
+    def count_sharded(cls, ctx: Context, comm: "Comm", seqset: SeqSet, k: int, nrec_per_rank, num_states: int = 4) -> "KFreqs":
+        """count this rank's records; the result holds the rows of ALL ranks (rank-major) on every rank"""
+        npr = np.ascontiguousarray(nrec_per_rank, dtype=np.uint32)
+        h = _vp()
+        check(ctx._lib.dvs_count_kmers_sharded(ctx.handle, comm.handle, seqset.handle, int(k), int(num_states), ptr(npr),
+                                               C.byref(h)))
+        out = cls(ctx, h)
+        out._comm = comm  # the rows live in the communicator's window: keep it alive
+        return out
+
+    def allgather(self, comm: "Comm", nrec_per_rank) -> "KFreqs":
+        npr = np.ascontiguousarray(nrec_per_rank, dtype=np.uint32)
+        h = _vp()
+        check(self.ctx._lib.dvs_kfreqs_allgather(self.ctx.handle, comm.handle, self.handle, ptr(npr), C.byref(h)))
+        out = KFreqs(self.ctx, h)
+        out._comm = comm
+        return out
+
+    def select_sharded(self, comm: "Comm", order, mode: int, min_size: int, max_size: int = 0):
+        """single-pass selection over the rows of all ranks, candidate-sharded over the GPUs (dvs_select_sharded)"""
+        order = np.ascontiguousarray(order, dtype=np.uint32)
+        cap = max(int(min_size), int(max_size), 1) + 1
+        if int(mode) != MODE_NMOST and int(max_size) < int(min_size):
+            cap = order.size + 1
+        idx = np.zeros(cap, dtype=np.uint32)
+        delta = np.zeros(cap, dtype=np.float64)
+        stats = np.zeros(5, dtype=np.float64)
+        size = _u32(0)
+        check(self.ctx._lib.dvs_select_sharded(self.ctx.handle, comm.handle, self.handle, ptr(order) if order.size else None,
+                                               order.size, int(mode), int(min_size), int(max_size), ptr(idx), ptr(delta),
+                                               ptr(stats), C.byref(size)))
+        n = size.value
+        return idx[:n].copy(), delta[:n].copy(), stats
 
     @classmethod
     def from_rows(cls, ctx: Context, rows: np.ndarray, entropies: np.ndarray | None = None) -> "KFreqs":
@@ -403,10 +517,56 @@ class KFreqs(_Handle):
         check(self.ctx._lib.dvs_euclid_distances(self.ctx.handle, self.handle, row_begin, row_end, ptr(out)))
         return out
 
+    def euclidean_sharded(self, comm: "Comm", device_ptr: int | None = None):
+        """whole matrix over the rows of all ranks, tiles dealt over the GPUs (dvs_euclid_distances_sharded)"""
+        out = None if device_ptr is not None else np.zeros((self.nrec, self.nrec), dtype=np.float64)
+        check(self.ctx._lib.dvs_euclid_distances_sharded(self.ctx.handle, comm.handle, self.handle,
+                                                         _vp(device_ptr) if device_ptr is not None else ptr(out)))
+        return out
+
     def euclidean_into(self, device_ptr: int, row_begin: int = 0, row_end: int | None = None) -> None:
         """same matrix written to device memory at `device_ptr` ((row_end-row_begin) x nrec f64)"""
         row_end = self.nrec if row_end is None else row_end
         check(self.ctx._lib.dvs_euclid_distances(self.ctx.handle, self.handle, row_begin, row_end, _vp(device_ptr)))
+
+
+class Comm:
+    """Peer windows over NVLink (dvs_comm): one per rank; `blob` is what the ranks exchange before connect()."""
+
+    def __init__(self, ctx: Context, rank: int, world: int, window_bytes: int):
+        self.ctx, self.rank, self.world = ctx, int(rank), int(world)
+        h = _vp()
+        buf = C.create_string_buffer(128)
+        check(ctx._lib.dvs_comm_create(ctx.handle, self.rank, self.world, int(window_bytes), C.byref(h), buf))
+        self.handle = h
+        self.blob = bytes(buf.raw)
+
+    def connect(self, blobs) -> "Comm":
+        blobs = list(blobs)
+        assert len(blobs) == self.world and all(len(b) == 128 for b in blobs)
+        check(self.ctx._lib.dvs_comm_connect(self.ctx.handle, self.handle, C.create_string_buffer(b"".join(blobs), 128 * self.world)))
+        return self
+
+    def barrier(self) -> None:
+        check(self.ctx._lib.dvs_comm_barrier(self.ctx.handle, self.handle))
+
+    def allgatherv(self, src_ptr: int, nbytes, dst_ptr: int) -> None:
+        """device buffers: this rank's nbytes[rank] bytes at src_ptr -> all pieces, in rank order, at dst_ptr"""
+        nb = np.ascontiguousarray(nbytes, dtype=np.uint64)
+        assert nb.size == self.world
+        check(self.ctx._lib.dvs_comm_allgatherv(self.ctx.handle, self.handle, _vp(src_ptr) if src_ptr else None, ptr(nb),
+                                                _vp(dst_ptr)))
+
+    def close(self) -> None:
+        if getattr(self, "handle", None) and not _shutdown and getattr(self.ctx, "handle", None):
+            self.ctx._lib.dvs_comm_destroy(self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Summed(_Handle):
@@ -491,6 +651,20 @@ class Sketches(_Handle):
         check(self.ctx._lib.dvs_mash_distances(self.ctx.handle, self.handle, int(k), int(sketch_size), row_begin,
                                                row_end, ptr(dist), ptr(inter), ptr(uni)))
         return (dist, inter, uni) if want_counts else dist
+
+    def allgather(self, comm: "Comm", nrec_per_rank, stride_all: int) -> "Sketches":
+        npr = np.ascontiguousarray(nrec_per_rank, dtype=np.uint32)
+        h = _vp()
+        check(self.ctx._lib.dvs_sketches_allgather(self.ctx.handle, comm.handle, self.handle, ptr(npr), int(stride_all),
+                                                   C.byref(h)))
+        return Sketches(self.ctx, h)
+
+    def distances_sharded(self, comm: "Comm", k: int, sketch_size: int, device_ptr: int | None = None):
+        """whole matrix, pairs dealt over the GPUs (dvs_mash_distances_sharded)"""
+        out = None if device_ptr is not None else np.zeros((self.nrec, self.nrec), dtype=np.float64)
+        check(self.ctx._lib.dvs_mash_distances_sharded(self.ctx.handle, comm.handle, self.handle, int(k), int(sketch_size),
+                                                       _vp(device_ptr) if device_ptr is not None else ptr(out)))
+        return out
 
     def distances_into(self, device_ptr: int, k: int, sketch_size: int) -> None:
         """the full nrec x nrec f64 matrix written to device memory at `device_ptr`"""

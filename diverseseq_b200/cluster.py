@@ -101,20 +101,19 @@ class dvs_ctree:
         return self.main(seq_names, seqs)
 
     def main(self, seq_names: Sequence[str], seqs) -> ClusterTree:
-        import torch
-
         ctx = self._ctx or _lib.default_context()
         arrays = [s.get_seq() if hasattr(s, "get_seq") else s for s in seqs]
         ss = _lib.SeqSet.from_seqs(ctx, arrays)
         n = ss.nrec
         if n < 2:
             return ClusterTree(seq_names, np.zeros((0, 2), np.int32), np.zeros(0), np.zeros(0, np.uint32))
-        dev = torch.device("cuda", ctx.device)
-        dmat = torch.empty((n, n), dtype=torch.float64, device=dev)  # plumbing: device memory for the matrix
+        dmat = _lib.DeviceBuffer(ctx, n * n * 8)  # the matrix never leaves the device
         if self._distance_mode == "mash":
             sk = _lib.Sketches.sketch(ctx, ss, self._k, int(self._sketch_size), self._num_states, self._mash_canonical)
-            sk.distances_into(dmat.data_ptr(), self._k, int(self._sketch_size))
+            sk.distances_into(dmat.ptr, self._k, int(self._sketch_size))
         else:
             kf = _lib.KFreqs.count(ctx, ss, self._k, self._num_states)
-            kf.euclidean_into(dmat.data_ptr())
-        return make_cluster_tree(seq_names, (dmat.data_ptr(), n), ctx=ctx)
+            kf.euclidean_into(dmat.ptr)
+        tree = make_cluster_tree(seq_names, (dmat.ptr, n), ctx=ctx)
+        dmat.close()
+        return tree

@@ -57,16 +57,24 @@ struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
     cudaStream_t stream = nullptr;  // stream the block was allocated on (nullptr: plain cudaMalloc)
+    bool borrowed = false;          // points into memory owned by somebody else (a peer window)
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
     void release() {
-        if (p) {
+        if (p && !borrowed) {
             if (stream) cudaFreeAsync(p, stream); else cudaFree(p);
         }
         p = nullptr;
         n = 0;
+        borrowed = false;
+    }
+    void borrow(T* ptr, size_t count) {
+        release();
+        p = ptr;
+        n = count;
+        borrowed = true;
     }
     int alloc(size_t count) {
         release();
@@ -121,7 +129,7 @@ struct PhaseTimer {
     dvs_ctx* ctx;
     int phase;
     PhaseTimer(dvs_ctx* c, int ph) : ctx(c), phase(ph) {
-        if (ctx->timing) {
+        if (ctx && ctx->timing) {
             cudaEventRecord(ctx->ev_start[phase], ctx->stream);
             ctx->ev_valid[phase] = false;
         }
@@ -153,6 +161,7 @@ struct dvs_seqset {
     mutable dvs::DevBuf<uint8_t> work_cache;
     mutable uint64_t work_chunk = 0;
     mutable uint32_t work_nparts = 0, work_items = 0;
+    mutable std::vector<uint32_t> work_item_begin;  // nrec+1: first work item of every record (items are record-major)
     const uint8_t* data() const { return raw.p + kSeqFrontPad; }
     uint8_t* data() { return raw.p + kSeqFrontPad; }
 };
@@ -170,6 +179,9 @@ struct dvs_kfreqs {
     dvs::DevBuf<uint8_t> err;       // [nrec]  1 = reference entropy() would panic (sum check)
     dvs::DevBuf<double> err_total;  // [nrec]  the offending total
     bool has_counts = false;
+    // rows gathered from all ranks live in the symmetric heap of a peer window (comm.cuh)
+    struct dvs_comm* heap = nullptr;
+    uint64_t heap_off = 0;
 };
 
 struct dvs_sketches {

@@ -117,6 +117,40 @@ double dvs_ctx_phase_ms(dvs_ctx* ctx, int phase) {
 }
 
 void* dvs_ctx_stream(dvs_ctx* ctx) { return (void*)ctx->stream; }
+
+// plain device / pinned host buffers for callers that have no other CUDA binding (the Python host code keeps
+// distance matrices on the device and stages sequences in pinned memory without importing torch)
+int dvs_device_malloc(dvs_ctx* ctx, uint64_t bytes, void** out) {
+    if (!ctx || !out) {
+        set_error("dvs_device_malloc: NULL argument");
+        return DVS_ERR_ARG;
+    }
+    DVS_CUDA_TRY(dvs::enter(ctx));
+    DVS_CUDA_TRY(cudaMalloc(out, bytes ? bytes : 1));
+    return DVS_OK;
+}
+void dvs_device_free(dvs_ctx* ctx, void* p) {
+    if (!p) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    cudaFree(p);
+}
+int dvs_device_memcpy(dvs_ctx* ctx, void* dst, const void* src, uint64_t bytes) {
+    DVS_CUDA_TRY(dvs::enter(ctx));
+    if (bytes) DVS_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
+    DVS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return DVS_OK;
+}
+int dvs_host_malloc_pinned(uint64_t bytes, void** out) {
+    if (!out) {
+        set_error("dvs_host_malloc_pinned: NULL argument");
+        return DVS_ERR_ARG;
+    }
+    DVS_CUDA_TRY(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return DVS_OK;
+}
+void dvs_host_free_pinned(void* p) {
+    if (p) cudaFreeHost(p);
+}
 uint64_t dvs_ctx_launch_count(dvs_ctx* ctx) { return ctx->launches; }
 
 // ---- sequence sets -----------------------------------------------------------------------

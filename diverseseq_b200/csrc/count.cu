@@ -19,6 +19,9 @@
 
 #include <algorithm>
 
+#include <functional>
+
+#include "comm.cuh"
 #include "common.cuh"
 #include "entropy.cuh"
 
@@ -653,62 +656,34 @@ using namespace dvs;
 
 extern "C" {
 
-int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dvs_kfreqs** out) {
-    if (!ctx || !s || !out) {
-        set_error("dvs_count_kmers: NULL argument");
-        return DVS_ERR_ARG;
-    }
-    if (k == 0) {
-        set_error("k cannot be 0");  // record.rs:126
-        return DVS_ERR_VALUE;
-    }
-    if (k < 0 || k > 16 || num_states < 1 || num_states > 255) {
-        set_error("dvs_count_kmers: unsupported k=%d / num_states=%d (need 1<=k<=16, 1<=num_states<=255)", k,
-                  num_states);
-        return DVS_ERR_ARG;
-    }
-    uint64_t dim = 0;
-    if (!pow_dim(num_states, k, &dim)) {
-        set_error("dvs_count_kmers: num_states^k = %d^%d does not fit a dense u32-indexed table", num_states, k);
-        return DVS_ERR_ARG;
-    }
-    // per-bin counters are u32 (the reference counts in usize): a bin cannot exceed the number of k-mers
-    // of its record, so records below 2^32 bases can never wrap; longer ones are refused, not miscounted
-    for (uint32_t r = 0; r < s->nrec; ++r)
-        if (s->h_offsets[r + 1] - s->h_offsets[r] >= (1ULL << 32)) {
-            set_error("dvs_count_kmers: record %u has %llu bases; records of 2^32 bases or more are not supported "
-                      "(32-bit bin counters)", r, (unsigned long long)(s->h_offsets[r + 1] - s->h_offsets[r]));
-            return DVS_ERR_ARG;
-        }
-    DVS_CUDA_TRY(dvs::enter(ctx));
-    size_t free_b = 0, total_b = 0;
-    const double need = (double)s->nrec * (double)dim * 12.0;
-    // cudaMemGetInfo costs milliseconds and pooled blocks count as "used": only ask when it can matter
-    if (need > 8e9) DVS_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-    if (need > 8e9 && need > 0.9 * (double)free_b) {
-        set_error("dvs_count_kmers: dense rows need %.1f GB (nrec=%u, dim=%llu) but only %.1f GB are free", need / 1e9,
-                  s->nrec, (unsigned long long)dim, free_b / 1e9);
-        return DVS_ERR_ARG;
-    }
-    dvs_kfreqs* f = nullptr;
-    DVS_TRY(kfreqs_alloc(ctx, s->nrec, dim, true, &f));
-    f->k = k;
-    f->num_states = num_states;
+// Where the rows of the local records go, and what happens after each chunk of records.  Plain counting:
+// the kfreqs' own arrays, one chunk.  Sharded counting (dvs_count_kmers_sharded): the arrays of the
+// all-ranks kfreqs inside the peer window at this rank's row offset, several chunks, and after every chunk
+// its rows are pushed to the peers on the side stream while the next chunk is being counted.
+struct CountDest {
+    double* freqs;
+    uint64_t* totals;
+    double* entropy;
+    uint8_t* valid;
+    uint8_t* err;
+    double* err_total;
+    uint32_t chunks;                                   // >= 1
+    std::function<int(uint32_t, uint32_t)> after_chunk;  // (first record, end record) of the chunk just enqueued
+};
+
+static int count_core(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, uint32_t* d_counts, uint64_t dim,
+                      const CountDest& dst) {
     cudaStream_t st = ctx->stream;
-    auto fail = [&](int rc) {
-        dvs_kfreqs_free(f);
-        return rc;
-    };
 #define TRY_F(expr)                                                          \
     do {                                                                     \
         cudaError_t _e = (expr);                                             \
         if (_e != cudaSuccess) {                                             \
             set_error("%s failed: %s", #expr, cudaGetErrorString(_e));       \
-            return fail(DVS_ERR_CUDA);                                       \
+            return DVS_ERR_CUDA;                                             \
         }                                                                    \
     } while (0)
 
-    TRY_F(cudaMemsetAsync(f->counts.p, 0, (size_t)s->nrec * dim * sizeof(uint32_t), st));
+    TRY_F(cudaMemsetAsync(d_counts, 0, (size_t)s->nrec * dim * sizeof(uint32_t), st));
 
     // ---- histogram placement ----
     const bool ns4 = (num_states == 4);
@@ -716,12 +691,10 @@ int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dv
     uint32_t nparts = 1, part_bins = (uint32_t)std::min<uint64_t>(dim, 1u << 31);
     int mode = MODE_SMEM;
     size_t hist_bytes = (size_t)dim * 4;
-    // DVS_COUNT_S3=1 selects the (k+2)-mer / 16-bit kernel for k = 4..6.  Off by default: it cuts the shared
-    // atomic wavefronts by 27 % but needs ~150 instructions per 512-byte step (runtime shifts, half select,
-    // address forming) and ends up issue-bound: 13.7 ms vs 11.2 ms for the (k+1)-mer kernel on the
-    // benchmark set (profiles/r1_ncu_k_count_s3.txt).
+    // (k+2)-mers at every third position in 16-bit packed counters (k_count_s3) for k = 4..6: a third fewer
+    // shared atomics than the (k+1)-mer kernel.  DVS_COUNT_S3=0 selects the (k+1)-mer kernel instead.
     const char* s3_env = getenv("DVS_COUNT_S3");
-    const bool want_s3 = s3_env && s3_env[0] == '1';
+    const bool want_s3 = !(s3_env && s3_env[0] == '0');
     if (ns4 && want_s3 && k >= 4 && dim * 36 + 2048 <= ctx->smem_optin && dim * 36 <= 160 * 1024) {
         // (k+2)-mers at every third position, 16-bit packed counters + side table: k = 4..6 -> at most 144 KB.
         // Smaller k would overflow the 16-bit halves routinely (4^(k+2) bins share the item's increments).
@@ -762,7 +735,7 @@ int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dv
         const uint64_t flush_bins =
             (mode == MODE_GLOBAL) ? 0 : (mode == MODE_SUPER ? dim : (mode == MODE_SUPER3 ? dim * 16 : part_bins));
         const uint64_t max_chunk = flush_bins >= 32768 ? (8u << 20) : (flush_bins >= 16384 ? (2u << 20) : (1u << 20));
-        uint64_t want_items = (uint64_t)grid * 8;
+        uint64_t want_items = (uint64_t)grid * 8 * dst.chunks;
         uint64_t c = (s->total + want_items - 1) / std::max<uint64_t>(want_items, 1);
         c = std::max<uint64_t>(64 << 10, std::min<uint64_t>(c, max_chunk));
         chunk = (c + 8191) / 8192 * 8192;
@@ -773,110 +746,366 @@ int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dv
     }
     if (s->work_chunk != chunk || s->work_nparts != nparts || !s->work_cache.p) {
         std::vector<CountWork> work;
+        s->work_item_begin.assign(s->nrec + 1, 0);
         for (uint32_t r = 0; r < s->nrec; ++r) {
+            s->work_item_begin[r] = (uint32_t)work.size();
             uint64_t b = s->h_offsets[r], e = s->h_offsets[r + 1];
             if (e <= b) continue;
             uint64_t a0 = b & ~15ULL, a1 = (e + 15) & ~15ULL;
             for (uint64_t a = a0; a < a1; a += chunk)
                 for (uint32_t p = 0; p < nparts; ++p) work.push_back({a, std::min(a + chunk, a1), r, p});
         }
-        if (work.size() > 0xFFFFFFFFull) {
+        if (work.size() > 0xFFFFFFF0ull) {
             dvs::set_error("too many counting work items");
-            return fail(DVS_ERR_ARG);
+            return DVS_ERR_ARG;
         }
+        s->work_item_begin[s->nrec] = (uint32_t)work.size();
         s->work_chunk = 0;
-        if (s->work_cache.alloc(work.size() * sizeof(CountWork)) != DVS_OK) return fail(DVS_ERR_CUDA);
+        if (s->work_cache.alloc(work.size() * sizeof(CountWork)) != DVS_OK) return DVS_ERR_CUDA;
         // pageable source: the copy is staged before the call returns, so `work` may die here
         TRY_F(cudaMemcpyAsync(s->work_cache.p, work.data(), work.size() * sizeof(CountWork), cudaMemcpyHostToDevice, st));
         s->work_chunk = chunk;
         s->work_nparts = nparts;
         s->work_items = (uint32_t)work.size();
     }
-    const CountWork* d_work = reinterpret_cast<const CountWork*>(s->work_cache.p);
-    const uint32_t n_work = s->work_items;
+    const CountWork* d_work_all = reinterpret_cast<const CountWork*>(s->work_cache.p);
+    const uint32_t nchunks = std::max<uint32_t>(1, std::min<uint32_t>(dst.chunks, std::max<uint32_t>(s->nrec, 1)));
     DevBuf<uint32_t> d_next, d_rc;
     DevBuf<CountWork> d_retry;
-    if (n_work) {
-        if (d_next.alloc(1) != DVS_OK) return fail(DVS_ERR_CUDA);
-        TRY_F(cudaMemsetAsync(d_next.p, 0, sizeof(uint32_t), st));
-        const uint32_t g = (uint32_t)std::min<size_t>(grid, n_work);
-        auto set_smem = [&](auto kern) -> cudaError_t {
-            return hist_bytes > 48 * 1024
-                       ? cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes)
-                       : cudaSuccess;
-        };
-        auto launch4 = [&](auto kern) -> cudaError_t {
-            cudaError_t e = set_smem(kern);
-            if (e != cudaSuccess) return e;
-            kern<<<g, threads4, hist_bytes, st>>>(s->data(), s->offsets.p, d_work, n_work,
-                                                  d_next.p, k, dim, part_bins, f->counts.p, nullptr);
-            ctx->launches++;
-            return cudaGetLastError();
-        };
-        auto launch_generic = [&](auto kern) -> cudaError_t {
-            cudaError_t e = set_smem(kern);
-            if (e != cudaSuccess) return e;
-            kern<<<g, kCountThreads, hist_bytes, st>>>(s->data(), s->offsets.p, d_work, n_work,
-                                                       d_next.p, k, (uint32_t)num_states, dim, part_bins,
-                                                       f->counts.p);
-            ctx->launches++;
-            return cudaGetLastError();
-        };
-        cudaError_t e;
-        PhaseTimer pt(ctx, DVS_PHASE_COUNT_KERNEL);
-        if (!ns4)
-            e = smem ? launch_generic(k_count_generic<true>) : launch_generic(k_count_generic<false>);
-        else if (mode == MODE_SUPER3) {
-            // main pass + retry pass (items whose 16-bit halves overflowed, recounted with 32-bit counters)
-            e = cudaSuccess;
-            if (d_retry.alloc(n_work) != DVS_OK || d_rc.alloc(2) != DVS_OK) return fail(DVS_ERR_CUDA);
-            TRY_F(cudaMemsetAsync(d_rc.p, 0, 2 * sizeof(uint32_t), st));
-            // the 8-mer table spreads over 32,768 words: bank scrambling costs two instructions per atomic and
-            // buys nothing here unless asked for (DVS_COUNT_SCRAMBLE=1)
-            const bool scr3 = scr_env && scr_env[0] == '1';
-            auto s3 = scr3 ? k_count_s3<true, 1024> : k_count_s3<false, 1024>;
-            auto rk = scramble ? k_count<MODE_SUPER, true, 512> : k_count<MODE_SUPER, false, 512>;
-            TRY_F(cudaFuncSetAttribute(s3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
-            const size_t retry_bytes = (size_t)dim * 20;
-            if (retry_bytes > 48 * 1024)
-                TRY_F(cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)retry_bytes));
-            s3<<<g, 1024, hist_bytes, st>>>(s->data(), s->offsets.p, d_work, n_work, d_next.p, k, dim, f->counts.p,
-                                            d_retry.p, d_rc.p);
-            ctx->launches++;
-            e = cudaGetLastError();
-            if (e == cudaSuccess) {
-                const uint32_t g2 = (uint32_t)std::min<size_t>((size_t)ctx->sm_count * 2, n_work);
-                rk<<<g2, 512, retry_bytes, st>>>(s->data(), s->offsets.p, d_retry.p, 0u, d_rc.p + 1, k, dim,
-                                                 (uint32_t)dim, f->counts.p, d_rc.p);
+    if (d_next.alloc(nchunks) != DVS_OK) return DVS_ERR_CUDA;
+    TRY_F(cudaMemsetAsync(d_next.p, 0, nchunks * sizeof(uint32_t), st));
+    if (mode == MODE_SUPER3) {
+        if (d_retry.alloc(std::max<uint32_t>(s->work_items, 1)) != DVS_OK || d_rc.alloc(2 * nchunks) != DVS_OK)
+            return DVS_ERR_CUDA;
+        TRY_F(cudaMemsetAsync(d_rc.p, 0, 2 * nchunks * sizeof(uint32_t), st));
+    }
+    // several chunks: one timer around the whole loop (it then includes the small freq/entropy launches)
+    PhaseTimer pt_all(nchunks > 1 ? ctx : nullptr, DVS_PHASE_COUNT_KERNEL);
+    struct TimingGuard {  // (the per-launch timers below stay silent while the loop timer runs)
+        dvs_ctx* c;
+        bool saved;
+        ~TimingGuard() { c->timing = saved; }
+    } timing_guard{ctx, ctx->timing};
+    if (nchunks > 1) ctx->timing = false;
+    for (uint32_t ch = 0; ch < nchunks; ++ch) {
+        const uint32_t rb = (uint32_t)((uint64_t)s->nrec * ch / nchunks), re = (uint32_t)((uint64_t)s->nrec * (ch + 1) / nchunks);
+        const uint32_t ib = s->work_item_begin[rb], ie = s->work_item_begin[re];
+        const CountWork* d_work = d_work_all + ib;
+        const uint32_t n_work = ie - ib;
+        uint32_t* d_nx = d_next.p + ch;
+        if (n_work) {
+            const uint32_t g = (uint32_t)std::min<size_t>(grid, n_work);
+            auto set_smem = [&](auto kern) -> cudaError_t {
+                return hist_bytes > 48 * 1024
+                           ? cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes)
+                           : cudaSuccess;
+            };
+            auto launch4 = [&](auto kern) -> cudaError_t {
+                cudaError_t e = set_smem(kern);
+                if (e != cudaSuccess) return e;
+                kern<<<g, threads4, hist_bytes, st>>>(s->data(), s->offsets.p, d_work, n_work, d_nx, k, dim, part_bins,
+                                                      d_counts, nullptr);
+                ctx->launches++;
+                return cudaGetLastError();
+            };
+            auto launch_generic = [&](auto kern) -> cudaError_t {
+                cudaError_t e = set_smem(kern);
+                if (e != cudaSuccess) return e;
+                kern<<<g, kCountThreads, hist_bytes, st>>>(s->data(), s->offsets.p, d_work, n_work, d_nx, k,
+                                                           (uint32_t)num_states, dim, part_bins, d_counts);
+                ctx->launches++;
+                return cudaGetLastError();
+            };
+            cudaError_t e;
+            PhaseTimer pt(ctx, DVS_PHASE_COUNT_KERNEL);
+            if (!ns4)
+                e = smem ? launch_generic(k_count_generic<true>) : launch_generic(k_count_generic<false>);
+            else if (mode == MODE_SUPER3) {
+                // main pass + retry pass (items whose 16-bit halves overflowed, recounted with 32-bit counters).
+                // The 8-mer table spreads over 32,768 words: bank scrambling costs two instructions per atomic
+                // and buys nothing here unless asked for (DVS_COUNT_SCRAMBLE=1)
+                const bool scr3 = scr_env && scr_env[0] == '1';
+                auto s3 = scr3 ? k_count_s3<true, 1024> : k_count_s3<false, 1024>;
+                auto rk = scramble ? k_count<MODE_SUPER, true, 512> : k_count<MODE_SUPER, false, 512>;
+                TRY_F(cudaFuncSetAttribute(s3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
+                const size_t retry_bytes = (size_t)dim * 20;
+                if (retry_bytes > 48 * 1024)
+                    TRY_F(cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)retry_bytes));
+                uint32_t* rc2 = d_rc.p + 2 * ch;
+                s3<<<g, 1024, hist_bytes, st>>>(s->data(), s->offsets.p, d_work, n_work, d_nx, k, dim, d_counts,
+                                                d_retry.p + ib, rc2);
                 ctx->launches++;
                 e = cudaGetLastError();
+                if (e == cudaSuccess) {
+                    const uint32_t g2 = (uint32_t)std::min<size_t>((size_t)ctx->sm_count * 2, n_work);
+                    rk<<<g2, 512, retry_bytes, st>>>(s->data(), s->offsets.p, d_retry.p + ib, 0u, rc2 + 1, k, dim,
+                                                     (uint32_t)dim, d_counts, rc2);
+                    ctx->launches++;
+                    e = cudaGetLastError();
+                }
+            } else if (mode == MODE_SUPER)
+                e = scramble ? launch4(k_count<MODE_SUPER, true, 512>) : launch4(k_count<MODE_SUPER, false, 512>);
+            else if (mode == MODE_SMEM)
+                e = scramble ? launch4(k_count<MODE_SMEM, true, 512>) : launch4(k_count<MODE_SMEM, false, 512>);
+            else if (mode == MODE_SMEM_PARTS)  // one 128 KB CTA per SM: 1024 threads keep 32 warps resident
+                e = scramble ? launch4(k_count<MODE_SMEM_PARTS, true, 1024>) : launch4(k_count<MODE_SMEM_PARTS, false, 1024>);
+            else
+                e = launch4(k_count<MODE_GLOBAL, false, 512>);
+            pt.stop();
+            if (e != cudaSuccess) {
+                set_error("k_count launch failed: %s", cudaGetErrorString(e));
+                return DVS_ERR_CUDA;
             }
-        } else if (mode == MODE_SUPER)
-            e = scramble ? launch4(k_count<MODE_SUPER, true, 512>) : launch4(k_count<MODE_SUPER, false, 512>);
-        else if (mode == MODE_SMEM)
-            e = scramble ? launch4(k_count<MODE_SMEM, true, 512>) : launch4(k_count<MODE_SMEM, false, 512>);
-        else if (mode == MODE_SMEM_PARTS)  // one 128 KB CTA per SM: 1024 threads keep 32 warps resident
-            e = scramble ? launch4(k_count<MODE_SMEM_PARTS, true, 1024>) : launch4(k_count<MODE_SMEM_PARTS, false, 1024>);
-        else
-            e = launch4(k_count<MODE_GLOBAL, false, 512>);
-        pt.stop();
-        if (e != cudaSuccess) {
-            set_error("k_count launch failed: %s", cudaGetErrorString(e));
-            return fail(DVS_ERR_CUDA);
+        }
+        if (re > rb) {
+            PhaseTimer pt(ctx, DVS_PHASE_FREQ_ENTROPY);
+            k_freq_entropy<<<re - rb, kEntThreads, kEntSmemBytes, st>>>(
+                d_counts + (size_t)rb * dim, dim, dst.freqs + (size_t)rb * dim, dst.totals + rb, dst.entropy + rb,
+                dst.valid + rb, dst.err + rb, dst.err_total + rb);
+            ctx->launches++;
+            TRY_F(cudaGetLastError());
+        }
+        if (dst.after_chunk) DVS_TRY(dst.after_chunk(rb, re));
+    }
+    ctx->timing = timing_guard.saved;
+    pt_all.stop();
+#undef TRY_F
+    return DVS_OK;
+}
+
+static int count_args_ok(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, const void* out, uint64_t* dim) {
+    if (!ctx || !s || !out) {
+        set_error("dvs_count_kmers: NULL argument");
+        return DVS_ERR_ARG;
+    }
+    if (k == 0) {
+        set_error("k cannot be 0");  // record.rs:126
+        return DVS_ERR_VALUE;
+    }
+    if (k < 0 || k > 16 || num_states < 1 || num_states > 255) {
+        set_error("dvs_count_kmers: unsupported k=%d / num_states=%d (need 1<=k<=16, 1<=num_states<=255)", k,
+                  num_states);
+        return DVS_ERR_ARG;
+    }
+    if (!pow_dim(num_states, k, dim)) {
+        set_error("dvs_count_kmers: num_states^k = %d^%d does not fit a dense u32-indexed table", num_states, k);
+        return DVS_ERR_ARG;
+    }
+    // per-bin counters are u32 (the reference counts in usize): a bin cannot exceed the number of k-mers
+    // of its record, so records below 2^32 bases can never wrap; longer ones are refused, not miscounted
+    for (uint32_t r = 0; r < s->nrec; ++r)
+        if (s->h_offsets[r + 1] - s->h_offsets[r] >= (1ULL << 32)) {
+            set_error("dvs_count_kmers: record %u has %llu bases; records of 2^32 bases or more are not supported "
+                      "(32-bit bin counters)", r, (unsigned long long)(s->h_offsets[r + 1] - s->h_offsets[r]));
+            return DVS_ERR_ARG;
+        }
+    return DVS_OK;
+}
+
+static int dense_rows_fit(double need, const char* what, uint32_t nrec, uint64_t dim) {
+    size_t free_b = 0, total_b = 0;
+    // cudaMemGetInfo costs milliseconds and pooled blocks count as "used": only ask when it can matter
+    if (need > 8e9) DVS_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    if (need > 8e9 && need > 0.9 * (double)free_b) {
+        set_error("%s: dense rows need %.1f GB (nrec=%u, dim=%llu) but only %.1f GB are free", what, need / 1e9, nrec,
+                  (unsigned long long)dim, free_b / 1e9);
+        return DVS_ERR_ARG;
+    }
+    return DVS_OK;
+}
+
+int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dvs_kfreqs** out) {
+    uint64_t dim = 0;
+    DVS_TRY(count_args_ok(ctx, s, k, num_states, out, &dim));
+    DVS_CUDA_TRY(dvs::enter(ctx));
+    DVS_TRY(dense_rows_fit((double)s->nrec * (double)dim * 12.0, "dvs_count_kmers", s->nrec, dim));
+    dvs_kfreqs* f = nullptr;
+    DVS_TRY(kfreqs_alloc(ctx, s->nrec, dim, true, &f));
+    f->k = k;
+    f->num_states = num_states;
+    CountDest dst{f->freqs.p, f->totals.p, f->entropy.p, f->valid.p, f->err.p, f->err_total.p, 1, nullptr};
+    int rc = count_core(ctx, s, k, num_states, f->counts.p, dim, dst);
+    if (rc != DVS_OK) {
+        dvs_kfreqs_free(f);
+        return rc;
+    }
+    // (no synchronisation: the work list is cached in the seqset and every scratch buffer is released in
+    // stream order, so the caller's next call can be enqueued while the counting is still running)
+    *out = f;
+    return DVS_OK;
+}
+
+// ---- rows of all ranks in one kfreqs: storage in the symmetric heap of the peer window --------------------
+struct AllRows {
+    dvs_kfreqs* f = nullptr;
+    uint64_t off_freqs = 0, off_ent = 0, off_et = 0, off_tot = 0, off_valid = 0, off_err = 0;  // inside the block
+    uint32_t row0 = 0, total = 0;
+};
+
+static int allrows_alloc(dvs_ctx* ctx, dvs_comm* c, const uint32_t* nrec_per_rank, uint64_t dim, AllRows* a) {
+    uint64_t total = 0;
+    for (int r = 0; r < c->world; ++r) {
+        if (r == c->rank) a->row0 = (uint32_t)total;
+        total += nrec_per_rank[r];
+    }
+    if (total > 0xFFFFFFF0ull) {
+        set_error("too many records in total");
+        return DVS_ERR_ARG;
+    }
+    a->total = (uint32_t)total;
+    auto up = [](uint64_t x) { return (x + 255) & ~255ull; };
+    const uint64_t n = std::max<uint64_t>(total, 1);
+    a->off_freqs = 0;
+    a->off_ent = up(n * dim * 8);
+    a->off_et = a->off_ent + up(n * 8);
+    a->off_tot = a->off_et + up(n * 8);
+    a->off_valid = a->off_tot + up(n * 8);
+    a->off_err = a->off_valid + up(n);
+    const uint64_t bytes = a->off_err + up(n);
+    uint64_t hoff = 0;
+    DVS_TRY(comm_heap_alloc(c, bytes, &hoff));
+    auto* f = new dvs_kfreqs();
+    f->device = ctx->device;
+    f->nrec = a->total;
+    f->dim = dim;
+    f->has_counts = false;
+    f->heap = c;
+    f->heap_off = hoff;
+    uint8_t* base = c->window + hoff;
+    f->freqs.borrow(reinterpret_cast<double*>(base + a->off_freqs), n * dim);
+    f->entropy.borrow(reinterpret_cast<double*>(base + a->off_ent), n);
+    f->err_total.borrow(reinterpret_cast<double*>(base + a->off_et), n);
+    f->totals.borrow(reinterpret_cast<uint64_t*>(base + a->off_tot), n);
+    f->valid.borrow(base + a->off_valid, n);
+    f->err.borrow(base + a->off_err, n);
+    a->f = f;
+    return DVS_OK;
+}
+
+// push rows [rb, re) of this rank (already in place in its own window) to the same place in every peer's window
+static int allrows_push(dvs_comm* c, const AllRows& a, uint32_t rb, uint32_t re, bool scalars) {
+    if (re <= rb) return DVS_OK;
+    const uint64_t dim = a.f->dim, hoff = a.f->heap_off;
+    const size_t g0 = (size_t)a.row0 + rb, cnt = re - rb;
+    for (int d = 1; d < c->world; ++d) {
+        const int r = (c->rank + d) % c->world;
+        uint8_t* pb = c->peer[r] + hoff;
+        const uint8_t* mb = c->window + hoff;
+        auto cp = [&](uint64_t off, size_t elem) {
+            return cudaMemcpyAsync(pb + off + g0 * elem, mb + off + g0 * elem, cnt * elem, cudaMemcpyDeviceToDevice, c->side);
+        };
+        DVS_CUDA_TRY(cp(a.off_freqs, dim * 8));
+        if (scalars) {
+            DVS_CUDA_TRY(cp(a.off_ent, 8));
+            DVS_CUDA_TRY(cp(a.off_et, 8));
+            DVS_CUDA_TRY(cp(a.off_tot, 8));
+            DVS_CUDA_TRY(cp(a.off_valid, 1));
+            DVS_CUDA_TRY(cp(a.off_err, 1));
         }
     }
-    if (s->nrec) {
-        PhaseTimer pt(ctx, DVS_PHASE_FREQ_ENTROPY);
-        k_freq_entropy<<<s->nrec, kEntThreads, kEntSmemBytes, st>>>(f->counts.p, dim, f->freqs.p, f->totals.p,
-                                                                    f->entropy.p, f->valid.p, f->err.p,
-                                                                    f->err_total.p);
-        ctx->launches++;
-        TRY_F(cudaGetLastError());
+    return DVS_OK;
+}
+
+static int sharded_args_ok(dvs_ctx* ctx, dvs_comm* c, const uint32_t* nrec_per_rank, uint32_t mine, const void* out) {
+    if (!ctx || !c || !nrec_per_rank || !out) {
+        set_error("sharded call: NULL argument");
+        return DVS_ERR_ARG;
     }
-    // the work list is freed on return: wait for the kernels that read it
-    TRY_F(cudaStreamSynchronize(st));
-#undef TRY_F
-    *out = f;
+    if (!c->connected) {
+        set_error("sharded call: the communicator is not connected (dvs_comm_connect)");
+        return DVS_ERR_ARG;
+    }
+    if (nrec_per_rank[c->rank] != mine) {
+        set_error("sharded call: nrec_per_rank[%d] = %u but this rank holds %u records", c->rank, nrec_per_rank[c->rank], mine);
+        return DVS_ERR_ARG;
+    }
+    return DVS_OK;
+}
+
+int dvs_count_kmers_sharded(dvs_ctx* ctx, dvs_comm* c, const dvs_seqset* s, int k, int num_states,
+                            const uint32_t* nrec_per_rank, dvs_kfreqs** out_all) {
+    uint64_t dim = 0;
+    DVS_TRY(count_args_ok(ctx, s, k, num_states, out_all, &dim));
+    DVS_TRY(sharded_args_ok(ctx, c, nrec_per_rank, s->nrec, out_all));
+    DVS_CUDA_TRY(dvs::enter(ctx));
+    DVS_TRY(dense_rows_fit((double)s->nrec * (double)dim * 4.0, "dvs_count_kmers_sharded", s->nrec, dim));
+    AllRows a;
+    DVS_TRY(allrows_alloc(ctx, c, nrec_per_rank, dim, &a));
+    a.f->k = k;
+    a.f->num_states = num_states;
+    auto fail = [&](int rc) {
+        cudaStreamSynchronize(c->side);
+        dvs_kfreqs_free(a.f);
+        return rc;
+    };
+    DevBuf<uint32_t> counts;
+    if (counts.alloc((size_t)s->nrec * dim) != DVS_OK) return fail(DVS_ERR_CUDA);
+    // every rank has left its previous use of this heap block before anybody writes into it
+    int rc = comm_push_begin(ctx, c);
+    if (rc == DVS_OK) rc = comm_barrier(ctx, c);
+    if (rc != DVS_OK) return fail(rc);
+    const char* ch_env = getenv("DVS_SHARD_CHUNKS");
+    const uint32_t chunks = c->world == 1 ? 1u : (uint32_t)std::max(1, std::min(64, ch_env ? atoi(ch_env) : 8));
+    const size_t r0 = a.row0;
+    CountDest dst{a.f->freqs.p + r0 * dim, a.f->totals.p + r0, a.f->entropy.p + r0, a.f->valid.p + r0, a.f->err.p + r0,
+                  a.f->err_total.p + r0, chunks, nullptr};
+    dst.after_chunk = [&](uint32_t rb, uint32_t re) -> int {
+        // rows [rb, re) are final once the stream gets here: push them behind an event, on the copy engines,
+        // while the next chunk is counted
+        DVS_CUDA_TRY(cudaEventRecord(c->ev_ready, ctx->stream));
+        DVS_CUDA_TRY(cudaStreamWaitEvent(c->side, c->ev_ready, 0));
+        return allrows_push(c, a, rb, re, true);
+    };
+    rc = count_core(ctx, s, k, num_states, counts.p, dim, dst);
+    if (rc == DVS_OK) rc = comm_push_commit(ctx, c);
+    if (rc == DVS_OK) rc = comm_push_wait(ctx, c);
+    if (rc != DVS_OK) return fail(rc);
+    *out_all = a.f;
+    return DVS_OK;
+}
+
+int dvs_kfreqs_allgather(dvs_ctx* ctx, dvs_comm* c, const dvs_kfreqs* f, const uint32_t* nrec_per_rank,
+                         dvs_kfreqs** out_all) {
+    if (!f) {
+        set_error("dvs_kfreqs_allgather: NULL argument");
+        return DVS_ERR_ARG;
+    }
+    DVS_TRY(sharded_args_ok(ctx, c, nrec_per_rank, f->nrec, out_all));
+    DVS_CUDA_TRY(dvs::enter(ctx));
+    AllRows a;
+    DVS_TRY(allrows_alloc(ctx, c, nrec_per_rank, f->dim, &a));
+    a.f->k = f->k;
+    a.f->num_states = f->num_states;
+    auto fail = [&](int rc) {
+        cudaStreamSynchronize(c->side);
+        dvs_kfreqs_free(a.f);
+        return rc;
+    };
+    cudaStream_t st = ctx->stream;
+    int rc = comm_push_begin(ctx, c);
+    if (rc == DVS_OK) rc = comm_barrier(ctx, c);
+    if (rc != DVS_OK) return fail(rc);
+    const size_t r0 = a.row0, n = f->nrec;
+    cudaError_t e = cudaSuccess;
+    if (n) {
+        e = cudaMemcpyAsync(a.f->freqs.p + r0 * f->dim, f->freqs.p, n * f->dim * 8, cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(a.f->entropy.p + r0, f->entropy.p, n * 8, cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(a.f->err_total.p + r0, f->err_total.p, n * 8, cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(a.f->totals.p + r0, f->totals.p, n * 8, cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(a.f->valid.p + r0, f->valid.p, n, cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(a.f->err.p + r0, f->err.p, n, cudaMemcpyDeviceToDevice, st);
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(c->ev_ready, st);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(c->side, c->ev_ready, 0);
+    if (e != cudaSuccess) {
+        set_error("dvs_kfreqs_allgather: %s", cudaGetErrorString(e));
+        return fail(DVS_ERR_CUDA);
+    }
+    rc = allrows_push(c, a, 0, f->nrec, true);
+    if (rc == DVS_OK) rc = comm_push_commit(ctx, c);
+    if (rc == DVS_OK) rc = comm_push_wait(ctx, c);
+    if (rc != DVS_OK) return fail(rc);
+    *out_all = a.f;
     return DVS_OK;
 }
 
@@ -1036,6 +1265,8 @@ int dvs_kfreqs_download(dvs_ctx* ctx, const dvs_kfreqs* f, uint32_t first, uint3
 void dvs_kfreqs_free(dvs_kfreqs* f) {
     if (!f) return;
     cudaSetDevice(f->device);
+    // rows held in a peer window: the block goes back to the symmetric heap (the communicator must still be alive)
+    if (f->heap) comm_heap_free(f->heap, f->heap_off);
     delete f;
 }
 

@@ -13,6 +13,10 @@
 // DFMA per pair-element, FP64-pipe bound — which has no cancellation (the Gram form
 // ||a||^2+||b||^2-2ab loses all digits once d^2 << ||a||^2).  Only tiles on or
 // below the diagonal are computed when both row ranges are in the shard; results are mirrored.
+#include <math.h>
+#include <string.h>
+
+#include "comm.cuh"
 #include "common.cuh"
 
 namespace dvs {
@@ -21,14 +25,32 @@ constexpr int kEuT = 128;  // tile edge (pairs)
 constexpr int kEuK = 16;   // columns per slab
 constexpr int kEuPad = 2;  // row padding of the [col][row] slabs (doubles)
 
+// where a tile's distances go: one matrix (plain call) or the same place in the matrix of every GPU
+// (dvs_euclid_distances_sharded: the tiles of the lower triangle are dealt over the GPUs and each kernel
+// stores its results straight into every peer's window - compute and all-gather in one kernel)
+struct EuOuts {
+    double* p[kCommMaxWorld];
+    int count;
+};
+
+// SHARDED: blockIdx.x enumerates this GPU's tiles t = tile_first + tile_step * blockIdx.x of the lower
+// triangle (t = ti (ti + 1) / 2 + tj, tj <= ti) of the whole n x n matrix
+template <bool SHARDED>
 __global__ void __launch_bounds__(256, 1)
 k_euclid_tiles(const double* __restrict__ F, uint64_t dim, uint32_t n, uint32_t row_begin, uint32_t row_end,
-               double* __restrict__ out /* [(row_end-row_begin)][n] */) {
+               const EuOuts outs /* each [(row_end-row_begin)][n] */, uint32_t tile_first, uint32_t tile_step) {
     extern __shared__ double eu_smem[];
     double(*sa)[kEuK][kEuT + kEuPad] = reinterpret_cast<double(*)[kEuK][kEuT + kEuPad]>(eu_smem);
     double(*sb)[kEuK][kEuT + kEuPad] =
         reinterpret_cast<double(*)[kEuK][kEuT + kEuPad]>(eu_smem + 2 * kEuK * (kEuT + kEuPad));
-    const uint32_t ti = blockIdx.y, tj = blockIdx.x;
+    uint32_t ti = blockIdx.y, tj = blockIdx.x;
+    if (SHARDED) {
+        const uint64_t t = (uint64_t)tile_first + (uint64_t)tile_step * blockIdx.x;
+        ti = (uint32_t)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+        while ((uint64_t)ti * (ti + 1) / 2 > t) --ti;
+        while ((uint64_t)(ti + 1) * (ti + 2) / 2 <= t) ++ti;
+        tj = (uint32_t)(t - (uint64_t)ti * (ti + 1) / 2);
+    }
     const uint32_t i0 = row_begin + ti * kEuT, j0 = tj * kEuT;
     if (i0 >= row_end) return;
     // a tile strictly above the diagonal whose transpose is also produced by this launch is skipped
@@ -124,9 +146,12 @@ k_euclid_tiles(const double* __restrict__ F, uint64_t dim, uint32_t n, uint32_t 
             const uint32_t j = j0 + 2 * tx + 32 * (b >> 1) + (b & 1);
             if (i >= row_end || j >= n) continue;
             const double d = (i == j) ? 0.0 : sqrt(acc[a][b]);
-            out[(size_t)(i - row_begin) * n + j] = d;
-            if (mirror_in_range && j >= row_begin && j < row_end && i < n)
-                out[(size_t)(j - row_begin) * n + i] = d;
+            const bool mirror = mirror_in_range && j >= row_begin && j < row_end && i < n;
+            for (int r = 0; r < (SHARDED ? outs.count : 1); ++r) {
+                double* out = outs.p[r];
+                out[(size_t)(i - row_begin) * n + j] = d;
+                if (mirror) out[(size_t)(j - row_begin) * n + i] = d;
+            }
         }
 }
 
@@ -149,11 +174,59 @@ extern "C" int dvs_euclid_distances(dvs_ctx* ctx, const dvs_kfreqs* f, uint32_t 
     DVS_TRY(d_out.alloc(nrows * n));
     dim3 grid((unsigned)((n + kEuT - 1) / kEuT), (unsigned)((nrows + kEuT - 1) / kEuT));
     PhaseTimer pt(ctx, DVS_PHASE_EUCLID);
-    DVS_CUDA_TRY(cudaFuncSetAttribute(k_euclid_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEuSmemBytes));
-    k_euclid_tiles<<<grid, 256, kEuSmemBytes, ctx->stream>>>(f->freqs.p, f->dim, (uint32_t)n, row_begin, row_end, d_out.p);
+    DVS_CUDA_TRY(cudaFuncSetAttribute(k_euclid_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEuSmemBytes));
+    EuOuts outs;
+    memset(&outs, 0, sizeof outs);
+    outs.p[0] = d_out.p;
+    outs.count = 1;
+    k_euclid_tiles<false><<<grid, 256, kEuSmemBytes, ctx->stream>>>(f->freqs.p, f->dim, (uint32_t)n, row_begin, row_end, outs, 0, 0);
     pt.stop();
     DVS_LAUNCHED(ctx);
     DVS_CUDA_TRY(cudaMemcpyAsync(dist, d_out.p, nrows * n * sizeof(double), cudaMemcpyDefault, ctx->stream));
     DVS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return DVS_OK;
+}
+
+// all ranks hold the same rows (dvs_count_kmers_sharded / dvs_kfreqs_allgather); every rank gets the whole matrix
+extern "C" int dvs_euclid_distances_sharded(dvs_ctx* ctx, dvs_comm* c, const dvs_kfreqs* f_all, double* dist) {
+    if (!ctx || !c || !c->connected || !f_all || !dist) {
+        set_error("dvs_euclid_distances_sharded: bad argument / communicator not connected");
+        return DVS_ERR_ARG;
+    }
+    const size_t n = f_all->nrec;
+    if (n == 0) return DVS_OK;
+    DVS_CUDA_TRY(dvs::enter(ctx));
+    cudaStream_t st = ctx->stream;
+    uint64_t hoff = 0;
+    DVS_TRY(comm_heap_alloc(c, n * n * sizeof(double), &hoff));
+    int rc = comm_barrier(ctx, c);  // nobody still uses this block of its window
+    cudaError_t e = cudaSuccess;
+    if (rc == DVS_OK) {
+        const uint64_t nt = (n + kEuT - 1) / kEuT, tiles = nt * (nt + 1) / 2;
+        const uint64_t mine = tiles > (uint64_t)c->rank ? (tiles - c->rank + c->world - 1) / c->world : 0;
+        EuOuts outs;
+        memset(&outs, 0, sizeof outs);
+        for (int r = 0; r < c->world; ++r) outs.p[r] = reinterpret_cast<double*>(c->peer[(c->rank + r) % c->world] + hoff);
+        outs.count = c->world;
+        PhaseTimer pt(ctx, DVS_PHASE_EUCLID);
+        e = cudaFuncSetAttribute(k_euclid_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEuSmemBytes);
+        if (e == cudaSuccess && mine) {
+            k_euclid_tiles<true><<<(unsigned)mine, 256, kEuSmemBytes, st>>>(f_all->freqs.p, f_all->dim, (uint32_t)n, 0,
+                                                                           (uint32_t)n, outs, (uint32_t)c->rank,
+                                                                           (uint32_t)c->world);
+            ctx->launches++;
+            e = cudaGetLastError();
+        }
+        pt.stop();
+        if (e == cudaSuccess) rc = comm_barrier(ctx, c);  // every GPU's tiles have landed in this window
+        if (e == cudaSuccess && rc == DVS_OK)
+            e = cudaMemcpyAsync(dist, c->window + hoff, n * n * sizeof(double), cudaMemcpyDefault, st);
+        if (e == cudaSuccess && rc == DVS_OK) rc = comm_check_error(ctx, c, "dvs_euclid_distances_sharded");
+    }
+    comm_heap_free(c, hoff);
+    if (e != cudaSuccess) {
+        set_error("dvs_euclid_distances_sharded: %s", cudaGetErrorString(e));
+        return DVS_ERR_CUDA;
+    }
+    return rc;
 }

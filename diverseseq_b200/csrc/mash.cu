@@ -19,6 +19,9 @@
 // threshold / buffer, so the result is exact for every input.
 #include <algorithm>
 
+#include <string.h>
+
+#include "comm.cuh"
 #include "common.cuh"
 
 namespace dvs {
@@ -308,27 +311,11 @@ k_mash_compact(const unsigned long long* __restrict__ keys, size_t nkeys, const 
     }
 }
 
-// mash_distance for all pairs touching rows [row_begin,row_end)  (distance.py:230-291)
-__global__ void k_mash_pairs(const uint32_t* __restrict__ sk, const uint32_t* __restrict__ lens, uint32_t stride,
-                             uint32_t n, int k, uint64_t sketch_size, uint32_t row_begin, uint32_t row_end,
-                             double* __restrict__ dist, uint32_t* __restrict__ inter_out, uint32_t* __restrict__ uni_out,
-                             int* __restrict__ err) {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t nrows = row_end - row_begin;
-    if (idx >= nrows * n) return;
-    const uint32_t i = row_begin + (uint32_t)(idx / n), j = (uint32_t)(idx % n);
-    const size_t o_ij = (size_t)(i - row_begin) * n + j;
-    if (i == j) {
-        dist[o_ij] = 0.0;
-        if (inter_out) inter_out[o_ij] = 0;
-        if (uni_out) uni_out[o_ij] = 0;
-        return;
-    }
-    const bool j_in = (j >= row_begin && j < row_end);
-    if (j_in && j > i) return;  // written by the (j,i) thread as the mirror
-    const uint32_t* A = sk + (size_t)i * stride;
-    const uint32_t* B = sk + (size_t)j * stride;
-    const uint32_t la = lens[i], lb = lens[j];
+// mash_distance of one pair of ascending sketches (distance.py:230-291): merge until `union == s` or one
+// side is exhausted, add the tails, cap at s; integer counts are exact, one f64 log at the end
+__device__ __forceinline__ double mash_pair(const uint32_t* __restrict__ A, const uint32_t* __restrict__ B, uint32_t la,
+                                            uint32_t lb, int k, uint64_t sketch_size, uint64_t& inter_o, uint64_t& uni_o,
+                                            int* __restrict__ err) {
     uint64_t inter = 0, uni = 0;
     uint32_t x = 0, y = 0;
     if (la && lb) {
@@ -368,6 +355,32 @@ __global__ void k_mash_pairs(const uint32_t* __restrict__ sk, const uint32_t* __
         d = __ddiv_rn(-log(__ddiv_rn(__dmul_rn(2.0, jac), __dadd_rn(1.0, jac))), (double)k);
         if (d > 1.0) d = 1.0;
     }
+    inter_o = inter;
+    uni_o = uni;
+    return d;
+}
+
+// all pairs touching rows [row_begin,row_end)
+__global__ void k_mash_pairs(const uint32_t* __restrict__ sk, const uint32_t* __restrict__ lens, uint32_t stride,
+                             uint32_t n, int k, uint64_t sketch_size, uint32_t row_begin, uint32_t row_end,
+                             double* __restrict__ dist, uint32_t* __restrict__ inter_out, uint32_t* __restrict__ uni_out,
+                             int* __restrict__ err) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nrows = row_end - row_begin;
+    if (idx >= nrows * n) return;
+    const uint32_t i = row_begin + (uint32_t)(idx / n), j = (uint32_t)(idx % n);
+    const size_t o_ij = (size_t)(i - row_begin) * n + j;
+    if (i == j) {
+        dist[o_ij] = 0.0;
+        if (inter_out) inter_out[o_ij] = 0;
+        if (uni_out) uni_out[o_ij] = 0;
+        return;
+    }
+    const bool j_in = (j >= row_begin && j < row_end);
+    if (j_in && j > i) return;  // written by the (j,i) thread as the mirror
+    uint64_t inter, uni;
+    const double d = mash_pair(sk + (size_t)i * stride, sk + (size_t)j * stride, lens[i], lens[j], k, sketch_size, inter,
+                               uni, err);
     dist[o_ij] = d;
     if (inter_out) inter_out[o_ij] = (uint32_t)inter;
     if (uni_out) uni_out[o_ij] = (uint32_t)uni;
@@ -376,6 +389,34 @@ __global__ void k_mash_pairs(const uint32_t* __restrict__ sk, const uint32_t* __
         dist[o_ji] = d;
         if (inter_out) inter_out[o_ji] = (uint32_t)inter;
         if (uni_out) uni_out[o_ji] = (uint32_t)uni;
+    }
+}
+
+// The pairs of the lower triangle dealt over the GPUs: this GPU takes pairs p = first + step * idx of the
+// linear enumeration p = i (i - 1) / 2 + j (j < i) and stores each distance (and its mirror) into the matrix
+// of EVERY GPU through the peer windows - the "all-gather of the matrix" happens inside the kernel.
+struct MashOuts {
+    double* p[kCommMaxWorld];
+    int* err[kCommMaxWorld];  // "a pair of empty sketches was seen" flag of every GPU (all ranks raise alike)
+    int count;
+};
+__global__ void k_mash_pairs_tri(const uint32_t* __restrict__ sk, const uint32_t* __restrict__ lens, uint32_t stride,
+                                 uint32_t n, int k, uint64_t sketch_size, uint64_t first, uint64_t step, uint64_t npairs,
+                                 const MashOuts outs) {
+    const uint64_t p = first + step * ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+    if (p >= npairs) return;
+    uint32_t i = (uint32_t)((sqrt(8.0 * (double)p + 1.0) + 1.0) * 0.5);
+    while ((uint64_t)i * (i - 1) / 2 > p) --i;
+    while ((uint64_t)(i + 1) * i / 2 <= p) ++i;
+    const uint32_t j = (uint32_t)(p - (uint64_t)i * (i - 1) / 2);
+    uint64_t inter, uni;
+    int bad = 0;
+    const double d = mash_pair(sk + (size_t)i * stride, sk + (size_t)j * stride, lens[i], lens[j], k, sketch_size, inter,
+                               uni, &bad);
+    for (int r = 0; r < outs.count; ++r) {
+        outs.p[r][(size_t)i * n + j] = d;
+        outs.p[r][(size_t)j * n + i] = d;
+        if (bad) *outs.err[r] = 1;
     }
 }
 
@@ -622,6 +663,108 @@ int dvs_mash_distances(dvs_ctx* ctx, const dvs_sketches* sk, int k, uint64_t ske
         return DVS_ERR_VALUE;
     }
     return DVS_OK;
+}
+
+int dvs_sketches_allgather(dvs_ctx* ctx, dvs_comm* c, const dvs_sketches* sk, const uint32_t* nrec_per_rank,
+                           uint32_t stride_all, dvs_sketches** out) {
+    if (!ctx || !c || !c->connected || !sk || !nrec_per_rank || !out || stride_all < sk->stride ||
+        nrec_per_rank[c->rank] != sk->nrec) {
+        set_error("dvs_sketches_allgather: bad argument (stride_all must be the largest stride of all ranks)");
+        return DVS_ERR_ARG;
+    }
+    DVS_CUDA_TRY(dvs::enter(ctx));
+    cudaStream_t st = ctx->stream;
+    uint64_t total = 0;
+    std::vector<uint64_t> bytes(c->world), lbytes(c->world);
+    for (int r = 0; r < c->world; ++r) {
+        total += nrec_per_rank[r];
+        bytes[r] = (uint64_t)nrec_per_rank[r] * stride_all * 4;
+        lbytes[r] = (uint64_t)nrec_per_rank[r] * 4;
+    }
+    auto* all = new dvs_sketches();
+    all->device = ctx->device;
+    all->nrec = (uint32_t)total;
+    all->stride = stride_all;
+    int rc = all->data.alloc((size_t)total * stride_all);
+    if (rc == DVS_OK) rc = all->lens.alloc(total);
+    DevBuf<uint32_t> wide;  // this rank's sketches at the common stride
+    const uint32_t* src = sk->data.p;
+    if (rc == DVS_OK && sk->stride != stride_all && sk->nrec) {
+        rc = wide.alloc((size_t)sk->nrec * stride_all);
+        cudaError_t e = cudaSuccess;
+        if (rc == DVS_OK) e = cudaMemsetAsync(wide.p, 0, (size_t)sk->nrec * stride_all * 4, st);
+        if (rc == DVS_OK && e == cudaSuccess)
+            e = cudaMemcpy2DAsync(wide.p, (size_t)stride_all * 4, sk->data.p, (size_t)sk->stride * 4, (size_t)sk->stride * 4,
+                                  sk->nrec, cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) {
+            set_error("dvs_sketches_allgather: %s", cudaGetErrorString(e));
+            rc = DVS_ERR_CUDA;
+        }
+        src = wide.p;
+    }
+    if (rc == DVS_OK) rc = dvs_comm_allgatherv(ctx, c, src, bytes.data(), all->data.p);
+    if (rc == DVS_OK) rc = dvs_comm_allgatherv(ctx, c, sk->lens.p, lbytes.data(), all->lens.p);
+    if (rc != DVS_OK) {
+        dvs_sketches_free(all);
+        return rc;
+    }
+    *out = all;
+    return DVS_OK;
+}
+
+int dvs_mash_distances_sharded(dvs_ctx* ctx, dvs_comm* c, const dvs_sketches* sk_all, int k, uint64_t sketch_size,
+                               double* dist) {
+    if (!ctx || !c || !c->connected || !sk_all || !dist) {
+        set_error("dvs_mash_distances_sharded: bad argument / communicator not connected");
+        return DVS_ERR_ARG;
+    }
+    const size_t n = sk_all->nrec;
+    if (n == 0) return DVS_OK;
+    DVS_CUDA_TRY(dvs::enter(ctx));
+    cudaStream_t st = ctx->stream;
+    uint64_t hoff = 0;
+    DVS_TRY(comm_heap_alloc(c, n * n * sizeof(double), &hoff));
+    int rc = DVS_OK;
+    int h_err = 0;
+    cudaError_t e = cudaMemsetAsync(c->window + kCommSelUpdOff, 0, sizeof(int), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->window + hoff, 0, n * n * sizeof(double), st);  // diagonal
+    if (rc == DVS_OK && e == cudaSuccess) rc = comm_barrier(ctx, c);  // every matrix is zeroed and free of old readers
+    if (rc == DVS_OK && e == cudaSuccess) {
+        const uint64_t npairs = (uint64_t)n * (n - 1) / 2;
+        const uint64_t mine = npairs > (uint64_t)c->rank ? (npairs - c->rank + c->world - 1) / c->world : 0;
+        MashOuts outs;
+        memset(&outs, 0, sizeof outs);
+        for (int r = 0; r < c->world; ++r) {
+            outs.p[r] = reinterpret_cast<double*>(c->peer[(c->rank + r) % c->world] + hoff);
+            outs.err[r] = reinterpret_cast<int*>(c->peer[(c->rank + r) % c->world] + kCommSelUpdOff);
+        }
+        outs.count = c->world;
+        PhaseTimer pt(ctx, DVS_PHASE_MASH_PAIRS);
+        if (mine) {
+            k_mash_pairs_tri<<<(unsigned)((mine + 127) / 128), 128, 0, st>>>(sk_all->data.p, sk_all->lens.p, sk_all->stride,
+                                                                            (uint32_t)n, k, sketch_size, (uint64_t)c->rank,
+                                                                            (uint64_t)c->world, npairs, outs);
+            ctx->launches++;
+            e = cudaGetLastError();
+        }
+        pt.stop();
+        if (e == cudaSuccess) rc = comm_barrier(ctx, c);
+        if (e == cudaSuccess && rc == DVS_OK)
+            e = cudaMemcpyAsync(dist, c->window + hoff, n * n * sizeof(double), cudaMemcpyDefault, st);
+        if (e == cudaSuccess && rc == DVS_OK)
+            e = cudaMemcpyAsync(&h_err, c->window + kCommSelUpdOff, sizeof(int), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && rc == DVS_OK) rc = comm_check_error(ctx, c, "dvs_mash_distances_sharded");
+    }
+    comm_heap_free(c, hoff);
+    if (e != cudaSuccess) {
+        set_error("dvs_mash_distances_sharded: %s", cudaGetErrorString(e));
+        return DVS_ERR_CUDA;
+    }
+    if (rc == DVS_OK && h_err) {  // a pair of empty sketches (seen by any rank): ZeroDivisionError in distance.py:283
+        set_error("division by zero");
+        return DVS_ERR_VALUE;
+    }
+    return rc;
 }
 
 int dvs_mash_sketch_host(dvs_ctx* ctx, const uint8_t* seq, uint64_t len, int k, uint64_t sketch_size, int num_states,

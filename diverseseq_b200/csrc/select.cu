@@ -15,12 +15,14 @@
 #include <limits.h>
 #include <stddef.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <limits>
 
 #include <cooperative_groups.h>
 
+#include "comm.cuh"
 #include "common.cuh"
 #include "entropy.cuh"
 
@@ -294,6 +296,7 @@ k_sel_scan(const double* __restrict__ F, const double* __restrict__ H, uint64_t 
     }
 }
 
+#include "select_shard.cuh"
 #include "select_fast.cuh"
 #include "select_grow.cuh"
 #include "select_sm.cuh"
@@ -330,6 +333,10 @@ __global__ void k_set_members(uint8_t* is_member, const unsigned* members, unsig
 }
 
 static int panic_error(const SelScal& h) {
+    if (h.panic == 2u) {
+        set_error("dvs_select_sharded: a peer GPU did not answer an exchange within 20 s (a rank is missing or died)");
+        return DVS_ERR_CUDA;
+    }
     set_error("cannot calculate entropy as frequency vector total %.17g!=1.0", h.panic_total);
     return DVS_ERR_VALUE;
 }
@@ -434,8 +441,13 @@ struct dvs_summed {
 
 extern "C" {
 
-int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_t num, int mode, uint32_t min_size,
-               uint32_t max_size, uint32_t* sel_idx, double* sel_delta, double* stats5, uint32_t* size_out) {
+// comm == nullptr: one GPU.  Otherwise every rank calls this with the same rows (a kfreqs made by
+// dvs_count_kmers_sharded / dvs_kfreqs_allgather), the same order and the same arguments: the state and
+// every host-side decision are replicated (identical inputs, identical kernels), while the windows of
+// candidates are scored candidate-sharded with an all-reduce(min) of the first interesting position.
+static int select_core(dvs_ctx* ctx, dvs_comm* comm, const dvs_kfreqs* f, const uint32_t* order, uint32_t num, int mode,
+                       uint32_t min_size, uint32_t max_size, uint32_t* sel_idx, double* sel_delta, double* stats5,
+                       uint32_t* size_out) {
     if (!ctx || !f || (!order && num) || !size_out) {
         set_error("dvs_select: NULL argument");
         return DVS_ERR_ARG;
@@ -459,6 +471,13 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
     DVS_CUDA_TRY(dvs::enter(ctx));
     cudaStream_t st = ctx->stream;
     const uint64_t dim = f->dim;
+    const unsigned world = comm ? (unsigned)comm->world : 1u, rank = comm ? (unsigned)comm->rank : 0u;
+    ShardArgs shard;
+    memset(&shard, 0, sizeof shard);
+    shard.rank = (int)rank;
+    shard.world = (int)world;
+    for (unsigned r = 0; r < world && comm; ++r) shard.xbase[r] = comm->peer[r];
+    if (world > 1) DVS_TRY(comm_barrier(ctx, comm));  // every rank is here: exchange slots of earlier calls are dead
 
     // validity / panic flags of the records, needed on the host to form the initial set
     std::vector<uint8_t> valid(f->nrec), err(f->nrec);
@@ -532,13 +551,17 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
     constexpr int kRoundsPerBatch = 32;
     // DVS_SELECT_PERSIST=0 keeps the two-launches-per-round form, =1 the global-state persistent kernel
     // (A/B measurements, fallbacks); default: SM-replicated rounds when the state fits in shared memory
+    // DVS_SELECT_GRID: CTAs of the persistent kernels (tests run several ranks on ONE GPU: their kernels must be
+    // co-resident, so each takes a share of the SMs)
+    const char* grid_env = getenv("DVS_SELECT_GRID");
+    const unsigned grid_cap = grid_env && atoi(grid_env) > 0 ? (unsigned)atoi(grid_env) : 0xFFFFFFFFu;
     const char* per_env = getenv("DVS_SELECT_PERSIST");
     int coop = 0, per_sm = 0, per_sm2 = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
     if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sel_persist, kFastThreads, 0) != cudaSuccess)
         per_sm = 0;
     const bool use_persist = use_dev && coop && per_sm > 0 && !(per_env && per_env[0] == '0');
-    const unsigned persist_grid = (unsigned)ctx->sm_count * (unsigned)std::min(per_sm, 2);
+    const unsigned persist_grid = std::min((unsigned)ctx->sm_count * (unsigned)std::min(per_sm, 2), std::max(1u, std::min(grid_cap, 0x7FFFFFFFu)));
     bool sm_ok = use_persist && !(per_env && per_env[0] == '1') && dim <= kSmMaxDim;
     if (sm_ok) {
         sm_ok = cudaFuncSetAttribute(k_sel_persist_sm, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -548,7 +571,7 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
                 per_sm2 > 0;
         (void)cudaGetLastError();
     }
-    const unsigned sm_grid = std::min<unsigned>((unsigned)ctx->sm_count, kSmMaxGrid);
+    const unsigned sm_grid = std::min(std::min<unsigned>((unsigned)ctx->sm_count, kSmMaxGrid), grid_cap);
     DevBuf<SmPart> d_spart, d_upart, d_dpart;
     if (sm_ok) {
         DVS_TRY(d_spart.alloc(2 * kSmMaxGrid));
@@ -559,7 +582,7 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
     // keeps one host-driven attempt per candidate
     const char* gb_env = getenv("DVS_SELECT_GROW_BATCH");
     const bool use_grow_batch = use_fast && grow_mode && !(gb_env && gb_env[0] == '0');
-    constexpr unsigned kGrowWindowMax = 64;
+    const unsigned kGrowWindowMax = 64 * world;
     SelState fresh;  // clone(): the members re-summed in order (S, E), refreshed whenever the set changes
     DevBuf<FastSum> d_gparts;
     DevBuf<double> d_gmd, d_gmb;
@@ -572,7 +595,7 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
         DVS_TRY(d_gparts.alloc((size_t)kGrowWindowMax * (cap + 3)));
         DVS_TRY(d_gmd.alloc((size_t)kGrowWindowMax * cap));
         DVS_TRY(d_gmb.alloc((size_t)kGrowWindowMax * cap));
-        DVS_TRY(d_gscratch.alloc(kGrowWindowMax));
+        DVS_TRY(d_gscratch.alloc(kGrowWindowMax));  // (indexed by the window offset)
         DVS_TRY(d_ginteresting.alloc(1));
     }
     unsigned fresh_n = 0;
@@ -600,14 +623,21 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
             }
             const unsigned W = std::min(grow_window, num - cursor);
             DVS_CUDA_TRY(cudaMemsetAsync(d_ginteresting.p, 0xFF, sizeof(unsigned), st));
-            k_grow_eval<<<dim3(n + 3, W), kFastThreads, 0, st>>>(f->freqs.p, dim, cur->S(), cur->members(), cur->sc.p,
-                                                                 fresh.S(), f->valid.p, is_member.p, d_order.p, cursor,
-                                                                 d_gparts.p);
-            DVS_LAUNCHED(ctx);
-            k_grow_decide<<<W, kFastThreads, 0, st>>>(f->entropy.p, dim, cur->members(), cur->sc.p, fresh.sc.p, f->valid.p,
-                                                      is_member.p, d_order.p, cursor, d_gparts.p, d_gmd.p, d_gmb.p, cap,
-                                                      d_gscratch.p, d_ginteresting.p, mode == DVS_MODE_MAX_COV ? 1 : 0);
-            DVS_LAUNCHED(ctx);
+            // candidate-sharded: this GPU evaluates the window candidates c with (cursor + c) % world == rank
+            const unsigned gc0 = (rank + world - cursor % world) % world;
+            const unsigned Wloc = W > gc0 ? (W - gc0 + world - 1) / world : 0;
+            if (Wloc) {
+                k_grow_eval<<<dim3(n + 3, Wloc), kFastThreads, 0, st>>>(f->freqs.p, dim, cur->S(), cur->members(), cur->sc.p,
+                                                                        fresh.S(), f->valid.p, is_member.p, d_order.p,
+                                                                        cursor, d_gparts.p, gc0, world);
+                DVS_LAUNCHED(ctx);
+                k_grow_decide<<<Wloc, kFastThreads, 0, st>>>(f->entropy.p, dim, cur->members(), cur->sc.p, fresh.sc.p,
+                                                             f->valid.p, is_member.p, d_order.p, cursor, d_gparts.p, d_gmd.p,
+                                                             d_gmb.p, cap, d_gscratch.p, d_ginteresting.p,
+                                                             mode == DVS_MODE_MAX_COV ? 1 : 0, gc0, world);
+                DVS_LAUNCHED(ctx);
+            }
+            if (world > 1) DVS_TRY(comm_min_u32(ctx, comm, d_ginteresting.p, d_ginteresting.p));
             unsigned* h_fi = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ctx->pinned) + sizeof(SelScal));
             DVS_CUDA_TRY(cudaMemcpyAsync(h_fi, d_ginteresting.p, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
             DVS_CUDA_TRY(cudaStreamSynchronize(st));
@@ -631,8 +661,9 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
             // every remaining round in one cooperative launch (until done, or halted for the host)
             const bool use_sm = sm_ok && n <= kSmMaxN;
             const unsigned grid = use_sm ? sm_grid : persist_grid;
-            k_sel_set_dev<<<1, 1, 0, st>>>(cur->sc.p, cursor, std::min(window, grid), grid, num, accepts,
+            k_sel_set_dev<<<1, 1, 0, st>>>(cur->sc.p, cursor, std::min(window, grid * world), grid * world, num, accepts,
                                            (unsigned)cur->which);
+            if (comm) shard.tag_base = (unsigned)((++comm->sel_tag_base) << 20);
             DVS_LAUNCHED(ctx);
             const double* a_F = f->freqs.p;
             const double* a_H = f->entropy.p;
@@ -644,7 +675,7 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
             SelScal* a_sc = cur->sc.p;
             const uint8_t* a_valid = f->valid.p;
             const unsigned* a_order = d_order.p;
-            unsigned a_rounds = 0x7fffffffu;
+            unsigned a_rounds = world > 1 ? 0xFFFF0u : 0x7fffffffu;  // (exchange tags of one launch are 20 bits)
             unsigned long long* a_trace = nullptr;
             DevBuf<unsigned long long> d_trace;
             const char* tr_env = getenv("DVS_SELECT_TRACE");
@@ -667,12 +698,12 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
                 DVS_CUDA_TRY(cudaMemsetAsync(d_spart.p, 0, 2 * kSmMaxGrid * sizeof(SmPart), st));
                 DVS_CUDA_TRY(cudaMemsetAsync(d_upart.p, 0, (kSmMaxN + 1) * sizeof(SmPart), st));
                 void* args[] = {&a_F, &a_H, &a_dim32, &a_S, &a_M, &a_mem, &a_md, &a_mb, &a_sc, &a_valid, &a_order,
-                                &a_sp, &a_up, &a_dp, &a_trace, &a_trace_all};
+                                &a_sp, &a_up, &a_dp, &a_trace, &a_trace_all, &shard};
                 DVS_CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_sel_persist_sm, dim3(grid), dim3(kFastThreads), args,
                                                          sizeof(SmShared), st));
             } else {
                 void* args[] = {&a_F, &a_H, &a_dim, &a_S0, &a_S1, &a_M0, &a_M1, &a_mem, &a_md, &a_mb, &a_sc, &a_valid,
-                                &a_order, &a_rounds, &a_trace};
+                                &a_order, &a_rounds, &a_trace, &shard};
                 DVS_CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_sel_persist, dim3(grid), dim3(kFastThreads), args, 0, st));
             }
             ctx->launches++;
@@ -708,7 +739,7 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
             if (!hd.halt) continue;  // finished
             DVS_TRY(sel.reset_scan(*cur));
             if (cursor >= num) break;
-        } else if (use_dev && (!grow_mode || n == max_size)) {
+        } else if (use_dev && world == 1 && (!grow_mode || n == max_size)) {
             // Device-driven rounds: scan + decide + replace/update are enqueued kRoundsPerBatch times
             // without any read-back; the kernels carry cursor / window / accepts in the scalar block
             // and stop doing work once they halt (undecided within the error bound) or finish.
@@ -872,7 +903,24 @@ int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_
     }
     *size_out = n;
     ctx->last_accepts = accepts;
+    if (world > 1) DVS_TRY(comm_check_error(ctx, comm, "dvs_select_sharded"));
     return DVS_OK;
+}
+
+int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_t num, int mode, uint32_t min_size,
+               uint32_t max_size, uint32_t* sel_idx, double* sel_delta, double* stats5, uint32_t* size_out) {
+    return select_core(ctx, nullptr, f, order, num, mode, min_size, max_size, sel_idx, sel_delta, stats5, size_out);
+}
+
+int dvs_select_sharded(dvs_ctx* ctx, dvs_comm* comm, const dvs_kfreqs* f_all, const uint32_t* order, uint32_t num,
+                       int mode, uint32_t min_size, uint32_t max_size, uint32_t* sel_idx, double* sel_delta,
+                       double* stats5, uint32_t* size_out) {
+    if (!comm || !comm->connected) {
+        set_error("dvs_select_sharded: the communicator is not connected");
+        return DVS_ERR_ARG;
+    }
+    return select_core(ctx, comm->world > 1 ? comm : nullptr, f_all, order, num, mode, min_size, max_size, sel_idx,
+                       sel_delta, stats5, size_out);
 }
 
 int dvs_debug_fast_terms(dvs_ctx* ctx, const double* a, const double* b, double* m, double* l, int32_t* special,

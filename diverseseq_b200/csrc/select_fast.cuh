@@ -585,9 +585,11 @@ __global__ void __launch_bounds__(kFastThreads)
 k_sel_persist(const double* __restrict__ F, const double* __restrict__ H, uint64_t dim, double* S0, double* S1,
               unsigned* M0, unsigned* M1, uint8_t* is_member, double* mdelta, double* mbound, SelScal* sc,
               const uint8_t* __restrict__ valid, const unsigned* __restrict__ order, unsigned max_rounds,
-              unsigned long long* trace) {
+              unsigned long long* trace, const ShardArgs sh) {
     cg::grid_group grid = cg::this_grid();
     __shared__ RoundScal rs;
+    __shared__ unsigned s_xft, s_xfu, s_xdead;
+    const unsigned world = (unsigned)sh.world, rank = (unsigned)sh.rank;
     // DVS_SELECT_TRACE: CTA 0 stamps %globaltimer at the four phase boundaries of the first rounds
     auto stamp = [&](unsigned round, int slot) {
         if (trace && blockIdx.x == 0 && threadIdx.x == 0 && round < 512) {
@@ -612,10 +614,37 @@ k_sel_persist(const double* __restrict__ F, const double* __restrict__ H, uint64
         if (rs.stop) break;  // grid-uniform: every CTA read the same scalar block
         const unsigned which = rs.which, cursor = rs.cursor, count = rs.count, n = rs.q.n;
         const ScanScal q = rs.q;
-        for (unsigned c = blockIdx.x; c < count; c += gridDim.x)
+        // candidate-sharded over the GPUs: this one scores the window positions p with p % world == rank
+        const unsigned woff = (rank + world - cursor % world) % world;
+        for (unsigned c = woff + world * blockIdx.x; c < count; c += world * gridDim.x)
             scan_fast_body(F, H, dim, which ? S1 : S0, sc, q, valid, is_member, order, cursor + c);
         stamp(round, 1);
         grid.sync();
+        if (world > 1u) {  // all-reduce(min) of {first_true, first_unsure} over NVLink by CTA 0 (select_sm.cuh)
+            if (blockIdx.x == 0) {
+                if (threadIdx.x == 0) {
+                    s_xft = kNone;
+                    s_xfu = kNone;
+                    s_xdead = 0;
+                }
+                __syncthreads();
+                shard_exchange_min(sh, round + 1u, __ldcg(&sc->first_true), __ldcg(&sc->first_unsure), &s_xft, &s_xfu,
+                                   &s_xdead);
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    if (s_xdead) {
+                        sc->panic = 2u;
+                        sc->halt = 1u;
+                        s_xft = kNone;
+                        s_xfu = 0u;
+                    }
+                    sc->first_true = s_xft;
+                    sc->first_unsure = s_xfu;
+                    __threadfence();
+                }
+            }
+            grid.sync();
+        }
         stamp(round, 2);
         if (threadIdx.x == 0) {
             rs.ft = __ldcg(&sc->first_true);

@@ -19,8 +19,9 @@ k_grow_eval(const double* __restrict__ F, uint64_t dim, const double* __restrict
             const unsigned* __restrict__ members, const SelScal* __restrict__ sc_cur,
             const double* __restrict__ S_fresh, const uint8_t* __restrict__ valid,
             const uint8_t* __restrict__ is_member, const unsigned* __restrict__ order, unsigned cursor,
-            FastSum* __restrict__ parts) {
-    const unsigned c = blockIdx.y, t = blockIdx.x, n = sc_cur->n;
+            FastSum* __restrict__ parts, unsigned c0, unsigned cstride) {
+    // (c0, cstride): the window candidates this GPU evaluates (candidate-sharded `max`, all of them on one GPU)
+    const unsigned c = c0 + cstride * blockIdx.y, t = blockIdx.x, n = sc_cur->n;
     const unsigned row = order[cursor + c];
     if (!valid[row] || is_member[row]) return;
     const double* fc = F + (size_t)row * dim;
@@ -46,9 +47,9 @@ k_grow_decide(const double* __restrict__ H, uint64_t dim, const unsigned* __rest
               const uint8_t* __restrict__ valid, const uint8_t* __restrict__ is_member,
               const unsigned* __restrict__ order, unsigned cursor, const FastSum* __restrict__ parts,
               double* __restrict__ md, double* __restrict__ mb, unsigned cap, SelScal* __restrict__ scratch,
-              unsigned* __restrict__ first_interesting, int use_cov) {
+              unsigned* __restrict__ first_interesting, int use_cov, unsigned c0, unsigned cstride) {
     __shared__ int s_dec;
-    const unsigned c = blockIdx.x, pos = cursor + c, n = sc_cur->n;
+    const unsigned c = c0 + cstride * blockIdx.x, pos = cursor + c, n = sc_cur->n;
     const unsigned row = order[pos];
     if (!valid[row] || is_member[row]) return;  // skipped silently, like the scan
     const FastSum* P = parts + (size_t)c * (n + 3);

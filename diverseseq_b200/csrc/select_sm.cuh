@@ -32,7 +32,7 @@
 // P - 1 sequential additions, covered by `depth`; `a` travels as a float rounded UP, which only widens a
 // bound), so decisions are identical; CTA 0 writes the state back to global memory when the rounds end or
 // halt for the host.
-constexpr unsigned kSmMaxDim = 4096, kSmMaxN = 1024, kSmMaxGrid = 256, kSmChunk = kFastThreads;
+constexpr unsigned kSmMaxDim = 4096, kSmMaxN = 1024, kSmMaxGrid = 256, kSmChunk = 4 * kFastThreads;
 constexpr double kSmDepth = 4.0;
 
 struct __align__(16) SmPart {
@@ -50,7 +50,7 @@ struct SmShared {
     unsigned char cvalid[kSmChunk];
     double pe[kSmMaxGrid], pt[kSmMaxGrid], pa[kSmMaxGrid];
     unsigned char pbad[kSmMaxGrid], wskip[kSmMaxGrid];
-    unsigned ft, fu, unsure;
+    unsigned ft, fu, unsure, xft, xfu, dead;
     double2 ltab[64];  // glibc log2 table {1/c, log2 c}
 };
 
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(kFastThreads, 1)
 k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, unsigned dim, double* S_glob,
                  unsigned* M_glob, uint8_t* is_member, double* mdelta_g, double* mbound_g, SelScal* sc,
                  const uint8_t* __restrict__ valid, const unsigned* __restrict__ order, SmPart* spart, SmPart* upart,
-                 SmPart* dpart, unsigned long long* trace, int trace_all) {
+                 SmPart* dpart, unsigned long long* trace, int trace_all, const ShardArgs sh) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     SmShared& sm = *reinterpret_cast<SmShared*>(sm_raw);
     const unsigned tid = threadIdx.x, b = blockIdx.x, G = gridDim.x;
@@ -161,7 +161,9 @@ k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, uns
         sm.mH[0][j] = H[r];
     }
     __syncthreads();
-    const unsigned wmin = max(1u, G / 4u);
+    const unsigned world = (unsigned)sh.world, rank = (unsigned)sh.rank, Gw = G * world;
+    const unsigned wmin = max(1u, Gw / 4u);
+    if (tid == 0) sm.dead = 0;
     // loop-invariant factors of fast_bound / fast_total_ok (same expressions, same rounding)
     const double kb0 = ((double)dim + fast_slack(dim) + 16.0) * 1.2e-16;
     const double kb4 = ((double)dim + fast_slack(dim, kSmDepth) + 16.0) * 1.2e-16;
@@ -173,21 +175,28 @@ k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, uns
 
     while (!halt && cursor < num) {
         stamp(0);
-        window = max(1u, min(window, G));
-        const unsigned P = (dim >= 2048u && window * 4u <= G) ? 4u : ((dim >= 2048u && window * 2u <= G) ? 2u : 1u);
+        if (xs >= 0xFFFF0u) {  // exchange tags of one launch are 20 bits: let the host start a new launch
+            halt = 1;
+            break;
+        }
+        window = max(1u, min(window, Gw));
+        const unsigned P = (dim >= 2048u && window * 4u <= Gw) ? 4u : ((dim >= 2048u && window * 2u <= Gw) ? 2u : 1u);
         const unsigned count = min(window, num - cursor);
+        // this GPU's candidates: window positions p with p % world == rank, i.e. offsets woff + world * i
+        const unsigned woff = (rank + world - cursor % world) % world;
+        const unsigned nloc = count > woff ? (count - woff + world - 1u) / world : 0u;
         if (cursor < cbase || cursor + count > cend) {  // stage the next chunk of positions (CTA-uniform)
             __syncthreads();
             cbase = cursor;
             cend = min(num, cbase + kSmChunk);
-            if (cbase + tid < cend) {
-                const unsigned row = order[cbase + tid];
-                sm.crow[tid] = row;
-                sm.cvalid[tid] = valid[row];
-                sm.cH[tid] = H[row];
+            for (unsigned q = tid; cbase + q < cend; q += kFastThreads) {
+                const unsigned row = order[cbase + q];
+                sm.crow[q] = row;
+                sm.cvalid[q] = valid[row];
+                sm.cH[q] = H[row];
             }
-            // ... and pull their rows towards L2, one 128-byte line per prefetch, rows dealt over the CTAs
-            for (unsigned r = b; r < cend - cbase; r += G) {
+            // ... and pull the rows this GPU will score towards L2, one 128-byte line per prefetch, dealt over the CTAs
+            for (unsigned r = (rank + world - cbase % world) % world + world * b; r < cend - cbase; r += world * G) {
                 const double* fr = F + (size_t)order[cbase + r] * dim;
                 for (unsigned l = tid * 16u; l < dim; l += kFastThreads * 16u)
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(fr + l));
@@ -199,14 +208,15 @@ k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, uns
             sm.ft = kNone;
             sm.fu = kNone;
         }
-        if (tid < count) sm.wskip[tid] = sm.cvalid[coff + tid] ? 0 : 1;
+        if (tid < nloc) sm.wskip[tid] = sm.cvalid[coff + woff + world * tid] ? 0 : 1;
         // ---- scan: slice p of candidate c ----
         ++xs;
         SmPart* const sbuf = spart + (xs & 1u) * kSmMaxGrid;
-        const unsigned c = b / P, p = b % P;
+        const unsigned c = b / P, p = b % P;  // c: index among this GPU's candidates of the window
+        const unsigned cw = woff + world * c;  // ... and its offset inside the window
         const double* fl = F + (size_t)sm.members[mw][lowest] * dim;
-        if (c < count && sm.cvalid[coff + c]) {  // CTA-uniform (a member's score is published but never read)
-            const double* fc = F + (size_t)sm.crow[coff + c] * dim;
+        if (c < nloc && sm.cvalid[coff + cw]) {  // CTA-uniform (a member's score is published but never read)
+            const double* fc = F + (size_t)sm.crow[coff + cw] * dim;
             const unsigned lo = (unsigned)(((uint64_t)dim * p) / P), hi = (unsigned)(((uint64_t)dim * (p + 1)) / P);
             auto num = [&](unsigned i) { return __dadd_rn(__dsub_rn(sm.S[i], fl[i]), fc[i]); };
             const FastSum h = P == 4u   ? block_entropy_ilp<false, 2>(lo, hi, num, div_n, sm.ltab)
@@ -230,27 +240,27 @@ k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, uns
             __syncthreads();  // wskip initialised (a CTA without a candidate has not passed a barrier yet)
             for (unsigned j = tid; j < n; j += kFastThreads) {
                 const unsigned r = sm.members[mw][j];
-                for (unsigned cc = 0; cc < count; ++cc)
-                    if (sm.crow[coff + cc] == r) sm.wskip[cc] = 1;
+                for (unsigned cc = 0; cc < nloc; ++cc)
+                    if (sm.crow[coff + woff + world * cc] == r) sm.wskip[cc] = 1;
             }
             __syncthreads();
             if (tid < G) {
                 const FastSum g = sm_gather(sbuf + tid, xs);
-                if (tid < count * P && !sm.wskip[tid / P]) {
+                if (tid < nloc * P && !sm.wskip[tid / P]) {
                     sm.pe[tid] = g.e; sm.pt[tid] = g.t; sm.pa[tid] = g.a; sm.pbad[tid] = (unsigned char)g.bad;
                 }
             }
             __syncthreads();
             stamp(2);
-            if (tid < count && !sm.wskip[tid]) {
+            if (tid < nloc && !sm.wskip[tid]) {
                 FastSum h{sm.pe[tid * P], sm.pt[tid * P], sm.pa[tid * P], sm.pbad[tid * P]};
                 for (unsigned q = 1; q < P; ++q) {
                     h.e += sm.pe[tid * P + q]; h.t += sm.pt[tid * P + q]; h.a += sm.pa[tid * P + q];
                     h.bad |= sm.pbad[tid * P + q];
                 }
-                const unsigned pos = cursor + tid;
+                const unsigned pos = cursor + woff + world * tid;
                 const double mean_entropy =
-                    div_exact(__dadd_rn(__dsub_rn(E, sm.mH[mw][lowest]), sm.cH[coff + tid]), div_n);
+                    div_exact(__dadd_rn(__dsub_rn(E, sm.mH[mw][lowest]), sm.cH[pos - cbase]), div_n);
                 const double d = h.e - mean_entropy;
                 const double bd = (P > 1u ? kb4 : kb0) * (h.a + fabs(mean_entropy) + 1.0);
                 const double thr = total_jsd + kEps, tb = total_bound + 4.0 * kEps;
@@ -263,6 +273,20 @@ k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, uns
                 }
             }
             __syncthreads();
+            if (world > 1u) {  // the leaders' all-reduce(min) over NVLink
+                const unsigned lft = sm.ft, lfu = sm.fu;
+                __syncthreads();
+                shard_exchange_min(sh, xs, lft, lfu, &sm.ft, &sm.fu, &sm.dead);
+                __syncthreads();
+                if (sm.dead) {  // a peer is gone: stop everything (the host reports the error)
+                    if (tid == 0) {
+                        sm.ft = kNone;
+                        sm.fu = 0u;
+                        sc->panic = 2u;
+                    }
+                    __syncthreads();
+                }
+            }
             if (tid == 0) sm_st128(&dslot->w[0], ((unsigned long long)sm.fu << 32) | sm.ft, xs);
         } else {
             if (tid == 0) {
@@ -283,7 +307,7 @@ k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, uns
         }
         if (ft == kNone) {  // empty window
             cursor += count;
-            window = min(window * 2u, G);
+            window = min(window * 2u, Gw);
             stamp(4); stamp(5); stamp(6);
             ++tr_round;
             continue;
@@ -382,7 +406,7 @@ k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, uns
         }
         lowest = lo2;
         touched = true;
-        window = max(wmin, min(G, 2u * (ft - cursor + 1u)));
+        window = max(wmin, min(Gw, 2u * (ft - cursor + 1u)));
         cursor = ft + 1u;
         ++accepts;
         stamp(6);

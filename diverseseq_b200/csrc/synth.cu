@@ -122,9 +122,10 @@ __global__ void k_syn_ancestors(uint64_t seed, uint32_t nfam, uint64_t anc_len, 
 }
 
 // one thread per output byte position group of 16 (records located by binary search on offsets)
+// records [first, first + nrec) of the set: local record r is record first + r of the generator
 __global__ void k_syn_members(uint64_t seed, uint32_t nrec, uint32_t nfam, uint64_t mean_len, uint64_t anc_len,
                               const uint64_t* __restrict__ offsets, const uint8_t* __restrict__ anc,
-                              uint8_t* __restrict__ out, uint64_t total) {
+                              uint8_t* __restrict__ out, uint64_t total, uint32_t first) {
     const uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
     if (g >= total) return;
     // record containing byte g
@@ -134,18 +135,18 @@ __global__ void k_syn_members(uint64_t seed, uint32_t nrec, uint32_t nfam, uint6
         if (offsets[mid] <= g) lo = mid; else hi = mid;
     }
     uint32_t r = lo;
-    SynRec sr = syn_record(seed, r, nfam, mean_len);
+    SynRec sr = syn_record(seed, first + r, nfam, mean_len);
     uint64_t rend = offsets[r + 1];
     for (int i = 0; i < 16; ++i) {
         uint64_t q = g + i;
         if (q >= total) break;
         while (q >= rend) {  // crossed into the next (non-empty) record
             ++r;
-            sr = syn_record(seed, r, nfam, mean_len);
+            sr = syn_record(seed, first + r, nfam, mean_len);
             rend = offsets[r + 1];
         }
         const uint64_t p = q - offsets[r];
-        out[q] = syn_member_byte(seed, r, sr.sub_thresh, p, anc[(size_t)sr.fam * anc_len + p]);
+        out[q] = syn_member_byte(seed, first + r, sr.sub_thresh, p, anc[(size_t)sr.fam * anc_len + p]);
     }
 }
 
@@ -202,12 +203,17 @@ int dvs_synth_host(uint64_t seed, uint32_t nrec, uint32_t nfam, uint64_t mean_le
 }
 
 int dvs_seqset_synth(dvs_ctx* ctx, uint64_t seed, uint32_t nrec, uint32_t nfam, uint64_t mean_len, dvs_seqset** out) {
-    if (!ctx || !out || mean_len < 4 || nfam == 0) {
+    return dvs_seqset_synth_range(ctx, seed, 0, nrec, nfam, mean_len, out);
+}
+
+int dvs_seqset_synth_range(dvs_ctx* ctx, uint64_t seed, uint32_t first, uint32_t nrec, uint32_t nfam, uint64_t mean_len,
+                           dvs_seqset** out) {
+    if (!ctx || !out || mean_len < 4 || nfam == 0 || (uint64_t)first + nrec > 0xFFFFFFFFull) {
         set_error("dvs_seqset_synth: bad argument");
         return DVS_ERR_ARG;
     }
     std::vector<uint64_t> offsets(nrec + 1, 0);
-    for (uint32_t r = 0; r < nrec; ++r) offsets[r + 1] = offsets[r] + syn_record(seed, r, nfam, mean_len).len;
+    for (uint32_t r = 0; r < nrec; ++r) offsets[r + 1] = offsets[r] + syn_record(seed, first + r, nfam, mean_len).len;
     dvs_seqset* s = nullptr;
     DVS_TRY(dvs_seqset_alloc_internal(ctx, offsets.data(), nrec, &s));
     auto fail = [&](const char* what, cudaError_t e) {
@@ -235,7 +241,7 @@ int dvs_seqset_synth(dvs_ctx* ctx, uint64_t seed, uint32_t nrec, uint32_t nfam, 
     if (s->total) {
         const uint64_t groups = (s->total + 15) / 16;
         k_syn_members<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(seed, nrec, nfam, mean_len, anc_len, s->offsets.p,
-                                                                        d_anc.p, s->data(), s->total);
+                                                                        d_anc.p, s->data(), s->total, first);
         ctx->launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return fail("k_syn_members", e);
     }

@@ -325,8 +325,7 @@ def load_seqset(ctx, store: DvseqszStore, seqids, threads: int | None = None, pi
     host = None
     if pinned:
         try:
-            import torch
-            host = torch.empty(max(total, 1), dtype=torch.uint8, pin_memory=True).numpy()
+            host = _lib.pinned_array(max(total, 1))
         except Exception:
             host = None
     if host is None:

@@ -63,9 +63,7 @@ def _alphabet(moltype: str) -> str:
 def _staging(total: int, pinned: bool) -> np.ndarray:
     if pinned:
         try:
-            import torch
-
-            return torch.empty(max(total, 1), dtype=torch.uint8, pin_memory=True).numpy()
+            return _lib.pinned_array(max(total, 1))
         except Exception:
             pass
     return np.empty(max(total, 1), dtype=np.uint8)

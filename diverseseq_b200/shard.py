@@ -1,21 +1,29 @@
-"""Multi-GPU sharding of the hot path: one process per GPU, torch.distributed
-for the plumbing (NCCL on GPUs, gloo in the CPU tests).
+"""Multi-GPU sharding of the hot path: one process (or host thread) per GPU over the
+library's own peer windows (include/dvs_b200.h, dvs_comm_*): no NCCL and no torch in the product.
 
-* counting / sketching: records are independent -> each rank counts its own shard, no collective.
-* nmost / max, two modes:
-  - "chunked" (default; the reference's own `-np N` semantics, diverse_seq/records.py:206-251): every
-    rank selects from its own records, the N x n winning rows are all-gathered (n x 4^k f64 per rank)
-    and merged with final_nmost / final_max (src/records.rs:363-382,456-507) - per-GPU work is
-    constant, i.e. true weak scaling;
-  - "union": the per-rank frequency rows (N x 4^k f64) are all-gathered once and every rank replays
-    the single-pass selection on the full row set (numprocs=1 semantics over all records; replicated
-    state, identical results on every rank, no per-step exchange).
-* distance matrices: rows of the symmetric matrix are block-partitioned; each rank computes its
-  row block against all columns and the blocks are all-gathered for the (CPU) clustering.
+* counting: records are independent -> each rank counts its own shard (`count_sharded`); each chunk of
+  frequency rows is pushed to every peer over the copy engines while the next chunk is being counted, so
+  when counting ends every GPU holds the rows of all records.
+* nmost / max: `select_sharded` = the reference's single pass (numprocs=1 semantics, src/records.rs:311-342,
+  390-454) with every window of candidates scored candidate-sharded (position % world) and one 16-byte
+  all-reduce(min) per round over NVLink; the state update is replayed identically on every GPU.
+  `chunked_select` keeps the reference's `-np N` chunk-then-merge semantics (diverse_seq/records.py:206-251,
+  a different result by design) for callers that want to reproduce numprocs > 1 outputs.
+* distance matrices: sketches / rows are all-gathered, the lower triangle is dealt over the GPUs (pairs for
+  mash, 128 x 128 tiles for Euclid) and every kernel stores its results straight into every peer's copy
+  of the matrix.
 
-The functions here only touch torch tensors / python ints so they run unchanged under gloo.
+The only host-side exchange is the rendezvous below (window handles and a few integers over TCP on
+MASTER_ADDR:MASTER_PORT+1, or in-process for ranks that are threads of one process).
 """
 from __future__ import annotations
+
+import os
+import pickle
+import socket
+import struct
+import threading
+import time
 
 import numpy as np
 
@@ -32,171 +40,212 @@ def global_order(seed: int, n_total: int) -> np.ndarray:
     return np.random.default_rng(seed).permutation(n_total).astype(np.uint32)
 
 
-def all_gather_concat(t, group=None):
-    """all-gather equally shaped tensors and concatenate along dim 0 in rank order"""
-    import torch
-    import torch.distributed as dist
-
-    world = dist.get_world_size(group)
-    out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-    dist.all_gather_into_tensor(out, t.contiguous(), group=group) if t.is_cuda else \
-        dist.all_gather(list(out.chunk(world, dim=0)), t.contiguous(), group=group)
-    return out
+# ------------------------------------------------------------------------------ rendezvous ----
+def _send(sock, obj) -> None:
+    data = pickle.dumps(obj, protocol=pickle.HIGHEST_PROTOCOL)
+    sock.sendall(struct.pack("<Q", len(data)) + data)
 
 
-def max_over_ranks(value: float, device=None, group=None) -> float:
-    """timing rule: a multi-GPU duration is the max over ranks"""
-    import torch
-    import torch.distributed as dist
+def _recv(sock):
+    def exactly(n):
+        buf = bytearray()
+        while len(buf) < n:
+            part = sock.recv(n - len(buf))
+            if not part:
+                raise ConnectionError("rendezvous peer closed the connection")
+            buf += part
+        return bytes(buf)
 
-    if not (dist.is_available() and dist.is_initialized()):
-        return float(value)
-    t = torch.tensor([float(value)], dtype=torch.float64, device=device if device is not None else "cpu")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-    return float(t.item())
-
-
-def sum_over_ranks(value: float, device=None, group=None) -> float:
-    import torch
-    import torch.distributed as dist
-
-    if not (dist.is_available() and dist.is_initialized()):
-        return float(value)
-    t = torch.tensor([float(value)], dtype=torch.float64, device=device if device is not None else "cpu")
-    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-    return float(t.item())
+    (n,) = struct.unpack("<Q", exactly(8))
+    return pickle.loads(exactly(n))
 
 
-class DeviceArray:
-    """zero-copy torch view of a raw device pointer owned by libdvs_b200 (via __cuda_array_interface__)"""
+class Rendezvous:
+    """all-gather of small python objects between the ranks over TCP (rank 0 listens); only used to exchange
+    window handles, record counts and the like - never on the data path"""
 
-    def __init__(self, ptr: int, shape: tuple, typestr: str):
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
-                                         "version": 3, "strides": None}
+    def __init__(self, rank: int | None = None, world: int | None = None, addr: str | None = None,
+                 port: int | None = None, timeout: float = 300.0):
+        self.rank = int(os.environ.get("RANK", "0")) if rank is None else int(rank)
+        self.world = int(os.environ.get("WORLD_SIZE", "1")) if world is None else int(world)
+        addr = addr or os.environ.get("MASTER_ADDR", "127.0.0.1")
+        port = int(port if port is not None else int(os.environ.get("MASTER_PORT", "29500")) + 1)
+        self.peers: list = []
+        self.sock = None
+        if self.world == 1:
+            return
+        if self.rank == 0:
+            srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+            srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+            srv.bind((addr if addr not in ("localhost",) else "127.0.0.1", port))
+            srv.listen(self.world)
+            srv.settimeout(timeout)
+            conns = {}
+            while len(conns) < self.world - 1:
+                c, _ = srv.accept()
+                c.settimeout(timeout)
+                conns[_recv(c)] = c
+            srv.close()
+            self.peers = [conns[r] for r in range(1, self.world)]
+        else:
+            deadline = time.time() + timeout
+            while True:
+                try:
+                    s = socket.create_connection((addr, port), timeout=5.0)
+                    break
+                except OSError:
+                    if time.time() > deadline:
+                        raise
+                    time.sleep(0.05)
+            s.settimeout(timeout)
+            _send(s, self.rank)
+            self.sock = s
+
+    def allgather(self, obj) -> list:
+        if self.world == 1:
+            return [obj]
+        if self.rank == 0:
+            out = [obj] + [_recv(c) for c in self.peers]
+            for c in self.peers:
+                _send(c, out)
+            return out
+        _send(self.sock, obj)
+        return _recv(self.sock)
+
+    def barrier(self) -> None:
+        self.allgather(None)
+
+    def close(self) -> None:
+        for c in self.peers:
+            c.close()
+        if self.sock is not None:
+            self.sock.close()
+        self.peers, self.sock = [], None
 
 
-def kfreqs_as_tensors(kf, device):
-    """(rows [nrec, dim] f64, entropies [nrec] f64, valid [nrec] u8) torch views of a KFreqs"""
-    import torch
+class LocalGroup:
+    """the same exchange for ranks that are THREADS of one process (tests: several ranks on one GPU, or one
+    thread per GPU): `group.member(rank)` has the Rendezvous interface"""
 
-    rows_p, ent_p, val_p = kf.device_ptrs()
-    n, d = kf.nrec, kf.dim
-    rows = torch.as_tensor(DeviceArray(rows_p, (n, d), "<f8"), device=device)
-    ent = torch.as_tensor(DeviceArray(ent_p, (n,), "<f8"), device=device)
-    valid = torch.as_tensor(DeviceArray(val_p, (n,), "|u1"), device=device)
-    return rows, ent, valid
+    def __init__(self, world: int):
+        self.world = world
+        self._bar = threading.Barrier(world)
+        self._slots = [None] * world
+
+    def member(self, rank: int) -> "_LocalMember":
+        return _LocalMember(self, rank)
 
 
-def all_gather_kfreqs(ctx, kf, device, group=None):
-    """every rank ends up with a KFreqs holding the rows of all ranks, in rank order"""
-    import torch
+class _LocalMember:
+    def __init__(self, group: LocalGroup, rank: int):
+        self.group, self.rank, self.world = group, rank, group.world
 
+    def allgather(self, obj) -> list:
+        g = self.group
+        g._slots[self.rank] = obj
+        g._bar.wait()
+        out = list(g._slots)
+        g._bar.wait()
+        return out
+
+    def barrier(self) -> None:
+        self.group._bar.wait()
+
+    def close(self) -> None:
+        pass
+
+
+def connect(ctx, rv, window_bytes: int):
+    """create this rank's peer window and map everybody else's (collective over the rendezvous `rv`)"""
     from . import _lib
 
-    rows, ent, valid = kfreqs_as_tensors(kf, device)
-    ctx.sync()  # the rows were produced on the library's stream
-    g_rows = all_gather_concat(rows, group)
-    g_ent = all_gather_concat(ent, group)
-    g_valid = all_gather_concat(valid, group)
-    torch.cuda.synchronize(device)
-    return _lib.KFreqs.from_device(ctx, g_rows.data_ptr(), g_ent.data_ptr(), g_valid.data_ptr(),
-                                   g_rows.shape[0], g_rows.shape[1])
+    comm = _lib.Comm(ctx, rv.rank, rv.world, int(window_bytes))
+    comm.connect(rv.allgather(comm.blob))
+    comm.rv = rv
+    return comm
 
 
-def chunked_select(ctx, kf, local_order, mode: int, min_size: int, max_size: int, device, group=None):
-    """The reference's multi-process selection with one chunk per GPU: select locally, all-gather the
-    winners' rows, merge with final_nmost / final_max on every rank (identical results everywhere).
+def window_bytes_for(nrec_total: int, dim: int, extra: int = 0) -> int:
+    """a window that holds the rows of all records (+ their scalars) and `extra` bytes of other objects"""
+    return int(nrec_total * (dim * 8 + 64) + extra + (64 << 20))
 
-    Returns (global ids, delta_jsd, stats5); a global id is rank * kf.nrec + local row."""
-    import torch
-    import torch.distributed as dist
 
+# --------------------------------------------------------------------------------- counting ----
+def count_sharded(ctx, comm, seqset_local, k: int, num_states: int = 4):
+    """(kfreqs with the rows of ALL ranks in rank-major order, records per rank)"""
     from . import _lib
 
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
-    idx, _delta, _stats = kf.select(local_order, mode, min_size, max_size)
-    cap = max(int(min_size), int(max_size))
-    won = kf.take_rows(idx)
-    rows, _ent, _valid = kfreqs_as_tensors(won, device)
-    pad = torch.zeros((cap, kf.dim), dtype=torch.float64, device=device)
-    pad[: rows.shape[0]] = rows
-    ids = torch.full((cap,), -1, dtype=torch.int64, device=device)
-    ids[: len(idx)] = torch.from_numpy(idx.astype(np.int64) + rank * kf.nrec).to(device)
-    ctx.sync()
-    g_rows = all_gather_concat(pad, group)
-    g_ids = all_gather_concat(ids, group)
-    torch.cuda.synchronize(device)
-    keep = torch.nonzero(g_ids >= 0).flatten()
-    g_rows = g_rows[keep].contiguous()
-    g_ids = g_ids[keep].cpu().numpy()
-    # final_*: entropies recomputed from the stored rows (KmerSeq::new), examined in concatenation order
-    merged = _lib.KFreqs.from_device(ctx, g_rows.data_ptr(), None, None, g_rows.shape[0], g_rows.shape[1])
-    order = np.arange(g_rows.shape[0], dtype=np.uint32)
-    midx, mdelta, mstats = merged.select(order, mode, min_size, max_size)
-    return g_ids[midx], mdelta, mstats
+    nrec = comm.rv.allgather(int(seqset_local.nrec))
+    return _lib.KFreqs.count_sharded(ctx, comm, seqset_local, k, nrec, num_states), nrec
 
 
-def row_blocks(n: int, world: int, align: int = 128) -> list[tuple[int, int]]:
-    """block partition of the rows of an n x n matrix; block starts are multiples of `align` (the
-    Euclidean kernel mirrors tiles only when its row range is tile aligned)"""
-    per = -(-n // world)
-    per = -(-per // align) * align
-    return [(min(n, r * per), min(n, (r + 1) * per)) for r in range(world)]
+def interleaved_order(local_orders, nrec_per_rank) -> np.ndarray:
+    """a global examination order over the rank-major rows of all ranks in which consecutive positions
+    come from different ranks (block-cyclic by position): position world*i + r is the i-th
+    record of rank r's own order; shorter ranks simply run out first"""
+    world = len(nrec_per_rank)
+    base = np.concatenate([[0], np.cumsum(nrec_per_rank)]).astype(np.int64)
+    longest = max(len(o) for o in local_orders) if world else 0
+    grid = np.full((longest, world), -1, dtype=np.int64)
+    for r, o in enumerate(local_orders):
+        grid[: len(o), r] = np.asarray(o, dtype=np.int64) + base[r]
+    flat = grid.reshape(-1)
+    return flat[flat >= 0].astype(np.uint32)
 
 
-def gather_row_blocks(local_rows: np.ndarray, n: int, device, group=None) -> np.ndarray:
-    """all-gather the per-rank row blocks of an n x n matrix (ctree's distance matrix) -> full matrix on
-    every rank (`ncclAllGather` of row blocks before the CPU clustering)"""
-    import torch
-    import torch.distributed as dist
-
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
-    blocks = row_blocks(n, world)
-    per = max(e - b for b, e in blocks)
-    pad = torch.zeros((per, n), dtype=torch.float64, device=device)
-    b, e = blocks[rank]
-    if e > b:
-        pad[: e - b] = torch.from_numpy(np.ascontiguousarray(local_rows)).to(device)
-    full = all_gather_concat(pad, group)
-    out = np.empty((n, n), dtype=np.float64)
-    for r, (b, e) in enumerate(blocks):
-        if e > b:
-            out[b:e] = full[r * per: r * per + (e - b)].cpu().numpy()
-    return out
+def select_sharded(ctx, comm, kf_all, order, mode: int, min_size: int, max_size: int = 0):
+    """single-pass selection over all rows, candidate-sharded (identical result on every rank)"""
+    return kf_all.select_sharded(comm, order, mode, min_size, max_size)
 
 
-def sharded_mash_distances(ctx, seqset_local, k: int, sketch_size: int, num_states: int, canonical: bool, device,
-                           group=None):
-    """ctree mash on N GPUs: every rank sketches its own records, the sketches are all-gathered
-    (records are rank-ordered), every rank computes its row block of the matrix, blocks are gathered."""
-    import torch
-    import torch.distributed as dist
+def chunked_select(ctx, comm, kf_local, local_order, mode: int, min_size: int, max_size: int):
+    """The reference's multi-process selection with one chunk per GPU (-np N semantics,
+    diverse_seq/records.py:206-251): select locally, gather the winners' rows, merge with final_nmost /
+    final_max on every rank (src/records.rs:363-382, 456-507: entropies recomputed from the stored rows).
 
+    Returns ((rank, local row) of every selected record, delta_jsd, stats5)."""
     from . import _lib
 
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    idx, _delta, _stats = kf_local.select(local_order, mode, min_size, max_size)
+    won = kf_local.take_rows(idx)
+    counts = comm.rv.allgather(int(len(idx)))
+    ids = comm.rv.allgather([(comm.rank, int(r)) for r in idx])
+    gathered = won.allgather(comm, counts)
+    rows_p, _e, _v = gathered.device_ptrs()
+    merged = _lib.KFreqs.from_device(ctx, rows_p, None, None, gathered.nrec, gathered.dim)  # KmerSeq::new: H recomputed
+    flat_ids = [x for part in ids for x in part]
+    midx, mdelta, mstats = merged.select(np.arange(gathered.nrec, dtype=np.uint32), mode, min_size, max_size)
+    merged.close()
+    gathered.close()
+    won.close()
+    return [flat_ids[i] for i in midx], mdelta, mstats
+
+
+# -------------------------------------------------------------------------------- distances ----
+def sharded_mash_distances(ctx, comm, seqset_local, k: int, sketch_size: int, num_states: int = 4,
+                           canonical: bool = False) -> np.ndarray:
+    """ctree mash on N GPUs: every rank sketches its own records, the sketches are all-gathered over NVLink,
+    the pairs of the lower triangle are dealt over the GPUs and each kernel stores its distances into every
+    peer's copy of the matrix; returns the full matrix (rank-major record order) on every rank"""
+    from . import _lib
+
     sk = _lib.Sketches.sketch(ctx, seqset_local, k, sketch_size, num_states, canonical)
-    data, lens = sk.download()
-    stride = torch.tensor([data.shape[1]], dtype=torch.int64, device=device)
-    dist.all_reduce(stride, op=dist.ReduceOp.MAX, group=group)
-    wide = np.zeros((data.shape[0], int(stride.item())), dtype=np.uint32)
-    wide[:, : data.shape[1]] = data
-    g_data = all_gather_concat(torch.from_numpy(wide.view(np.int32)).to(device), group).cpu().numpy().view(np.uint32)
-    g_lens = all_gather_concat(torch.from_numpy(lens.view(np.int32)).to(device), group).cpu().numpy().view(np.uint32)
-    allsk = _lib.Sketches.from_host(ctx, g_data, g_lens)
-    n = allsk.nrec
-    b, e = row_blocks(n, world)[rank]
-    local = allsk.distances(k, sketch_size, b, e) if e > b else np.zeros((0, n))
-    return gather_row_blocks(local, n, device, group)
+    meta = comm.rv.allgather((int(sk.nrec), int(sk.stride)))
+    allsk = sk.allgather(comm, [m[0] for m in meta], max(m[1] for m in meta))
+    out = allsk.distances_sharded(comm, k, sketch_size)
+    allsk.close()
+    sk.close()
+    return out
 
 
-def sharded_euclidean(ctx, kf_local, device, group=None):
-    """ctree Euclidean on N GPUs: all-gather the frequency rows, row block per rank, gather blocks"""
-    import torch.distributed as dist
-
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
-    allf = all_gather_kfreqs(ctx, kf_local, device, group)
-    n = allf.nrec
-    b, e = row_blocks(n, world)[rank]
-    local = allf.euclidean(b, e) if e > b else np.zeros((0, n))
-    return gather_row_blocks(local, n, device, group)
+def sharded_euclidean(ctx, comm, kf_local=None, kf_all=None) -> np.ndarray:
+    """ctree Euclidean on N GPUs: all-gather the frequency rows (or take them from count_sharded), deal the
+    128 x 128 tiles of the lower triangle over the GPUs, results stored into every peer's matrix"""
+    own = kf_all is None
+    if own:
+        nrec = comm.rv.allgather(int(kf_local.nrec))
+        kf_all = kf_local.allgather(comm, nrec)
+    out = kf_all.euclidean_sharded(comm)
+    if own:
+        kf_all.close()
+    return out

@@ -54,6 +54,13 @@ void dvs_ctx_destroy(dvs_ctx* ctx);
 int dvs_ctx_sync(dvs_ctx* ctx);
 /* the CUDA stream (cudaStream_t) every kernel of this ctx is launched on, for event timing */
 void* dvs_ctx_stream(dvs_ctx* ctx);
+/* plain device / pinned host buffers for host code without another CUDA binding (distance matrices that stay on
+ * the device, pinned staging of sequences); dvs_device_memcpy copies in any direction and waits */
+int dvs_device_malloc(dvs_ctx* ctx, uint64_t bytes, void** out);
+void dvs_device_free(dvs_ctx* ctx, void* p);
+int dvs_device_memcpy(dvs_ctx* ctx, void* dst, const void* src, uint64_t bytes);
+int dvs_host_malloc_pinned(uint64_t bytes, void** out);
+void dvs_host_free_pinned(void* p);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 uint64_t dvs_ctx_launch_count(dvs_ctx* ctx);
 
@@ -84,6 +91,9 @@ int dvs_seqset_upload(dvs_ctx* ctx, const uint8_t* seqs, const uint64_t* offsets
  * [mean_len*0.75, mean_len*1.25].  dvs_synth_host() is the bit-identical host generator. */
 int dvs_seqset_synth(dvs_ctx* ctx, uint64_t seed, uint32_t nrec, uint32_t nfam, uint64_t mean_len,
                      dvs_seqset** out);
+/* records [first, first + nrec) of the same generator (one set split over several GPUs) */
+int dvs_seqset_synth_range(dvs_ctx* ctx, uint64_t seed, uint32_t first, uint32_t nrec, uint32_t nfam, uint64_t mean_len,
+                           dvs_seqset** out);
 int dvs_synth_host(uint64_t seed, uint32_t nrec, uint32_t nfam, uint64_t mean_len, uint32_t first,
                    uint32_t count, uint8_t* seqs_out, uint64_t* offsets_out);
 int dvs_synth_lengths(uint64_t seed, uint32_t nrec, uint64_t mean_len, uint64_t* lens_out);
@@ -215,6 +225,59 @@ int dvs_euclid_distances(dvs_ctx* ctx, const dvs_kfreqs* f, uint32_t row_begin, 
  * cluster size per row. */
 int dvs_linkage_average(dvs_ctx* ctx, const double* dist, uint32_t n, int32_t* children, double* heights,
                         uint32_t* counts);
+
+/* ---- multi-GPU: peer windows over NVLink -------------------------------------
+ * One process (or host thread) per GPU, no NCCL and no torch in the data path.  Every rank owns a WINDOW (one
+ * cudaMalloc'ed block) that all peers map (cudaIpc across processes, the raw pointer inside one process);
+ * its head holds control words (barrier / arrival flags, the selection kernels' exchange slots), the rest is
+ * a symmetric heap.  Set-up is two steps around ONE host-side exchange of DVS_COMM_HANDLE_BYTES per rank
+ * over any transport (diverseseq_b200/shard.py uses a TCP rendezvous on MASTER_ADDR:MASTER_PORT):
+ *   dvs_comm_create   allocate this rank's window, describe it in handle_out
+ *   dvs_comm_connect  handles = the `world` blobs in rank order; maps every peer
+ * All ranks must call the collective entry points (barrier, allgatherv, *_sharded) in the same order.
+ * Device-side waits give up after 20 s (a missing rank becomes DVS_ERR_CUDA instead of a hang). */
+typedef struct dvs_comm dvs_comm;
+#define DVS_COMM_HANDLE_BYTES 128
+int dvs_comm_create(dvs_ctx* ctx, int rank, int world, uint64_t window_bytes, dvs_comm** out, void* handle_out);
+int dvs_comm_connect(dvs_ctx* ctx, dvs_comm* c, const void* handles /* world x DVS_COMM_HANDLE_BYTES */);
+int dvs_comm_rank(const dvs_comm* c);
+int dvs_comm_world(const dvs_comm* c);
+int dvs_comm_barrier(dvs_ctx* ctx, dvs_comm* c);
+/* all-gather of device buffers of different sizes: rank r contributes bytes_per_rank[r] bytes from d_src;
+ * d_dst (device, sum of the sizes) receives them in rank order.  The window must hold the largest piece. */
+int dvs_comm_allgatherv(dvs_ctx* ctx, dvs_comm* c, const void* d_src, const uint64_t* bytes_per_rank, void* d_dst);
+void dvs_comm_destroy(dvs_comm* c);
+
+/* Rows of ALL ranks in one kfreqs on every rank (rank-major: rank 0's records first), stored in the
+ * symmetric heap of the window.  nrec_per_rank[world] = records held by each rank (the host exchanges these
+ * counts; they may differ).  dvs_count_kmers_sharded counts this rank's records in chunks and pushes each
+ * chunk's rows to the peers over the copy engines while the next chunk is being counted (prep sharded by
+ * record); dvs_kfreqs_allgather does the same for rows that already exist.  The result
+ * carries entropies, validity and the reference's panic flags of every record; it holds no counts.  Free it
+ * with dvs_kfreqs_free BEFORE dvs_comm_destroy. */
+int dvs_count_kmers_sharded(dvs_ctx* ctx, dvs_comm* c, const dvs_seqset* local, int k, int num_states,
+                            const uint32_t* nrec_per_rank, dvs_kfreqs** out_all);
+int dvs_kfreqs_allgather(dvs_ctx* ctx, dvs_comm* c, const dvs_kfreqs* local, const uint32_t* nrec_per_rank,
+                         dvs_kfreqs** out_all);
+/* dvs_select over the rows of all ranks with the scan CANDIDATE-SHARDED over the GPUs:
+ * the single-pass, numprocs=1 semantics of src/records.rs:311-342 / :390-454 - NOT the -np chunk merge.  Every
+ * rank passes the same f_all (from dvs_count_kmers_sharded / dvs_kfreqs_allgather), order and arguments and
+ * receives the same result.  Each GPU scores the window positions p with p % world == rank; per round the
+ * leaders all-reduce(min) {first_true, first_unsure} through 16-byte tagged slots in the peer windows (one
+ * NVLink store per peer and round); the state update is replayed identically on every GPU. */
+/* ctree on several GPUs.  Sketches of all ranks on every rank (stride_all = the largest
+ * dvs_sketches_stride of any rank); then the pairs of the lower triangle (mash) / its 128 x 128 tiles (Euclid)
+ * are dealt over the GPUs round-robin and every kernel stores its distances straight into the matrix of EVERY
+ * GPU through the peer windows (compute and all-gather in one kernel).  dist: n x n f64, host or device; every
+ * rank receives the whole matrix (the row order is the rank-major record order). */
+int dvs_sketches_allgather(dvs_ctx* ctx, dvs_comm* c, const dvs_sketches* local, const uint32_t* nrec_per_rank,
+                           uint32_t stride_all, dvs_sketches** out_all);
+int dvs_mash_distances_sharded(dvs_ctx* ctx, dvs_comm* c, const dvs_sketches* sk_all, int k, uint64_t sketch_size,
+                               double* dist);
+int dvs_euclid_distances_sharded(dvs_ctx* ctx, dvs_comm* c, const dvs_kfreqs* f_all, double* dist);
+int dvs_select_sharded(dvs_ctx* ctx, dvs_comm* c, const dvs_kfreqs* f_all, const uint32_t* order, uint32_t num,
+                       int mode, uint32_t min_size, uint32_t max_size, uint32_t* sel_idx, double* sel_delta,
+                       double* stats5, uint32_t* size_out);
 
 /* ---- test hooks ---------------------------------------------------------------------------- */
 /* host half of the packed upload (transfer encoding, no GPU needed): packs src[0..n) 4 bases per

@@ -532,44 +532,6 @@ def test_euclidean(lib, ctx, orc, brca1, k):
     assert np.array_equal(kf.euclidean(0, 1), got[0:1])
 
 
-# ------------------------------------------------------------- multi-GPU plumbing (1 rank) ----
-
-def test_chunked_select_world1_matches_oracle(lib, ctx, orc):
-    """shard.chunked_select (reference -np semantics: select per chunk, final_nmost merge) on a
-    1-rank NCCL group; with 2+ GPUs the same code gathers every rank's winners"""
-    import socket
-    import torch
-    import torch.distributed as dist
-    from diverseseq_b200 import shard
-
-    with socket.socket() as s:
-        s.bind(("127.0.0.1", 0))
-        port = s.getsockname()[1]
-    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1,
-                            device_id=torch.device("cuda", 0))
-    try:
-        flat, off = lib.synth_host(5, 300, 6, 4000)
-        kf = lib.KFreqs.count(ctx, lib.SeqSet.upload(ctx, flat, off), 4)
-        order = shard.global_order(11, 300)
-        ids, delta, stats = shard.chunked_select(ctx, kf, order, lib.MODE_NMOST, 12, 12, torch.device("cuda", 0))
-        _, of, oe, ov = orc.count_batch(flat, off, 4)
-        first = orc.select_rows(of, oe, order, "nmost", 12, valid=ov, want_freqs=True)
-        merged = orc.select_rows(first.kfreqs, None, np.arange(12), "nmost", 12, recompute_entropy=True)
-        assert ids.tolist() == first.ids[merged.ids].tolist()
-        assert np.array_equal(delta, merged.delta_jsd) and stats[0] == merged.total_jsd
-        # union mode plumbing: gather (1 rank) + device-to-device adoption keeps rows bit-identical
-        allf = shard.all_gather_kfreqs(ctx, kf, torch.device("cuda", 0))
-        i2, d2, s2 = allf.select(order, lib.MODE_NMOST, 12)
-        assert i2.tolist() == first.ids.tolist() and np.array_equal(d2, first.delta_jsd)
-        # ctree matrices through the sharded helpers (row blocks + gather) == the single-call matrices
-        ss = lib.SeqSet.upload(ctx, flat, off)
-        full_mash = lib.Sketches.sketch(ctx, ss, 8, 64, 4, True).distances(8, 64)
-        assert np.array_equal(shard.sharded_mash_distances(ctx, ss, 8, 64, 4, True, torch.device("cuda", 0)), full_mash)
-        assert np.array_equal(shard.sharded_euclidean(ctx, kf, torch.device("cuda", 0)), kf.euclidean())
-    finally:
-        dist.destroy_process_group()
-
-
 def test_dvs_on_disk_store_matches_in_memory(tmp_path, brca1, orc):
     """`.dvseqsz` directory store (threaded zstd decode -> pinned staging -> GPU) == in-memory store"""
     from diverseseq_b200 import _dvs as dvs, dvseqsz, _lib
