@@ -328,7 +328,7 @@ k_count(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offsets, 
 // window fall back to single k-mers in the side table (per-byte path); a record that ends before its
 // last triplet completes flushes the pending k-mers at its last byte, so the block holding the last
 // byte always takes the per-byte path when end % 3 != 0.
-template <bool SCR, int THREADS>
+template <bool SCR, int THREADS, int PF>
 __global__ void __launch_bounds__(THREADS, 1)
 k_count_s3(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offsets, const CountWork* __restrict__ work,
            uint32_t nwork, uint32_t* __restrict__ next_item, int k, uint64_t dim, uint32_t* __restrict__ counts,
@@ -391,9 +391,9 @@ k_count_s3(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offset
         bool carry_ok = false;
         // phase of the lane's block start (absolute position mod 3); 16 == 1 and 512 == 2 (mod 3)
         uint32_t ph = (uint32_t)((w.begin + r0 + 16ull * lane) % 3ull);
-        uint4 ring[kPrefetch];
+        uint4 ring[PF];
 #pragma unroll
-        for (int u = 0; u < kPrefetch; ++u) {
+        for (int u = 0; u < PF; ++u) {
             const uint32_t a = r0 + 512u * u + 16 * lane;
             ring[u] = (a < r1) ? ldg16(base + a) : make_uint4(~0u, ~0u, ~0u, ~0u);
         }
@@ -403,9 +403,9 @@ k_count_s3(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offset
             carry_ok = (((h.x | h.y | h.z | h.w) & 0xFCFCFCFCu) == 0) && (a0 >= start + 16) && (a0 <= end);
             carry_pc = pack16p(h);
         }
-        for (uint32_t rbase = r0; rbase < r1; rbase += 512u * kPrefetch) {
+        for (uint32_t rbase = r0; rbase < r1; rbase += 512u * PF) {
 #pragma unroll
-          for (int u = 0; u < kPrefetch; ++u) {
+          for (int u = 0; u < PF; ++u) {
             const uint32_t r = rbase + 512u * u;
             if (r >= r1) break;  // warp-uniform
             const uint32_t a = r + 16 * lane;
@@ -417,7 +417,7 @@ k_count_s3(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offset
             const uint32_t pc = pack16p(cur);
             // refill the slot only now: in the common path `cur` is dead from here on, so the load lands in
             // the same registers without a copy (the per-byte path re-reads its 32 bytes)
-            ring[u] = (a + 512u * kPrefetch < r1) ? ldg16(base + a + 512u * kPrefetch) : make_uint4(~0u, ~0u, ~0u, ~0u);
+            ring[u] = (a + 512u * PF < r1) ? ldg16(base + a + 512u * PF) : make_uint4(~0u, ~0u, ~0u, ~0u);
             uint32_t pp = __shfl_up_sync(kFull, pc, 1);
             if (lane == 0) pp = carry_pc;
             const uint32_t okmask = __ballot_sync(kFull, ok);
@@ -825,14 +825,21 @@ static int count_core(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, 
                 // The 8-mer table spreads over 32,768 words: bank scrambling costs two instructions per atomic
                 // and buys nothing here unless asked for (DVS_COUNT_SCRAMBLE=1)
                 const bool scr3 = scr_env && scr_env[0] == '1';
-                auto s3 = scr3 ? k_count_s3<true, 1024> : k_count_s3<false, 1024>;
+                // DVS_COUNT_S3_SHAPE (A/B measurements): 0 = 1024 threads x 4 steps in flight (64 registers),
+                // 1 = 512 threads x 8 steps, 2 = 512 threads x 4 steps
+                const char* shape_env = getenv("DVS_COUNT_S3_SHAPE");
+                const int shape = shape_env ? atoi(shape_env) : 0;
+                auto s3 = scr3 ? k_count_s3<true, 1024, 4>
+                               : (shape == 1 ? k_count_s3<false, 512, 8>
+                                             : (shape == 2 ? k_count_s3<false, 512, 4> : k_count_s3<false, 1024, 4>));
+                const int s3_threads = (!scr3 && (shape == 1 || shape == 2)) ? 512 : 1024;
                 auto rk = scramble ? k_count<MODE_SUPER, true, 512> : k_count<MODE_SUPER, false, 512>;
                 TRY_F(cudaFuncSetAttribute(s3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
                 const size_t retry_bytes = (size_t)dim * 20;
                 if (retry_bytes > 48 * 1024)
                     TRY_F(cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)retry_bytes));
                 uint32_t* rc2 = d_rc.p + 2 * ch;
-                s3<<<g, 1024, hist_bytes, st>>>(s->data(), s->offsets.p, d_work, n_work, d_nx, k, dim, d_counts,
+                s3<<<g, s3_threads, hist_bytes, st>>>(s->data(), s->offsets.p, d_work, n_work, d_nx, k, dim, d_counts,
                                                 d_retry.p + ib, rc2);
                 ctx->launches++;
                 e = cudaGetLastError();
