@@ -146,6 +146,181 @@ k_mash_filter(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ off
     }
 }
 
+// ---- k = 16, num_states = 4: the ctree default (diverse_seq/cluster.py), rebuilt around the pipe balance ----
+// k_mash_filter spends 5 ALU-pipe + 3 FMA-pipe instructions per hash round and is ALU bound (ncu: ALU pipe
+// 91 %, FMA pipe 39 %).  Here
+//   * the per-base term rotl(b*C1,15)*C2 depends on the base alone: it is looked up ONCE per sequence position
+//     (31 positions serve the 16 windows of a lane's block) from a 4-entry shared-memory table, for the base and
+//     for its complement, instead of being recomputed in every round of every window;
+//   * a round is then  h ^= t;  h = rotl(h,13)*5 + c.  The rotate is taken off the ALU pipe in two rounds out of
+//     three: h * 2^13 as a 64-bit product gives (h << 13, h >> 19) in one IMAD.WIDE, and
+//     rotl*5 + c = lo*5 + (hi*5 + c) is two more IMADs (the multiplier 2^13 comes from a kernel argument so
+//     that the compiler cannot turn the product back into shifts);
+//   * canonical k-mers: the reverse complement of the whole 31-base string is formed once, every window's
+//     reverse complement is one funnel shift of it, and the rounds pick the forward or the complemented term
+//     with one SEL.
+// Same hash values bit for bit (distance.rs:21-87); blocks with an invalid byte or a record edge go through
+// hash_packed like before.
+template <bool CANON>
+__global__ void __launch_bounds__(kMashThreads)
+k_mash_filter16(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offsets, const MashWork* __restrict__ work,
+                uint32_t nwork, uint32_t* __restrict__ next_item, const MashActive* __restrict__ active,
+                uint32_t* __restrict__ cnt, unsigned long long* __restrict__ keys, uint32_t two13) {
+    __shared__ uint32_t s_item;
+    __shared__ uint2 s_T[4];  // {term of base b, term of its complement b ^ 2}
+    const int tid = threadIdx.x;
+    if (tid < 4) {
+        auto term = [](uint32_t b) { return rotl32(b * 0xCC9E2D51u, 15) * 0x1B873593u; };
+        s_T[tid] = make_uint2(term((uint32_t)tid), term((uint32_t)tid ^ 2u));
+    }
+    __syncthreads();
+    constexpr int k = 16;
+    auto revpairs = [](uint32_t x) {  // complement + reverse the base order of 16 packed bases
+        uint32_t r = __brev(x ^ 0xAAAAAAAAu);
+        return ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
+    };
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(next_item, 1u);
+        __syncthreads();
+        const uint32_t item = s_item;
+        __syncthreads();
+        if (item >= nwork) break;
+        const MashWork w = work[item];
+        const MashActive act = active[w.slot];
+        const uint64_t start = offsets[w.rec], end = offsets[w.rec + 1];
+        for (uint64_t a = w.begin + (uint64_t)tid * 16; a < w.end; a += (uint64_t)kMashThreads * 16) {
+            const uint4 cur = __ldg(reinterpret_cast<const uint4*>(seqs + a));
+            const uint4 prev = __ldg(reinterpret_cast<const uint4*>(seqs + a - 16));
+            uint32_t any = cur.x | cur.y | cur.z | cur.w | prev.x | prev.y | prev.z | prev.w;
+            const bool fast = ((any & 0xFCFCFCFCu) == 0) && (a >= start + 16) && (a + 16 <= end);
+            if (fast) {
+                // terms of the 31 positions q = 0..30 (q = 15 + byte index of the block; the halo is q < 15)
+                const uint32_t wv[8] = {prev.x, prev.y, prev.z, prev.w, cur.x, cur.y, cur.z, cur.w};
+                uint32_t tf[31], tr[31];
+#pragma unroll
+                for (int q = 0; q < 31; ++q) {
+                    const int bi = q + 1;  // byte index inside the 32 loaded bytes
+                    const uint32_t b = (wv[bi >> 2] >> (8 * (bi & 3))) & 0xFFu;
+                    const uint2 t = s_T[b];
+                    tf[q] = t.x;
+                    tr[q] = t.y;
+                }
+                const uint32_t pc = mpack16(cur), pp = mpack16(prev);
+                uint32_t ylo = 0, yhi = 0;
+                if (CANON) {  // reverse complement of the 32-base string pp:pc
+                    ylo = revpairs(pp);
+                    yhi = revpairs(pc);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    bool use_rc = false;
+                    if (CANON) {
+                        const uint32_t v = j == 15 ? pc : __funnelshift_r(pc, pp, 2 * (15 - j));
+                        const uint32_t rc = j == 15 ? yhi : __funnelshift_r(ylo, yhi, 2 * (j + 1));
+                        use_rc = rc < v;  // ties keep the k-mer itself
+                    }
+                    uint32_t h = 0x9747B28Cu ^ (uint32_t)k;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const uint32_t t = CANON ? (use_rc ? tr[j + 15 - i] : tf[j + i]) : tf[j + i];
+                        h ^= t;
+                        if (i % 3 != 2) {  // rotl(h,13)*5 + c on the FMA pipe
+                            const unsigned long long wide = (unsigned long long)h * two13;
+                            const uint32_t lo = (uint32_t)wide, hi = (uint32_t)(wide >> 32);
+                            h = lo * 5u + (hi * 5u + 0xE6546B64u);
+                        } else {
+                            h = rotl32(h, 13) * 5u + 0xE6546B64u;
+                        }
+                    }
+                    mash_emit(mm_fmix(h), act, w.slot, cnt, keys);
+                }
+            } else {
+                const uint32_t wv[8] = {prev.x, prev.y, prev.z, prev.w, cur.x, cur.y, cur.z, cur.w};
+                uint32_t run = 0, v = 0;
+#pragma unroll 1
+                for (int i = 0; i < 32; ++i) {
+                    const uint64_t p = a - 16 + i;
+                    uint32_t b = (wv[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+                    if (p < start || p >= end) b = 0xFFu;
+                    if (b >= 4u) {
+                        run = 0;
+                        v = 0;
+                    } else {
+                        v = (v << 2) | b;
+                        ++run;
+                        if (i >= 16 && run >= (uint32_t)k) mash_emit(hash_packed(v, k, CANON), act, w.slot, cnt, keys);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---- per-record sort + unique + bottom-s in shared memory ----------------------------------------------------
+// The threshold leaves ~2s + 512 candidates per record; one CTA sorts them in shared memory (bitonic, u32),
+// drops duplicates and writes the first s - instead of one global bitonic network over the padded key buffer of
+// all records (~30 launches over 16 M keys for 1,000 genomes).  A record with more than kSortRecMax candidates
+// (a widened threshold, sketch_size = "all") is left to the global path.
+constexpr unsigned kSortRecMax = 32768;
+constexpr unsigned kSortRecThreads = 1024;
+__global__ void __launch_bounds__(kSortRecThreads)
+k_mash_sort_record(const unsigned long long* __restrict__ keys, const MashActive* __restrict__ active,
+                   const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ slot_rec, uint64_t sketch_size,
+                   uint32_t stride, uint32_t* __restrict__ sketches, uint32_t* __restrict__ lens,
+                   uint32_t* __restrict__ ndistinct) {
+    extern __shared__ uint32_t s_h[];
+    __shared__ unsigned s_warp[kSortRecThreads / 32];
+    __shared__ unsigned s_base;
+    const unsigned slot = blockIdx.x, t = threadIdx.x;
+    const MashActive act = active[slot];
+    const unsigned n = min(cnt[slot], act.cap);
+    if (n > kSortRecMax) return;  // (the host has seen the same count and sends this launch's records elsewhere)
+    unsigned P = 2;
+    while (P < n) P <<= 1;
+    for (unsigned i = t; i < P; i += kSortRecThreads) s_h[i] = i < n ? (uint32_t)keys[act.base + i] : 0xFFFFFFFFu;
+    __syncthreads();
+    for (unsigned kk = 2; kk <= P; kk <<= 1)
+        for (unsigned j = kk >> 1; j > 0; j >>= 1) {
+            for (unsigned q = t; q < P / 2; q += kSortRecThreads) {
+                const unsigned i = 2 * q - (q & (j - 1));
+                const uint32_t x = s_h[i], y = s_h[i + j];
+                if ((x > y) == ((i & kk) == 0)) {
+                    s_h[i] = y;
+                    s_h[i + j] = x;
+                }
+            }
+            __syncthreads();
+        }
+    // the first n elements are the record's candidates in ascending order (padding sorts last)
+    const uint32_t rec = slot_rec[slot];
+    uint32_t* out = sketches + (size_t)rec * stride;
+    const uint64_t want = min(sketch_size, (uint64_t)stride);
+    if (t == 0) s_base = 0;
+    __syncthreads();
+    for (unsigned c = 0; c < n; c += kSortRecThreads) {
+        const unsigned i = c + t;
+        const unsigned flag = (i < n) && (i == 0 || s_h[i - 1] != s_h[i]);
+        const unsigned lane = t & 31, wid = t >> 5;
+        const unsigned bal = __ballot_sync(0xffffffffu, flag);
+        if (lane == 0) s_warp[wid] = __popc(bal);
+        __syncthreads();
+        unsigned woff = 0, tot = 0;
+        for (unsigned wdx = 0; wdx < kSortRecThreads / 32; ++wdx) {
+            if (wdx < wid) woff += s_warp[wdx];
+            tot += s_warp[wdx];
+        }
+        const unsigned pos = s_base + woff + __popc(bal & ((1u << lane) - 1u));
+        if (flag && pos < want) out[pos] = s_h[i];
+        __syncthreads();
+        if (t == 0) s_base += tot;
+        __syncthreads();
+    }
+    if (t == 0) {
+        ndistinct[slot] = s_base;
+        lens[rec] = (uint32_t)min((uint64_t)s_base, want);
+    }
+}
+
 // generic path (any num_states, any k): one thread per window start, bytes re-read from L1/L2
 __global__ void __launch_bounds__(kMashThreads)
 k_mash_filter_generic(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offsets,
@@ -420,6 +595,22 @@ __global__ void k_mash_pairs_tri(const uint32_t* __restrict__ sk, const uint32_t
     }
 }
 
+// the global sort path needs sentinels (all ones, they sort last) in every key slot that holds no candidate:
+// the tail of each record's region and the padding behind the last region
+__global__ void k_mash_pad_keys(unsigned long long* __restrict__ keys, size_t npad, const MashActive* __restrict__ active,
+                                const uint32_t* __restrict__ cnt, uint32_t na) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npad; i += (size_t)gridDim.x * blockDim.x) {
+        // region containing i: the last record whose base <= i
+        uint32_t lo = 0, hi = na;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (active[mid].base <= i) lo = mid; else hi = mid;
+        }
+        const size_t off = i - active[lo].base;
+        if (off >= min(cnt[lo], active[lo].cap)) keys[i] = ~0ull;
+    }
+}
+
 static int bitonic_sort(dvs_ctx* ctx, unsigned long long* keys, size_t n) {
     cudaStream_t st = ctx->stream;
     k_bitonic_tiles<<<(unsigned)(n / kSortTile), kSortTile / 2, 0, st>>>(keys);
@@ -524,14 +715,24 @@ int dvs_mash_sketch(dvs_ctx* ctx, const dvs_seqset* s, int k, uint64_t sketch_si
             d_cnt.alloc(na) != DVS_OK || d_next.alloc(1) != DVS_OK || d_slot_rec.alloc(na) != DVS_OK ||
             d_nd.alloc(na) != DVS_OK)
             return fail(DVS_ERR_CUDA);
-        TRY_S(cudaMemsetAsync(d_keys.p, 0xFF, npad * sizeof(unsigned long long), st));  // sentinels sort last
         TRY_S(cudaMemsetAsync(d_cnt.p, 0, na * sizeof(uint32_t), st));
         TRY_S(cudaMemsetAsync(d_next.p, 0, sizeof(uint32_t), st));
         TRY_S(cudaMemcpyAsync(d_act.p, h_act.data(), na * sizeof(MashActive), cudaMemcpyHostToDevice, st));
         TRY_S(cudaMemcpyAsync(d_work.p, work.data(), work.size() * sizeof(MashWork), cudaMemcpyHostToDevice, st));
         TRY_S(cudaMemcpyAsync(d_slot_rec.p, act.data(), na * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         const unsigned grid = (unsigned)std::min<size_t>(work.size(), (size_t)ctx->sm_count * 8);
-        if (fast)
+        // DVS_MASH_FILTER16=0: the general k <= 16 kernel also for k = 16 (A/B measurements)
+        const char* f16_env = getenv("DVS_MASH_FILTER16");
+        if (fast && k == 16 && !(f16_env && f16_env[0] == '0')) {
+            if (canonical)
+                k_mash_filter16<true><<<grid, kMashThreads, 0, st>>>(s->data(), s->offsets.p, d_work.p,
+                                                                     (uint32_t)work.size(), d_next.p, d_act.p, d_cnt.p,
+                                                                     d_keys.p, 8192u);
+            else
+                k_mash_filter16<false><<<grid, kMashThreads, 0, st>>>(s->data(), s->offsets.p, d_work.p,
+                                                                      (uint32_t)work.size(), d_next.p, d_act.p, d_cnt.p,
+                                                                      d_keys.p, 8192u);
+        } else if (fast)
             k_mash_filter<<<grid, kMashThreads, 0, st>>>(s->data(), s->offsets.p, d_work.p, (uint32_t)work.size(),
                                                          d_next.p, k, canonical, d_act.p, d_cnt.p, d_keys.p);
         else
@@ -551,11 +752,31 @@ int dvs_mash_sketch(dvs_ctx* ctx, const dvs_seqset* s, int k, uint64_t sketch_si
                 cap[act[a]] = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(2ull * h_cnt[a], 2ull * cap[act[a]]), nk[act[a]]);
             }
         if (overflow) continue;  // rare: redo the active set with bigger buffers
-        if (bitonic_sort(ctx, d_keys.p, npad) != DVS_OK) return fail(DVS_ERR_CUDA);
-        k_mash_compact<<<na, 256, 0, st>>>(d_keys.p, npad, d_slot_rec.p, sketch_size, sk->stride, sk->data.p,
-                                           sk->lens.p, d_nd.p);
-        ctx->launches++;
-        TRY_S(cudaGetLastError());
+        uint32_t max_cnt = 0;
+        for (uint32_t a = 0; a < na; ++a) max_cnt = std::max(max_cnt, h_cnt[a]);
+        const char* gs_env = getenv("DVS_MASH_GLOBAL_SORT");
+        if (max_cnt <= kSortRecMax && !(gs_env && gs_env[0] == '1')) {
+            // every record's candidates fit shared memory: one CTA sorts, dedups and truncates a record
+            unsigned P = 2;
+            while (P < max_cnt) P <<= 1;
+            const size_t smem = (size_t)P * sizeof(uint32_t);
+            TRY_S(cudaFuncSetAttribute(k_mash_sort_record, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_mash_sort_record<<<na, kSortRecThreads, smem, st>>>(d_keys.p, d_act.p, d_cnt.p, d_slot_rec.p, sketch_size,
+                                                                  sk->stride, sk->data.p, sk->lens.p, d_nd.p);
+            ctx->launches++;
+            TRY_S(cudaGetLastError());
+        } else {
+            // global bitonic network over the whole key buffer: unused slots must hold sentinels that sort last
+            k_mash_pad_keys<<<(unsigned)std::min<size_t>((npad + 255) / 256, 65535), 256, 0, st>>>(
+                d_keys.p, npad, d_act.p, d_cnt.p, na);
+            ctx->launches++;
+            TRY_S(cudaGetLastError());
+            if (bitonic_sort(ctx, d_keys.p, npad) != DVS_OK) return fail(DVS_ERR_CUDA);
+            k_mash_compact<<<na, 256, 0, st>>>(d_keys.p, npad, d_slot_rec.p, sketch_size, sk->stride, sk->data.p,
+                                               sk->lens.p, d_nd.p);
+            ctx->launches++;
+            TRY_S(cudaGetLastError());
+        }
         TRY_S(cudaMemcpyAsync(h_nd.data(), d_nd.p, na * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         TRY_S(cudaStreamSynchronize(st));
         std::vector<uint32_t> again;
