@@ -33,6 +33,8 @@ import numpy as np
 
 ROOT = pathlib.Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
+# kernels of different ranks wait for each other: keep every stream on its own hardware queue (before CUDA starts)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 SEED = 20261017
 METRIC = "prep_nmost_throughput"

@@ -1,6 +1,7 @@
 // comm.cu — peer windows over NVLink (see comm.cuh): creation / mapping, device-side barrier, push flags,
 // small all-reduce(min), generic all-gather.  Replaces the torch.distributed / NCCL plumbing of round 1
 // ("tiny all-reduce over NVLink", "all-gather of the row blocks").
+#include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
 
@@ -161,6 +162,11 @@ int comm_check_error(dvs_ctx* ctx, dvs_comm* c, const char* what) {
         return DVS_ERR_CUDA;
     }
     return DVS_OK;
+}
+
+int comm_check_error_async(dvs_ctx* ctx, dvs_comm* c, const char* what) {
+    const char* env = getenv("DVS_COMM_CHECK");
+    return (env && env[0] == '1') ? comm_check_error(ctx, c, what) : DVS_OK;
 }
 
 int comm_barrier(dvs_ctx* ctx, dvs_comm* c) {

@@ -57,4 +57,7 @@ int comm_push_wait(dvs_ctx* ctx, dvs_comm* c);
 // all-reduce(min) of one u32 over the ranks, device side, result in *d_out (device) when the stream gets there
 int comm_min_u32(dvs_ctx* ctx, dvs_comm* c, const uint32_t* d_in, uint32_t* d_out);
 int comm_check_error(dvs_ctx* ctx, dvs_comm* c, const char* what);
+// the same only when DVS_COMM_CHECK=1 (it waits for the stream): the call in which a device-side wait timed out
+// reports it itself (tests); otherwise the next synchronous check does (dvs_select_sharded, distances, barrier)
+int comm_check_error_async(dvs_ctx* ctx, dvs_comm* c, const char* what);
 }  // namespace dvs

@@ -1066,6 +1066,7 @@ int dvs_count_kmers_sharded(dvs_ctx* ctx, dvs_comm* c, const dvs_seqset* s, int 
     rc = count_core(ctx, s, k, num_states, counts.p, dim, dst);
     if (rc == DVS_OK) rc = comm_push_commit(ctx, c);
     if (rc == DVS_OK) rc = comm_push_wait(ctx, c);
+    if (rc == DVS_OK) rc = comm_check_error_async(ctx, c, "dvs_count_kmers_sharded");
     if (rc != DVS_OK) return fail(rc);
     *out_all = a.f;
     return DVS_OK;
@@ -1111,6 +1112,7 @@ int dvs_kfreqs_allgather(dvs_ctx* ctx, dvs_comm* c, const dvs_kfreqs* f, const u
     rc = allrows_push(c, a, 0, f->nrec, true);
     if (rc == DVS_OK) rc = comm_push_commit(ctx, c);
     if (rc == DVS_OK) rc = comm_push_wait(ctx, c);
+    if (rc == DVS_OK) rc = comm_check_error_async(ctx, c, "dvs_kfreqs_allgather");
     if (rc != DVS_OK) return fail(rc);
     *out_all = a.f;
     return DVS_OK;

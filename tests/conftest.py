@@ -1,5 +1,11 @@
+import os
 import pathlib
 import sys
+
+# The multi-GPU tests run several ranks as threads on ONE GPU; their kernels wait for each other, so their
+# streams must not share a hardware queue (8 by default): a spinning kernel at the head of a shared queue
+# would hold back another rank's copies.  Must be set before the CUDA runtime initialises.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 import numpy as np
 import pytest

@@ -9,6 +9,7 @@ import numpy as np
 
 ROOT = pathlib.Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 from diverseseq_b200 import _lib, shard  # noqa: E402
 from oracle import oracle as orc  # noqa: E402

@@ -54,6 +54,7 @@ def run_ranks(world, fn, window_bytes=256 << 20):
     ndev = device_count()
     devices = list(range(world)) if ndev >= world else [0] * world
     old = os.environ.get("DVS_SELECT_GRID")
+    os.environ["DVS_COMM_CHECK"] = "1"  # a timed-out device-side wait is reported by the call it happened in
     if ndev < world:
         os.environ["DVS_SELECT_GRID"] = str(max(8, 148 // world - 2))
     group = shard.LocalGroup(world)
