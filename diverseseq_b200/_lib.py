@@ -19,6 +19,7 @@ MODE_NMOST, MODE_MAX_STDEV, MODE_MAX_COV = 0, 1, 2
 PHASE_COUNT_KERNEL, PHASE_FREQ_ENTROPY, PHASE_SELECT, PHASE_SKETCH, PHASE_MASH_PAIRS, PHASE_EUCLID, PHASE_UPLOAD = range(7)
 PHASE_PREP = 7
 PHASE_CLUSTER = 8
+PHASE_SPARSE = 9
 
 _vp = C.c_void_p
 _u32, _u64, _i32, _f64 = C.c_uint32, C.c_uint64, C.c_int, C.c_double
@@ -62,6 +63,11 @@ SIGNATURES = {
     "dvs_kfreqs_download": (_i32, [_vp, _vp, _u32, _u32, _vp, _vp, _vp, _vp]),
     "dvs_kfreqs_free": (None, [_vp]),
     "dvs_count_kmers_host": (_i32, [_vp, _vp, _vp, _u32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "dvs_count_kmers_sparse": (_i32, [_vp, _vp, _i32, _i32, _i32, C.POINTER(_vp)]),
+    "dvs_ksparse_nrec": (_u32, [_vp]),
+    "dvs_ksparse_stats": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "dvs_ksparse_download": (_i32, [_vp, _vp, _u32, _vp, _vp, _u64, C.POINTER(_u64)]),
+    "dvs_ksparse_free": (None, [_vp]),
     "dvs_select": (_i32, [_vp, _vp, _vp, _u32, _i32, _u32, _u32, _vp, _vp, _vp, C.POINTER(_u32)]),
     "dvs_select_last_accepts": (_u32, [_vp]),
     "dvs_select_last_exact_evals": (_u32, [_vp]),
@@ -528,6 +534,44 @@ class KFreqs(_Handle):
         """same matrix written to device memory at `device_ptr` ((row_end-row_begin) x nrec f64)"""
         row_end = self.nrec if row_end is None else row_end
         check(self.ctx._lib.dvs_euclid_distances(self.ctx.handle, self.handle, row_begin, row_end, _vp(device_ptr)))
+
+
+class KSparse(_Handle):
+    """Sparse (index, count) k-mer rows for 9 <= k <= 12 (dvs_ksparse)."""
+
+    _free = "dvs_ksparse_free"
+
+    @classmethod
+    def count(cls, ctx: Context, seqset: SeqSet, k: int, num_states: int = 4, want_entropy: bool = False) -> "KSparse":
+        h = _vp()
+        check(ctx._lib.dvs_count_kmers_sparse(ctx.handle, seqset.handle, int(k), int(num_states), int(want_entropy),
+                                              C.byref(h)))
+        out = cls(ctx, h)
+        out.has_entropy = bool(want_entropy)
+        return out
+
+    @property
+    def nrec(self) -> int:
+        return int(self.ctx._lib.dvs_ksparse_nrec(self.handle))
+
+    def stats(self):
+        """(distinct k-mers, valid k-mers, entropies or None, valid flags) per record"""
+        n = self.nrec
+        nnz, tot = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint64)
+        ent = np.zeros(n, dtype=np.float64) if self.has_entropy else None
+        valid = np.zeros(n, dtype=np.uint8)
+        check(self.ctx._lib.dvs_ksparse_stats(self.ctx.handle, self.handle, ptr(nnz), ptr(tot), ptr(ent), ptr(valid)))
+        return nnz, tot, ent, valid
+
+    def record(self, rec: int):
+        """(ascending k-mer indices, counts) of one record"""
+        n = _u64(0)
+        check(self.ctx._lib.dvs_ksparse_download(self.ctx.handle, self.handle, int(rec), None, None, 0, C.byref(n)))
+        idx, cnt = np.zeros(n.value, dtype=np.uint32), np.zeros(n.value, dtype=np.uint32)
+        if n.value:
+            check(self.ctx._lib.dvs_ksparse_download(self.ctx.handle, self.handle, int(rec), ptr(idx), ptr(cnt), n.value,
+                                                     C.byref(n)))
+        return idx, cnt
 
 
 class Comm:

@@ -39,6 +39,11 @@ static CommPeers peers_of(const dvs_comm* c) {
 }
 
 constexpr unsigned long long kWatchdogNs = 20ull * 1000 * 1000 * 1000;  // a wait longer than this is a hang
+// DVS_WATCHDOG_MS overrides it (tests)
+static unsigned long long watchdog_ns() {
+    const char* e = getenv("DVS_WATCHDOG_MS");
+    return e && atoll(e) > 0 ? (unsigned long long)atoll(e) * 1000000ull : kWatchdogNs;
+}
 
 __device__ __forceinline__ unsigned long long gtime() {
     unsigned long long t;
@@ -55,7 +60,7 @@ __device__ __forceinline__ uint64_t ld_sys_u64(const uint64_t* p) {
 }
 
 // every rank writes `epoch` into its word of every peer's flag array, then waits for all of its own words
-__global__ void k_comm_barrier(CommPeers P, uint64_t epoch) {
+__global__ void k_comm_barrier(CommPeers P, uint64_t epoch, unsigned long long wd) {
     const int t = threadIdx.x;
     if (t >= P.world) return;
     __threadfence_system();
@@ -63,7 +68,7 @@ __global__ void k_comm_barrier(CommPeers P, uint64_t epoch) {
     const uint64_t* mine = reinterpret_cast<const uint64_t*>(P.base[P.rank] + kCommBarrierOff) + t;
     const unsigned long long t0 = gtime();
     while (ld_sys_u64(mine) < epoch) {
-        if (gtime() - t0 > kWatchdogNs) {
+        if (gtime() - t0 > wd) {
             *reinterpret_cast<volatile uint32_t*>(P.base[P.rank] + kCommErrOff) = 1u;
             break;
         }
@@ -72,13 +77,13 @@ __global__ void k_comm_barrier(CommPeers P, uint64_t epoch) {
 }
 
 // wait until the pushes of `epoch` from every peer have landed (their flag copies travel behind the data)
-__global__ void k_comm_wait_push(CommPeers P, uint64_t epoch) {
+__global__ void k_comm_wait_push(CommPeers P, uint64_t epoch, unsigned long long wd) {
     const int t = threadIdx.x;
     if (t >= P.world || t == P.rank) return;
     const uint64_t* mine = reinterpret_cast<const uint64_t*>(P.base[P.rank] + kCommPushOff) + t;
     const unsigned long long t0 = gtime();
     while (ld_sys_u64(mine) < epoch) {
-        if (gtime() - t0 > kWatchdogNs) {
+        if (gtime() - t0 > wd) {
             *reinterpret_cast<volatile uint32_t*>(P.base[P.rank] + kCommErrOff) = 2u;
             break;
         }
@@ -89,7 +94,7 @@ __global__ void k_comm_wait_push(CommPeers P, uint64_t epoch) {
 __global__ void k_comm_set_u64(uint64_t* p, uint64_t v) { *p = v; }
 
 // all-reduce(min) of one u32: value and the exchange's tag travel in one 8-byte word
-__global__ void k_comm_min_u32(CommPeers P, uint32_t tag, const uint32_t* in, uint32_t* out) {
+__global__ void k_comm_min_u32(CommPeers P, uint32_t tag, const uint32_t* in, uint32_t* out, unsigned long long wd) {
     __shared__ uint32_t s_v[kCommMaxWorld];
     const int t = threadIdx.x;
     if (t < P.world) {
@@ -100,7 +105,7 @@ __global__ void k_comm_min_u32(CommPeers P, uint32_t tag, const uint32_t* in, ui
         const unsigned long long t0 = gtime();
         uint64_t w;
         while ((uint32_t)(w = ld_sys_u64(mine)) != tag) {
-            if (gtime() - t0 > kWatchdogNs) {
+            if (gtime() - t0 > wd) {
                 *reinterpret_cast<volatile uint32_t*>(P.base[P.rank] + kCommErrOff) = 3u;
                 w = ~0ull;
                 break;
@@ -157,8 +162,8 @@ int comm_check_error(dvs_ctx* ctx, dvs_comm* c, const char* what) {
     DVS_CUDA_TRY(cudaMemcpyAsync(&flag, c->window + kCommErrOff, sizeof flag, cudaMemcpyDeviceToHost, ctx->stream));
     DVS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     if (flag) {
-        set_error("%s: a device-side wait on a peer gave up after %llu s (code %u): a rank is missing or died", what,
-                  kWatchdogNs / 1000000000ull, flag);
+        set_error("%s: a device-side wait on a peer gave up after %.1f s (code %u): a rank is missing or died", what,
+                  watchdog_ns() / 1e9, flag);
         return DVS_ERR_CUDA;
     }
     return DVS_OK;
@@ -172,7 +177,7 @@ int comm_check_error_async(dvs_ctx* ctx, dvs_comm* c, const char* what) {
 int comm_barrier(dvs_ctx* ctx, dvs_comm* c) {
     if (c->world == 1) return DVS_OK;
     ++c->epoch;
-    k_comm_barrier<<<1, 32, 0, ctx->stream>>>(peers_of(c), c->epoch);
+    k_comm_barrier<<<1, 32, 0, ctx->stream>>>(peers_of(c), c->epoch, watchdog_ns());
     DVS_LAUNCHED(ctx);
     return DVS_OK;
 }
@@ -197,7 +202,7 @@ int comm_push_commit(dvs_ctx* ctx, dvs_comm* c) {
 int comm_push_wait(dvs_ctx* ctx, dvs_comm* c) {
     DVS_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, c->ev_pushed, 0));
     if (c->world > 1) {
-        k_comm_wait_push<<<1, 32, 0, ctx->stream>>>(peers_of(c), c->push_epoch);
+        k_comm_wait_push<<<1, 32, 0, ctx->stream>>>(peers_of(c), c->push_epoch, watchdog_ns());
         DVS_LAUNCHED(ctx);
     }
     return DVS_OK;
@@ -205,7 +210,7 @@ int comm_push_wait(dvs_ctx* ctx, dvs_comm* c) {
 
 int comm_min_u32(dvs_ctx* ctx, dvs_comm* c, const uint32_t* d_in, uint32_t* d_out) {
     ++c->min_tag;
-    k_comm_min_u32<<<1, 32, 0, ctx->stream>>>(peers_of(c), (uint32_t)c->min_tag, d_in, d_out);
+    k_comm_min_u32<<<1, 32, 0, ctx->stream>>>(peers_of(c), (uint32_t)c->min_tag, d_in, d_out, watchdog_ns());
     DVS_LAUNCHED(ctx);
     return DVS_OK;
 }

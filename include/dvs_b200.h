@@ -75,6 +75,7 @@ uint64_t dvs_ctx_launch_count(dvs_ctx* ctx);
 #define DVS_PHASE_EUCLID 5         /* k_euclid_tiles */
 #define DVS_PHASE_UPLOAD 6         /* host->device sequence copy of dvs_seqset_upload */
 #define DVS_PHASE_CLUSTER 8        /* k_cl_symmetrise + k_cl_nn_chain of one dvs_linkage_average */
+#define DVS_PHASE_SPARSE 9         /* the partition passes of one dvs_count_kmers_sparse (without the optional entropies) */
 #define DVS_PHASE_PREP 7           /* all device work of one dvs_prep_fasta (k_prep x2 + k_prep_carry) */
 /* bytes that actually crossed PCIe during the last dvs_seqset_upload (2-bit packed + exceptions for
  * large uploads, see csrc/upload.cu; equal to the input size for the plain copy) */
@@ -152,6 +153,24 @@ void dvs_kfreqs_free(dvs_kfreqs* f);
 /* one-call host->host form (upload, count, download) */
 int dvs_count_kmers_host(dvs_ctx* ctx, const uint8_t* seqs, const uint64_t* offsets, uint32_t nrec, int k,
                          int num_states, uint64_t* counts, double* freqs, double* entropies, uint8_t* valid);
+
+/* ---- sparse counting for large k (9 <= k <= 12, num_states 4) ----------------------------------------
+ * to_kcounts where the dense vector is out of reach (4^12 bins = 134 MB of f64 per record, src/record.rs:41-84,
+ * 124-131): the result of a record is the ascending list of its DISTINCT k-mer indices with their counts, i.e.
+ * the non-zero entries of the reference's vector (8 bytes per distinct k-mer).  Frequencies are
+ * count / total; want_entropy != 0 also evaluates the reference's sequential entropy over the non-zero entries
+ * (bit-identical: the reference skips zeros; ~30 ms per 4 Mbp record, records in parallel).
+ * dvs_ksparse_stats: per record the number of distinct k-mers, of valid k-mers, the entropy (NULL unless
+ * requested at count time) and validity.  dvs_ksparse_download: one record's (index, count) lists; call with
+ * idx = cnt = NULL to learn the length first. */
+typedef struct dvs_ksparse dvs_ksparse;
+int dvs_count_kmers_sparse(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, int want_entropy, dvs_ksparse** out);
+uint32_t dvs_ksparse_nrec(const dvs_ksparse* sp);
+int dvs_ksparse_stats(dvs_ctx* ctx, const dvs_ksparse* sp, uint64_t* nnz, uint64_t* totals, double* entropy,
+                      uint8_t* valid);
+int dvs_ksparse_download(dvs_ctx* ctx, const dvs_ksparse* sp, uint32_t rec, uint32_t* idx, uint32_t* cnt, uint64_t cap,
+                         uint64_t* nnz_out);
+void dvs_ksparse_free(dvs_ksparse* sp);
 
 /* ---- nmost / max selection ------------------------------------------------------------------
  * select_nmost_divergent / select_max_divergent and their *_final forms (src/records.rs:311-507)
