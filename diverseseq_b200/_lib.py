@@ -87,6 +87,7 @@ SIGNATURES = {
     "dvs_euclid_distances": (_i32, [_vp, _vp, _u32, _u32, _vp]),
     "dvs_comm_create": (_i32, [_vp, _i32, _i32, _u64, C.POINTER(_vp), _vp]),
     "dvs_comm_connect": (_i32, [_vp, _vp, _vp]),
+    "dvs_comm_set_host_barrier": (_i32, [_vp, _vp, _vp]),
     "dvs_comm_rank": (_i32, [_vp]),
     "dvs_comm_world": (_i32, [_vp]),
     "dvs_comm_barrier": (_i32, [_vp, _vp]),
@@ -590,6 +591,11 @@ class Comm:
         assert len(blobs) == self.world and all(len(b) == 128 for b in blobs)
         check(self.ctx._lib.dvs_comm_connect(self.ctx.handle, self.handle, C.create_string_buffer(b"".join(blobs), 128 * self.world)))
         return self
+
+    def set_host_barrier(self, fn) -> None:
+        """ranks sharing one GPU: `fn()` returns once every rank has called it (dvs_comm_set_host_barrier)"""
+        self._host_barrier_cb = C.CFUNCTYPE(None, _vp)(lambda _arg: fn())
+        check(self.ctx._lib.dvs_comm_set_host_barrier(self.handle, C.cast(self._host_barrier_cb, _vp), None))
 
     def barrier(self) -> None:
         check(self.ctx._lib.dvs_comm_barrier(self.ctx.handle, self.handle))

@@ -174,8 +174,33 @@ int comm_check_error_async(dvs_ctx* ctx, dvs_comm* c, const char* what) {
     return (env && env[0] == '1') ? comm_check_error(ctx, c, what) : DVS_OK;
 }
 
+int comm_host_rendezvous(dvs_ctx* ctx, dvs_comm* c) {
+    if (!c->host_barrier || c->world == 1) return DVS_OK;
+    DVS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    DVS_CUDA_TRY(cudaStreamSynchronize(c->side));
+    c->host_barrier(c->host_barrier_arg);
+    return DVS_OK;
+}
+
+// host-synchronised all-reduce(min): values travel through the same slots, the waiting happens on the host
+__global__ void k_comm_min_local(CommPeers P, uint32_t tag, uint32_t* out) {
+    uint32_t m = 0xFFFFFFFFu;
+    for (int r = 0; r < P.world; ++r) {
+        const uint64_t w = *(reinterpret_cast<const uint64_t*>(P.base[P.rank] + kCommMinOff) + (tag & 1u) * kCommMaxWorld + r);
+        m = min(m, (uint32_t)(w >> 32));
+    }
+    *out = m;
+}
+__global__ void k_comm_min_post(CommPeers P, uint32_t tag, const uint32_t* in) {
+    const int t = threadIdx.x;
+    if (t < P.world)
+        st_sys_u64(reinterpret_cast<uint64_t*>(P.base[t] + kCommMinOff) + (tag & 1u) * kCommMaxWorld + P.rank,
+                   ((uint64_t)(*in) << 32) | tag);
+}
+
 int comm_barrier(dvs_ctx* ctx, dvs_comm* c) {
     if (c->world == 1) return DVS_OK;
+    if (c->host_barrier) return comm_host_rendezvous(ctx, c);
     ++c->epoch;
     k_comm_barrier<<<1, 32, 0, ctx->stream>>>(peers_of(c), c->epoch, watchdog_ns());
     DVS_LAUNCHED(ctx);
@@ -201,6 +226,7 @@ int comm_push_commit(dvs_ctx* ctx, dvs_comm* c) {
 
 int comm_push_wait(dvs_ctx* ctx, dvs_comm* c) {
     DVS_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, c->ev_pushed, 0));
+    if (c->host_barrier) return comm_host_rendezvous(ctx, c);  // every rank's pushes have completed
     if (c->world > 1) {
         k_comm_wait_push<<<1, 32, 0, ctx->stream>>>(peers_of(c), c->push_epoch, watchdog_ns());
         DVS_LAUNCHED(ctx);
@@ -210,6 +236,14 @@ int comm_push_wait(dvs_ctx* ctx, dvs_comm* c) {
 
 int comm_min_u32(dvs_ctx* ctx, dvs_comm* c, const uint32_t* d_in, uint32_t* d_out) {
     ++c->min_tag;
+    if (c->host_barrier) {
+        k_comm_min_post<<<1, 32, 0, ctx->stream>>>(peers_of(c), (uint32_t)c->min_tag, d_in);
+        DVS_LAUNCHED(ctx);
+        DVS_TRY(comm_host_rendezvous(ctx, c));
+        k_comm_min_local<<<1, 1, 0, ctx->stream>>>(peers_of(c), (uint32_t)c->min_tag, d_out);
+        DVS_LAUNCHED(ctx);
+        return DVS_OK;
+    }
     k_comm_min_u32<<<1, 32, 0, ctx->stream>>>(peers_of(c), (uint32_t)c->min_tag, d_in, d_out, watchdog_ns());
     DVS_LAUNCHED(ctx);
     return DVS_OK;
@@ -306,6 +340,16 @@ int dvs_comm_connect(dvs_ctx* ctx, dvs_comm* c, const void* handles) {
         }
     }
     c->connected = true;
+    return DVS_OK;
+}
+
+int dvs_comm_set_host_barrier(dvs_comm* c, void (*barrier)(void*), void* arg) {
+    if (!c) {
+        set_error("dvs_comm_set_host_barrier: NULL argument");
+        return DVS_ERR_ARG;
+    }
+    c->host_barrier = barrier;
+    c->host_barrier_arg = arg;
     return DVS_OK;
 }
 

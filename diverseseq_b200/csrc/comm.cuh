@@ -41,6 +41,13 @@ struct dvs_comm {
     cudaStream_t side = nullptr;      // pushes run here, behind an event of the main stream
     cudaEvent_t ev_ready = nullptr, ev_pushed = nullptr;
     std::vector<CommBlock> blocks;    // symmetric heap (first fit over [kCommCtrlBytes, window_bytes))
+    // Host-synchronised mode (dvs_comm_set_host_barrier): for ranks that SHARE one GPU (threads of one process in
+    // the tests).  There, a kernel of one rank that spins on a peer can deadlock against a peer's host call that
+    // implicitly waits for the whole device (allocation, pool growth), so the waits are taken on the host instead:
+    // finish this rank's stream, meet the other ranks in `host_barrier`, carry on.  Ranks on their own GPUs never
+    // set it and keep the device-side waits.
+    void (*host_barrier)(void*) = nullptr;
+    void* host_barrier_arg = nullptr;
     uint8_t* ctrl(int r) const { return peer[r]; }
 };
 
@@ -56,6 +63,9 @@ int comm_push_commit(dvs_ctx* ctx, dvs_comm* c);
 int comm_push_wait(dvs_ctx* ctx, dvs_comm* c);
 // all-reduce(min) of one u32 over the ranks, device side, result in *d_out (device) when the stream gets there
 int comm_min_u32(dvs_ctx* ctx, dvs_comm* c, const uint32_t* d_in, uint32_t* d_out);
+// host-synchronised mode only: every rank's stream is drained and all ranks meet on the host (no-op otherwise);
+// called before a kernel that spins on its peers is launched
+int comm_host_rendezvous(dvs_ctx* ctx, dvs_comm* c);
 int comm_check_error(dvs_ctx* ctx, dvs_comm* c, const char* what);
 // the same only when DVS_COMM_CHECK=1 (it waits for the stream): the call in which a device-side wait timed out
 // reports it itself (tests); otherwise the next synchronous check does (dvs_select_sharded, distances, barrier)

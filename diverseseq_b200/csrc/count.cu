@@ -313,21 +313,19 @@ k_count(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offsets, 
     }
 }
 
-// ---- MODE_SUPER3: (k+2)-mers at every THIRD position, 16-bit packed counters ------------------------
-// The k-mer kernels above sit on the shared-memory atomic rate (~4 bank-conflict wavefronts per ATOMS,
-// the floor for 32 random banks), so the remaining lever is fewer atomics per base.  Here the (k+2)-mer
-// ending at every absolute position p == 2 (mod 3) is histogrammed: it carries the three k-mers ending
-// at p-2, p-1 and p, i.e. one ATOMS per three bases (5.33 per 16-base block instead of 8).  4^(k+2)
-// counters only fit shared memory as 16-bit halves of 32-bit words (k = 6: 128 KB); a half can
-// overflow after 65,535 hits in one work item, which is detected exactly at the flush: every overflow
-// (carry into the neighbour half or out of the word) lowers the sum of all halves, so sum == number of
-// increments  <=>  no overflow.  An item that fails the check is not added; it is appended to a retry
-// list and recounted by the 32-bit (k+1)-mer kernel.
-// Ownership: the lane whose block contains p handles the triplet (the k-mers at p-2, p-1 may sit in the
-// previous block: they are in the halo).  Triplets cut by an invalid byte, the record start or a short
-// window fall back to single k-mers in the side table (per-byte path); a record that ends before its
-// last triplet completes flushes the pending k-mers at its last byte, so the block holding the last
-// byte always takes the per-byte path when end % 3 != 0.
+// ---- MODE_SUPER3: (k+2)-mers at every third position, 16-bit packed counters ------------------------------
+// The k-mer kernels above sit on the shared-memory atomic rate (~3.5 bank-conflict wavefronts per ATOMS, the
+// expectation for 32 random banks), so the lever is fewer atomics per base.  Here every lane histograms, for its
+// 16-base block, the five (k+2)-mers ending at block positions 2, 5, 8, 11, 14 - each carries the three k-mers
+// ending at its last three positions - plus the single k-mer ending at position 15 in a small side table:
+// 6 ATOMS per 16 bases instead of 8, all at compile-time shifts of the packed window pp:pc (the triplets are
+// local to the lane's block, so there is no phase to track and no triplet ever spans a block boundary, a record
+// boundary or two work items).  4^(k+2) counters only fit shared memory as 16-bit halves of 32-bit words (k = 6:
+// 128 KB); a half can overflow after 65,535 hits in one work item, which is detected exactly at the flush: every
+// overflow (carry into the neighbour half or out of the word) lowers the sum of all halves, so
+// sum == number of increments  <=>  no overflow.  An item that fails the check is not added; it is appended to a
+// retry list and recounted by the 32-bit (k+1)-mer kernel.  Blocks that contain an invalid byte, a record edge,
+// or follow such a block count their k-mers one by one in the side table (the reference's run-length rule).
 template <bool SCR, int THREADS, int PF>
 __global__ void __launch_bounds__(THREADS, 1)
 k_count_s3(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offsets, const CountWork* __restrict__ work,
@@ -344,6 +342,9 @@ k_count_s3(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offset
     const uint32_t hwords = (uint32_t)(dim * 8);  // 4^(k+2) / 2
     uint32_t* side = hist + hwords;
     char* const hist_b = reinterpret_cast<char*>(hist);
+    char* const side_b = reinterpret_cast<char*>(side);
+    const uint32_t offmask = mask << 1 & ~3u, sidemask4 = mask_k << 2;
+    const uint32_t lane16 = 16u * (uint32_t)lane;
 
     for (;;) {
         if (tid == 0) {
@@ -363,14 +364,8 @@ k_count_s3(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offset
             for (uint32_t i = tid; i < n4; i += THREADS) h4[i] = make_uint4(0, 0, 0, 0);
         }
         __syncthreads();
-        uint32_t n_inc = 0;
-        auto bump = [&](uint32_t y) {  // y = (k+2)-mer
-            uint32_t off = (y & ~1u) << 1;  // byte offset of its word
-            if (SCR) off ^= (off >> 5) & ~3u;
-            atomicAdd(reinterpret_cast<uint32_t*>(hist_b + off), 1u << ((y & 1u) << 4));
-        };
-        // same, from v = y << 1 with garbage above bit 2kk (fast path: 3-4 instructions per atomic)
-        const uint32_t offmask = mask << 1 & ~3u;
+        uint32_t n_fast = 0;  // fast blocks of this thread: 5 (k+2)-mer increments each
+        // v = (k+2)-mer << 1 with garbage above bit 2kk: byte offset of its counter word in bits [2kk:2], half in bit 1
         auto bump_v = [&](uint32_t v) {
             uint32_t off = v & offmask;
             if (SCR) off ^= (off >> 5) & ~3u;
@@ -380,21 +375,17 @@ k_count_s3(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offset
         const uint32_t item_len = (uint32_t)(w.end - w.begin);
         const uint32_t rs = start > w.begin ? (uint32_t)min(start - w.begin, (uint64_t)item_len) : 0u;
         const uint32_t re = end < w.end ? (end > w.begin ? (uint32_t)(end - w.begin) : 0u) : item_len;
-        // the full block that holds the record's last byte must flush pending k-mers (per-byte path)
-        const uint32_t tail_a = (end > w.begin && end <= w.end && (end % 3ull) != 0 && re >= 16 && (re & 15u) == 0) ? re - 16 : 0xffffffffu;
         const uint32_t span = ((item_len + kWarps - 1) / kWarps + 511u) & ~511u;
         const uint32_t r0 = min(item_len, (uint32_t)warp * span);
         const uint32_t r1 = min(item_len, r0 + span);
         const uint8_t* base = seqs + w.begin;
-        const uint32_t safe_hi = min(min(re, r1), tail_a);
+        const uint32_t safe_hi = min(re, r1);
         uint32_t carry_pc = 0;
         bool carry_ok = false;
-        // phase of the lane's block start (absolute position mod 3); 16 == 1 and 512 == 2 (mod 3)
-        uint32_t ph = (uint32_t)((w.begin + r0 + 16ull * lane) % 3ull);
         uint4 ring[PF];
 #pragma unroll
         for (int u = 0; u < PF; ++u) {
-            const uint32_t a = r0 + 512u * u + 16 * lane;
+            const uint32_t a = r0 + 512u * u + lane16;
             ring[u] = (a < r1) ? ldg16(base + a) : make_uint4(~0u, ~0u, ~0u, ~0u);
         }
         if (r0 < r1) {
@@ -408,12 +399,12 @@ k_count_s3(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offset
           for (int u = 0; u < PF; ++u) {
             const uint32_t r = rbase + 512u * u;
             if (r >= r1) break;  // warp-uniform
-            const uint32_t a = r + 16 * lane;
+            const uint32_t a = r + lane16;
             const uint4 cur = ring[u];
-            // interior steps (warp-uniform test): all 512 bytes lie inside the record, the span and before
-            // the tail block, so only the bytes themselves can invalidate a block
+            // interior steps (warp-uniform test): all 512 bytes lie inside the record and the span, so only the
+            // bytes themselves can invalidate a block
             bool ok = ((cur.x | cur.y | cur.z | cur.w) & 0xFCFCFCFCu) == 0;
-            if (!(r >= rs && r + 512u <= safe_hi)) ok = ok && (a >= rs) && (a + 16 <= re) && (a < r1) && (a != tail_a);
+            if (!(r >= rs && r + 512u <= safe_hi)) ok = ok && (a >= rs) && (a + 16 <= re) && (a < r1);
             const uint32_t pc = pack16p(cur);
             // refill the slot only now: in the common path `cur` is dead from here on, so the load lands in
             // the same registers without a copy (the per-byte path re-reads its 32 bytes)
@@ -421,65 +412,42 @@ k_count_s3(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offset
             uint32_t pp = __shfl_up_sync(kFull, pc, 1);
             if (lane == 0) pp = carry_pc;
             const uint32_t okmask = __ballot_sync(kFull, ok);
-            const bool prev_ok = lane == 0 ? carry_ok : ((okmask >> (lane - 1)) & 1u) != 0;
-            // (k+2)-mers ending at j = j0, j0+3, ... (< 16), j0 = 2 - ph.  The 64-bit window pp:pc is
-            // aligned once by the lane's phase (W = pp:pc >> 2 ph), after which the five words sit at
-            // compile-time shifts: v_i = W >> (25 - 6 i) holds (k+2)-mer i in bits [2kk:1], i.e. the byte
-            // offset of its counter word in bits [2kk:2] and the half selector in bit 1.
+            // the five (k+2)-mers ending at block positions 2, 5, 8, 11, 14 and the k-mer ending at position 15
             auto fast_block = [&]() {
-                const uint32_t sa = 2u * ph;
-                const uint32_t wlo = __funnelshift_r(pc, pp, sa), whi = pp >> sa;
 #pragma unroll
-                for (int t = 0; t < 5; ++t) bump_v(__funnelshift_r(wlo, whi, 25 - 6 * t));
-                if (ph == 2) bump_v(pc << 1);  // j0 = 0: a sixth one ends at j = 15
-                n_inc += 5u + (ph == 2 ? 1u : 0u);
+                for (int t = 0; t < 5; ++t) bump_v(__funnelshift_r(pc, pp, 25 - 6 * t));
+                atomicAdd(reinterpret_cast<uint32_t*>(side_b + ((pc << 2) & sidemask4)), 1u);
+                ++n_fast;
             };
             if (okmask == kFull && carry_ok) {  // warp-uniform: the common case
                 fast_block();
-            } else if (ok && prev_ok) {
-                fast_block();
-            } else if (a < r1) {
-                const uint4 prev = ldg16(base + a - 16), cur2 = ldg16(base + a);
-                const uint32_t wv[8] = {prev.x, prev.y, prev.z, prev.w, cur2.x, cur2.y, cur2.z, cur2.w};
-                uint32_t run = 0, idx = 0, run1 = 0, idx1 = 0, run2 = 0, idx2 = 0;
-                uint32_t pm = (ph + 2u) % 3u;  // phase of position a - 16
+            } else {
+                const bool prev_ok = lane == 0 ? carry_ok : ((okmask >> (lane - 1)) & 1u) != 0;
+                if (ok && prev_ok) {
+                    fast_block();
+                } else if (a < r1) {
+                    // per-byte path: every k-mer ending in this block, one by one, into the side table
+                    const uint4 prev = ldg16(base + a - 16), cur2 = ldg16(base + a);
+                    const uint32_t wv[8] = {prev.x, prev.y, prev.z, prev.w, cur2.x, cur2.y, cur2.z, cur2.w};
+                    uint32_t run = 0, idx = 0;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const uint64_t p = w.begin + a + i - 16;
-                    uint32_t bb = (wv[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-                    if (p < start || p >= end) bb = 0xFFu;
-                    run2 = run1;
-                    idx2 = idx1;
-                    run1 = run;
-                    idx1 = idx;
-                    if (bb >= 4u) {
-                        run = 0;
-                        idx = 0;
-                    } else {
-                        idx = ((idx << 2) | bb) & mask;
-                        ++run;
-                    }
-                    if (i >= 16 && p < end) {  // (past the end nothing is pending: the last byte flushed it)
-                        if (pm == 2) {
-                            if (run >= (uint32_t)kk) {
-                                bump(idx);
-                                ++n_inc;
-                            } else {
-                                if (run2 >= (uint32_t)k) atomicAdd(&side[idx2 & mask_k], 1u);
-                                if (run1 >= (uint32_t)k) atomicAdd(&side[idx1 & mask_k], 1u);
-                                if (run >= (uint32_t)k) atomicAdd(&side[idx & mask_k], 1u);
-                            }
-                        } else if (p + 1 == end) {  // the record ends inside a triplet: flush what is pending
-                            if (pm == 1 && run1 >= (uint32_t)k) atomicAdd(&side[idx1 & mask_k], 1u);
-                            if (run >= (uint32_t)k) atomicAdd(&side[idx & mask_k], 1u);
+                    for (int i = 0; i < 32; ++i) {
+                        const uint64_t p = w.begin + a + i - 16;
+                        uint32_t bb = (wv[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+                        if (p < start || p >= end) bb = 0xFFu;
+                        if (bb >= 4u) {
+                            run = 0;
+                            idx = 0;
+                        } else {
+                            idx = ((idx << 2) | bb) & mask_k;
+                            ++run;
+                            if (i >= 16 && run >= (uint32_t)k) atomicAdd(&side[idx], 1u);
                         }
                     }
-                    pm = pm == 2 ? 0u : pm + 1u;
                 }
             }
             carry_pc = __shfl_sync(kFull, pc, 31);
             carry_ok = (okmask >> 31) != 0;
-            ph = ph == 0 ? 2u : ph - 1u;  // + 512 == + 2 (mod 3)
           }
         }
         __syncthreads();
@@ -510,6 +478,7 @@ k_count_s3(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offset
             }
             side[x] = c;  // thread-private slot until the overflow check has passed
         }
+        uint32_t n_inc = 5u * n_fast;
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
             pre_sum += __shfl_xor_sync(kFull, pre_sum, o);

@@ -663,7 +663,10 @@ static int select_core(dvs_ctx* ctx, dvs_comm* comm, const dvs_kfreqs* f, const 
             const unsigned grid = use_sm ? sm_grid : persist_grid;
             k_sel_set_dev<<<1, 1, 0, st>>>(cur->sc.p, cursor, std::min(window, grid * world), grid * world, num, accepts,
                                            (unsigned)cur->which);
-            if (comm) shard.tag_base = (unsigned)((++comm->sel_tag_base) << 20);
+            if (comm) {
+                shard.tag_base = (unsigned)((++comm->sel_tag_base) << 20);
+                DVS_TRY(comm_host_rendezvous(ctx, comm));  // (ranks sharing one GPU only)
+            }
             DVS_LAUNCHED(ctx);
             const double* a_F = f->freqs.p;
             const double* a_H = f->entropy.p;

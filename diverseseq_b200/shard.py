@@ -162,6 +162,9 @@ def connect(ctx, rv, window_bytes: int):
     comm = _lib.Comm(ctx, rv.rank, rv.world, int(window_bytes))
     comm.connect(rv.allgather(comm.blob))
     comm.rv = rv
+    devices = rv.allgather((os.getpid(), ctx.device))
+    if isinstance(rv, _LocalMember) and len(set(devices)) < len(devices):
+        comm.set_host_barrier(rv.barrier)  # thread ranks sharing a GPU: waits are taken on the host
     return comm
 
 

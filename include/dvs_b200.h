@@ -259,6 +259,11 @@ typedef struct dvs_comm dvs_comm;
 #define DVS_COMM_HANDLE_BYTES 128
 int dvs_comm_create(dvs_ctx* ctx, int rank, int world, uint64_t window_bytes, dvs_comm** out, void* handle_out);
 int dvs_comm_connect(dvs_ctx* ctx, dvs_comm* c, const void* handles /* world x DVS_COMM_HANDLE_BYTES */);
+/* Ranks that SHARE one GPU (threads of one process, as in the tests) must take their waits on the host: a kernel
+ * that spins on a peer could deadlock against the peer's host calls that implicitly wait for the whole device.
+ * `barrier(arg)` must return once every rank has called it (e.g. a thread barrier); all ranks set it or none.
+ * Ranks on their own GPUs never call this and keep the device-side flags. */
+int dvs_comm_set_host_barrier(dvs_comm* c, void (*barrier)(void*), void* arg);
 int dvs_comm_rank(const dvs_comm* c);
 int dvs_comm_world(const dvs_comm* c);
 int dvs_comm_barrier(dvs_ctx* ctx, dvs_comm* c);

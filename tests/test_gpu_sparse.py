@@ -80,7 +80,7 @@ def test_sparse_k12_full_length_genomes(lib, ctx, orc):
     # every record: the counts add up to its number of valid 12-mers (checked against a k=6 style total is not
     # possible; the run-length identity total <= len - k + 1 is)
     lens = np.diff(off.astype(np.int64))
-    assert (tot.astype(np.int64) <= lens - 11).all() and (nnz <= tot).all() and (nnz > 0.7 * tot).all()
+    assert (tot.astype(np.int64) <= lens - 11).all() and (nnz <= tot).all() and (nnz > 0.3 * tot).all()
 
 
 def test_sparse_argument_errors(lib, ctx):
