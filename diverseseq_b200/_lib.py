@@ -85,6 +85,7 @@ SIGNATURES = {
     "dvs_mash_distances": (_i32, [_vp, _vp, _i32, _u64, _u32, _u32, _vp, _vp, _vp]),
     "dvs_mash_sketch_host": (_i32, [_vp, _vp, _u64, _i32, _u64, _i32, _i32, _vp, _u64, C.POINTER(_u64)]),
     "dvs_euclid_distances": (_i32, [_vp, _vp, _u32, _u32, _vp]),
+    "dvs_euclid_last_fallback_pairs": (_u32, [_vp]),
     "dvs_comm_create": (_i32, [_vp, _i32, _i32, _u64, C.POINTER(_vp), _vp]),
     "dvs_comm_connect": (_i32, [_vp, _vp, _vp]),
     "dvs_comm_set_host_barrier": (_i32, [_vp, _vp, _vp]),

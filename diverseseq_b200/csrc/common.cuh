@@ -110,6 +110,7 @@ struct dvs_ctx {
     uint32_t last_accepts = 0;
     uint32_t last_exact_evals = 0;  // exact re-evaluations forced by the fast path's error bound
     uint64_t last_upload_wire_bytes = 0;
+    uint32_t last_euclid_fallback_pairs = 0;  // pairs the Gram-form Euclid kernel handed to the difference form
     void* upload_stage = nullptr;  // pinned/device staging ring of the packed upload path (upload.cu)
     // pinned scratch for small device->host readbacks
     void* pinned = nullptr;

@@ -233,6 +233,9 @@ int dvs_mash_sketch_host(dvs_ctx* ctx, const uint8_t* seq, uint64_t len, int k, 
  * euclidean_distances (diverse_seq/distance.py:294-336, cluster.py:647-680): ||f_i - f_j||_2 over
  * frequency rows, rows [row_begin,row_end) x all columns, zero diagonal; `dist` may be host or device memory. */
 int dvs_euclid_distances(dvs_ctx* ctx, const dvs_kfreqs* f, uint32_t row_begin, uint32_t row_end, double* dist);
+/* pairs that the Gram-form kernel of the last dvs_euclid_distances(_sharded) on this ctx handed to the
+ * difference form because |a|^2 + |b|^2 - 2 a.b would have cancelled too many digits (near-duplicate rows) */
+uint32_t dvs_euclid_last_fallback_pairs(dvs_ctx* ctx);
 
 /* ---- `dvs ctree` tail: average-linkage tree of a precomputed distance matrix -----------------
  * Replaces sklearn AgglomerativeClustering(metric="precomputed", linkage="average").fit(D) in
