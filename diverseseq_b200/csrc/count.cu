@@ -326,6 +326,18 @@ k_count(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offsets, 
 // sum == number of increments  <=>  no overflow.  An item that fails the check is not added; it is appended to a
 // retry list and recounted by the 32-bit (k+1)-mer kernel.  Blocks that contain an invalid byte, a record edge,
 // or follow such a block count their k-mers one by one in the side table (the reference's run-length rule).
+// 32 contiguous bytes per lane and step (one LDG.256; a warp walks 1 KB per step): the per-step overhead -
+// validity test, halo shuffle, ballot, loop control - is shared by two 16-base blocks, and the second block's
+// halo is the lane's own first block.  Work items start on 32-byte boundaries for this kernel.
+__device__ __forceinline__ void ldg32(const uint8_t* p, uint32_t (&v)[8]) {
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ uint32_t pack16w(uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    return pack16p(make_uint4(x, y, z, w));
+}
+
 template <bool SCR, int THREADS, int PF>
 __global__ void __launch_bounds__(THREADS, 1)
 k_count_s3(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offsets, const CountWork* __restrict__ work,
@@ -335,7 +347,7 @@ k_count_s3(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offset
     __shared__ uint32_t s_item, s_sum, s_inc;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int kWarps = THREADS / 32;
-    constexpr uint32_t kFull = 0xffffffffu;
+    constexpr uint32_t kFull = 0xffffffffu, kStep = 1024u;
     const int kk = k + 2;
     const uint32_t mask = (1u << (2 * kk)) - 1u;  // kk <= 8
     const uint32_t mask_k = (1u << (2 * k)) - 1u;
@@ -344,7 +356,7 @@ k_count_s3(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offset
     char* const hist_b = reinterpret_cast<char*>(hist);
     char* const side_b = reinterpret_cast<char*>(side);
     const uint32_t offmask = mask << 1 & ~3u, sidemask4 = mask_k << 2;
-    const uint32_t lane16 = 16u * (uint32_t)lane;
+    const uint32_t lane32 = 32u * (uint32_t)lane;
 
     for (;;) {
         if (tid == 0) {
@@ -364,29 +376,39 @@ k_count_s3(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offset
             for (uint32_t i = tid; i < n4; i += THREADS) h4[i] = make_uint4(0, 0, 0, 0);
         }
         __syncthreads();
-        uint32_t n_fast = 0;  // fast blocks of this thread: 5 (k+2)-mer increments each
+        uint32_t n_fast = 0;  // fast 16-base blocks of this thread: 5 (k+2)-mer increments each
         // v = (k+2)-mer << 1 with garbage above bit 2kk: byte offset of its counter word in bits [2kk:2], half in bit 1
         auto bump_v = [&](uint32_t v) {
             uint32_t off = v & offmask;
             if (SCR) off ^= (off >> 5) & ~3u;
             atomicAdd(reinterpret_cast<uint32_t*>(hist_b + off), (v & 2u) ? 0x10000u : 1u);
         };
+        // the five (k+2)-mers ending at block positions 2, 5, 8, 11, 14 and the k-mer ending at position 15
+        auto fast_block = [&](uint32_t pc, uint32_t pp) {
+#pragma unroll
+            for (int t = 0; t < 5; ++t) bump_v(__funnelshift_r(pc, pp, 25 - 6 * t));
+            atomicAdd(reinterpret_cast<uint32_t*>(side_b + ((pc << 2) & sidemask4)), 1u);
+        };
 
         const uint32_t item_len = (uint32_t)(w.end - w.begin);
         const uint32_t rs = start > w.begin ? (uint32_t)min(start - w.begin, (uint64_t)item_len) : 0u;
         const uint32_t re = end < w.end ? (end > w.begin ? (uint32_t)(end - w.begin) : 0u) : item_len;
-        const uint32_t span = ((item_len + kWarps - 1) / kWarps + 511u) & ~511u;
+        const uint32_t span = ((item_len + kWarps - 1) / kWarps + kStep - 1u) & ~(kStep - 1u);
         const uint32_t r0 = min(item_len, (uint32_t)warp * span);
         const uint32_t r1 = min(item_len, r0 + span);
         const uint8_t* base = seqs + w.begin;
         const uint32_t safe_hi = min(re, r1);
         uint32_t carry_pc = 0;
         bool carry_ok = false;
-        uint4 ring[PF];
+        uint32_t ring[PF][8];
 #pragma unroll
         for (int u = 0; u < PF; ++u) {
-            const uint32_t a = r0 + 512u * u + lane16;
-            ring[u] = (a < r1) ? ldg16(base + a) : make_uint4(~0u, ~0u, ~0u, ~0u);
+            const uint32_t a = r0 + kStep * u + lane32;
+            if (a < r1) ldg32(base + a, ring[u]);
+            else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) ring[u][q] = ~0u;
+            }
         }
         if (r0 < r1) {
             const uint4 h = ldg16(base + r0 - 16);
@@ -394,59 +416,61 @@ k_count_s3(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offset
             carry_ok = (((h.x | h.y | h.z | h.w) & 0xFCFCFCFCu) == 0) && (a0 >= start + 16) && (a0 <= end);
             carry_pc = pack16p(h);
         }
-        for (uint32_t rbase = r0; rbase < r1; rbase += 512u * PF) {
+        for (uint32_t rbase = r0; rbase < r1; rbase += kStep * PF) {
 #pragma unroll
           for (int u = 0; u < PF; ++u) {
-            const uint32_t r = rbase + 512u * u;
+            const uint32_t r = rbase + kStep * u;
             if (r >= r1) break;  // warp-uniform
-            const uint32_t a = r + lane16;
-            const uint4 cur = ring[u];
-            // interior steps (warp-uniform test): all 512 bytes lie inside the record and the span, so only the
-            // bytes themselves can invalidate a block
-            bool ok = ((cur.x | cur.y | cur.z | cur.w) & 0xFCFCFCFCu) == 0;
-            if (!(r >= rs && r + 512u <= safe_hi)) ok = ok && (a >= rs) && (a + 16 <= re) && (a < r1);
-            const uint32_t pc = pack16p(cur);
-            // refill the slot only now: in the common path `cur` is dead from here on, so the load lands in
-            // the same registers without a copy (the per-byte path re-reads its 32 bytes)
-            ring[u] = (a + 512u * PF < r1) ? ldg16(base + a + 512u * PF) : make_uint4(~0u, ~0u, ~0u, ~0u);
-            uint32_t pp = __shfl_up_sync(kFull, pc, 1);
-            if (lane == 0) pp = carry_pc;
+            const uint32_t a = r + lane32;
+            uint32_t any = ring[u][0] | ring[u][1] | ring[u][2] | ring[u][3] | ring[u][4] | ring[u][5] | ring[u][6] | ring[u][7];
+            // interior steps (warp-uniform test): the whole KB lies inside the record and the span, so only the
+            // bytes themselves can invalidate a lane's 32 bases
+            bool ok = (any & 0xFCFCFCFCu) == 0;
+            if (!(r >= rs && r + kStep <= safe_hi)) ok = ok && (a >= rs) && (a + 32 <= safe_hi);
+            const uint32_t pc0 = pack16w(ring[u][0], ring[u][1], ring[u][2], ring[u][3]);
+            const uint32_t pc1 = pack16w(ring[u][4], ring[u][5], ring[u][6], ring[u][7]);
+            // refill the slot only now: the raw bytes are dead from here on (the per-byte path re-reads them)
+            {
+                const uint32_t an = a + kStep * PF;
+                if (an < r1) ldg32(base + an, ring[u]);
+                else {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) ring[u][q] = ~0u;
+                }
+            }
+            uint32_t pp0 = __shfl_up_sync(kFull, pc1, 1);
+            if (lane == 0) pp0 = carry_pc;
             const uint32_t okmask = __ballot_sync(kFull, ok);
-            // the five (k+2)-mers ending at block positions 2, 5, 8, 11, 14 and the k-mer ending at position 15
-            auto fast_block = [&]() {
-#pragma unroll
-                for (int t = 0; t < 5; ++t) bump_v(__funnelshift_r(pc, pp, 25 - 6 * t));
-                atomicAdd(reinterpret_cast<uint32_t*>(side_b + ((pc << 2) & sidemask4)), 1u);
-                ++n_fast;
-            };
-            if (okmask == kFull && carry_ok) {  // warp-uniform: the common case
-                fast_block();
-            } else {
+            bool fast = okmask == kFull && carry_ok;  // warp-uniform: the common case
+            if (!fast) {
                 const bool prev_ok = lane == 0 ? carry_ok : ((okmask >> (lane - 1)) & 1u) != 0;
-                if (ok && prev_ok) {
-                    fast_block();
-                } else if (a < r1) {
-                    // per-byte path: every k-mer ending in this block, one by one, into the side table
-                    const uint4 prev = ldg16(base + a - 16), cur2 = ldg16(base + a);
-                    const uint32_t wv[8] = {prev.x, prev.y, prev.z, prev.w, cur2.x, cur2.y, cur2.z, cur2.w};
-                    uint32_t run = 0, idx = 0;
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const uint64_t p = w.begin + a + i - 16;
-                        uint32_t bb = (wv[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-                        if (p < start || p >= end) bb = 0xFFu;
-                        if (bb >= 4u) {
-                            run = 0;
-                            idx = 0;
-                        } else {
-                            idx = ((idx << 2) | bb) & mask_k;
-                            ++run;
-                            if (i >= 16 && run >= (uint32_t)k) atomicAdd(&side[idx], 1u);
-                        }
+                fast = ok && prev_ok;
+            }
+            if (fast) {
+                fast_block(pc0, pp0);
+                fast_block(pc1, pc0);
+                n_fast += 2;
+            } else if (a < r1) {
+                // per-byte path: every k-mer ending in this lane's bytes (inside the item), one by one, side table
+                const uint4 q0 = ldg16(base + a - 16), q1 = ldg16(base + a), q2 = ldg16(base + a + 16);
+                const uint32_t wv[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+                uint32_t run = 0, idx = 0;
+#pragma unroll 4
+                for (int i = 0; i < 48; ++i) {
+                    const uint64_t p = w.begin + a + i - 16;
+                    uint32_t bb = (wv[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+                    if (p < start || p >= end) bb = 0xFFu;
+                    if (bb >= 4u) {
+                        run = 0;
+                        idx = 0;
+                    } else {
+                        idx = ((idx << 2) | bb) & mask_k;
+                        ++run;
+                        if (i >= 16 && a + i - 16 < r1 && run >= (uint32_t)k) atomicAdd(&side[idx], 1u);
                     }
                 }
             }
-            carry_pc = __shfl_sync(kFull, pc, 31);
+            carry_pc = __shfl_sync(kFull, pc1, 31);
             carry_ok = (okmask >> 31) != 0;
           }
         }
@@ -720,7 +744,7 @@ static int count_core(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, 
             s->work_item_begin[r] = (uint32_t)work.size();
             uint64_t b = s->h_offsets[r], e = s->h_offsets[r + 1];
             if (e <= b) continue;
-            uint64_t a0 = b & ~15ULL, a1 = (e + 15) & ~15ULL;
+            uint64_t a0 = b & ~31ULL, a1 = (e + 15) & ~15ULL;  // (32-byte aligned starts: k_count_s3 loads 32 bytes per lane)
             for (uint64_t a = a0; a < a1; a += chunk)
                 for (uint32_t p = 0; p < nparts; ++p) work.push_back({a, std::min(a + chunk, a1), r, p});
         }
@@ -794,14 +818,14 @@ static int count_core(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, 
                 // The 8-mer table spreads over 32,768 words: bank scrambling costs two instructions per atomic
                 // and buys nothing here unless asked for (DVS_COUNT_SCRAMBLE=1)
                 const bool scr3 = scr_env && scr_env[0] == '1';
-                // DVS_COUNT_S3_SHAPE (A/B measurements): 0 = 1024 threads x 4 steps in flight (64 registers),
-                // 1 = 512 threads x 8 steps, 2 = 512 threads x 4 steps
+                // DVS_COUNT_S3_SHAPE (A/B measurements): 0 = 1024 threads x 2 KB-steps in flight per warp,
+                // 1 = 1024 threads x 3 steps, 2 = 512 threads x 4 steps
                 const char* shape_env = getenv("DVS_COUNT_S3_SHAPE");
                 const int shape = shape_env ? atoi(shape_env) : 0;
-                auto s3 = scr3 ? k_count_s3<true, 1024, 4>
-                               : (shape == 1 ? k_count_s3<false, 512, 8>
-                                             : (shape == 2 ? k_count_s3<false, 512, 4> : k_count_s3<false, 1024, 4>));
-                const int s3_threads = (!scr3 && (shape == 1 || shape == 2)) ? 512 : 1024;
+                auto s3 = scr3 ? k_count_s3<true, 1024, 2>
+                               : (shape == 1 ? k_count_s3<false, 1024, 3>
+                                             : (shape == 2 ? k_count_s3<false, 512, 4> : k_count_s3<false, 1024, 2>));
+                const int s3_threads = (!scr3 && shape == 2) ? 512 : 1024;
                 auto rk = scramble ? k_count<MODE_SUPER, true, 512> : k_count<MODE_SUPER, false, 512>;
                 TRY_F(cudaFuncSetAttribute(s3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
                 const size_t retry_bytes = (size_t)dim * 20;
