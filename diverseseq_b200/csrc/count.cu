@@ -818,13 +818,13 @@ static int count_core(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, 
                 // The 8-mer table spreads over 32,768 words: bank scrambling costs two instructions per atomic
                 // and buys nothing here unless asked for (DVS_COUNT_SCRAMBLE=1)
                 const bool scr3 = scr_env && scr_env[0] == '1';
-                // DVS_COUNT_S3_SHAPE (A/B measurements): 0 = 1024 threads x 2 KB-steps in flight per warp,
-                // 1 = 1024 threads x 3 steps, 2 = 512 threads x 4 steps
+                // DVS_COUNT_S3_SHAPE (A/B measurements): 0 = 1024 threads x 3 KB-steps in flight per warp (8.78 ms on
+                // the bench set), 1 = 1024 threads x 2 steps (8.97 ms), 2 = 512 threads x 4 steps (9.03 ms)
                 const char* shape_env = getenv("DVS_COUNT_S3_SHAPE");
                 const int shape = shape_env ? atoi(shape_env) : 0;
                 auto s3 = scr3 ? k_count_s3<true, 1024, 2>
-                               : (shape == 1 ? k_count_s3<false, 1024, 3>
-                                             : (shape == 2 ? k_count_s3<false, 512, 4> : k_count_s3<false, 1024, 2>));
+                               : (shape == 1 ? k_count_s3<false, 1024, 2>
+                                             : (shape == 2 ? k_count_s3<false, 512, 4> : k_count_s3<false, 1024, 3>));
                 const int s3_threads = (!scr3 && shape == 2) ? 512 : 1024;
                 auto rk = scramble ? k_count<MODE_SUPER, true, 512> : k_count<MODE_SUPER, false, 512>;
                 TRY_F(cudaFuncSetAttribute(s3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));

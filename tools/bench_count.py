@@ -17,8 +17,8 @@ sys.path.insert(0, str(ROOT))
 from diverseseq_b200 import _lib  # noqa: E402
 
 VARIANTS = {
-    "default": {},                                   # (k+2)-mers / 16-bit halves, 1024 threads x 2 KB-steps in flight
-    "s3_1024x3": {"DVS_COUNT_S3_SHAPE": "1"},
+    "default": {},                                   # (k+2)-mers / 16-bit halves, 1024 threads x 3 KB-steps in flight
+    "s3_1024x2": {"DVS_COUNT_S3_SHAPE": "1"},
     "s3_512x4": {"DVS_COUNT_S3_SHAPE": "2"},
     "s3scr": {"DVS_COUNT_SCRAMBLE": "1"},
     "super": {"DVS_COUNT_S3": "0"},                   # (k+1)-mer kernel of round 1
@@ -32,7 +32,7 @@ def main():
     ap.add_argument("--k", type=int, default=6)
     ap.add_argument("--nrec", type=int, default=10500)
     ap.add_argument("--mean-len", type=int, default=4_000_000)
-    ap.add_argument("--variants", default="default,s3_1024x3,s3_512x4,super")
+    ap.add_argument("--variants", default="default,s3_1024x2,s3_512x4,super")
     ap.add_argument("--reps", type=int, default=5)
     a = ap.parse_args()
     ctx = _lib.Context(0)
