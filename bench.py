@@ -389,19 +389,36 @@ def side_metrics(a, ctx, comm, rank, world, device, barrier, hbm_peak):
     out[f"max_k8_{n_e}_genomes"] = sweeps
     kf8.close(); ss.close()
 
-    # ---- north star: k=12 counting (dense u32 rows, global RED.ADD), records sharded, no collective ----
+    # ---- north star: k=12 counting, records sharded, no collective ----
+    # sparse rows (distinct k-mers + counts, 8 bytes each: the only form that holds 10.5k genomes) ...
+    n12 = 512
+    ss = _lib.SeqSet.synth(ctx, SEED + 12 + rank, n12, a.nfam, a.mean_len)
+    _lib.KSparse.count(ctx, ss, 12).close()
+    w12, sp = wall(lambda: _lib.KSparse.count(ctx, ss, 12))
+    ms12 = max_over_ranks(ctx.phase_ms(_lib.PHASE_SPARSE), device)
+    nnz, tot, _e, _v = sp.stats()
+    b12 = sum_over_ranks(ss.total_bases, device)
+    nnz_all = sum_over_ranks(float(nnz.sum()), device)
+    sparse_bytes = b12 + 8.0 * nnz_all  # L + 8 D_r per record
+    out["count_k12_sparse"] = {"genomes": n12 * world, "gbp": b12 / 1e9, "kernel_ms": ms12, "gbp_per_s": b12 / ms12 / 1e6,
+                               "gbp_per_s_wall": b12 / w12 / 1e9, "distinct_per_valid_kmer": nnz_all / max(sum_over_ranks(float(tot.sum()), device), 1.0),
+                               "roofline": {"bound": "hbm", "achieved": sparse_bytes / ms12 / 1e6, "peak": hbm_peak * world,
+                                            "unit": "GB/s", "frac": sparse_bytes / ms12 / 1e6 / (hbm_peak * world),
+                                            "note": "sparse rows: L + 8 D_r bytes per record (~8 B/bp); three radix passes "
+                                                    "through shared memory (csrc/sparse.cu)"}}
+    sp.close(); ss.close()
+    # ... and the dense u32 rows of round 1 (global RED.ADD into an L2-resident 64 MB row), for comparison
     n12 = 64
-    b, e = shard.shard_bounds(n12 * world, world, rank)
     ss = _lib.SeqSet.synth(ctx, SEED + 12 + rank, n12, a.nfam, a.mean_len)
     _lib.KFreqs.count(ctx, ss, 12).close()
     w12, kf12 = wall(lambda: _lib.KFreqs.count(ctx, ss, 12))
     ms12 = max_over_ranks(ctx.phase_ms(_lib.PHASE_COUNT_KERNEL), device)
     b12 = sum_over_ranks(ss.total_bases, device)
     dense_bytes = b12 + n12 * world * 4 * 4 ** 12
-    out["count_k12"] = {"genomes": n12 * world, "gbp": b12 / 1e9, "kernel_ms": ms12, "gbp_per_s": b12 / ms12 / 1e6,
-                        "roofline": {"bound": "hbm", "achieved": dense_bytes / ms12 / 1e6, "peak": hbm_peak * world,
-                                     "unit": "GB/s", "frac": dense_bytes / ms12 / 1e6 / (hbm_peak * world),
-                                     "note": "dense u32 rows: L + 4*4^k bytes per record (17.8 B/bp)"}}
+    out["count_k12_dense"] = {"genomes": n12 * world, "gbp": b12 / 1e9, "kernel_ms": ms12, "gbp_per_s": b12 / ms12 / 1e6,
+                              "roofline": {"bound": "hbm", "achieved": dense_bytes / ms12 / 1e6, "peak": hbm_peak * world,
+                                           "unit": "GB/s", "frac": dense_bytes / ms12 / 1e6 / (hbm_peak * world),
+                                           "note": "dense u32 rows: L + 4*4^k bytes per record (17.8 B/bp)"}}
     kf12.close(); ss.close()
     return out
 
@@ -541,7 +558,7 @@ def main():
     achieved = algo_bytes / (kc_ms * 1e-3) / 1e9
     traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture
     try:
-        tr = json.loads((ROOT / "profiles" / "r1_k_count_traffic.json").read_text())
+        tr = json.loads((ROOT / "profiles" / "r2_k_count_traffic.json").read_text())
         wl = tr["workload"]
         if (wl["nrec"], wl["mean_len"], wl["k"]) == (a.nrec, a.mean_len, a.k):
             traffic = tr["traffic_bytes_per_launch"]

@@ -113,3 +113,34 @@ def test_count_refuses_nothing_below_4g_bases(lib, ctx):
     kf = lib.KFreqs.count(ctx, lib.SeqSet.from_seqs(ctx, [np.zeros(70_000, dtype=np.uint8)]), 2)
     c = kf.download()[0]
     assert int(c[0, 0]) == 69_999 and int(c.sum()) == 69_999
+
+
+def test_include_rerun_matches_oracle(lib, orc, brca1):
+    """`dvs nmost --include` (cli.py:445-474): shuffle with the seed, select, then nmost over selected + included
+    names with n = their number; a name already selected is listed twice and contributes two rows, as upstream"""
+    from diverseseq_b200 import _dvs as dvs, records
+    store = dvs.make_zarr_store()
+    names = list(brca1)
+    for nm in names:
+        store.write(nm, brca1[nm].tobytes())
+    k, n, seed = 4, 8, 11
+    order = records.shuffled_seqids(store.get_seqids(), seed)
+    rng = np.random.default_rng(seed=seed)
+    expect_order = list(names)
+    rng.shuffle(expect_order)
+    assert order == expect_order
+    flat, off = lib.concat([brca1[nm] for nm in order])
+    first = orc.select_seqs(flat, off, np.arange(len(order)), k, "nmost", n)
+    sel_names = [order[i] for i in first.ids]
+    include = ["Human", sel_names[2]]  # one new record and one that is already selected
+    res = records.select_nmost(store, n, k, seed=seed, include=include)
+    final_names = sel_names + include
+    flat2, off2 = lib.concat([brca1[nm] for nm in final_names])
+    second = orc.select_seqs(flat2, off2, np.arange(len(final_names)), k, "nmost", len(final_names))
+    assert res.record_names == [final_names[i] for i in second.ids] and res.size == len(final_names)
+    assert [r[2] for r in res.records] == second.delta_jsd.tolist() and res.total_jsd == second.total_jsd
+    with pytest.raises(ValueError):
+        records.select_nmost(store, n, k, seed=seed, include=["not-there"])
+    m = records.select_max(store, 5, 9, k, stat="cov", seed=seed)
+    mexp = orc.select_seqs(flat, off, np.arange(len(order)), k, "cov", 5, 9)
+    assert m.record_names == [order[i] for i in mexp.ids]
