@@ -211,12 +211,14 @@ k_sp_partition(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ of
 __global__ void __launch_bounds__(kSpBucketThreads)
 k_sp_bucket(const uint16_t* __restrict__ lowbuf, const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ bucket_ptr,
             uint32_t nrec, uint32_t nb, uint32_t* __restrict__ out_idx, uint32_t* __restrict__ out_cnt,
-            uint32_t* __restrict__ bucket_nnz) {
+            uint32_t* __restrict__ bucket_nnz, const uint64_t* __restrict__ list, const uint32_t* __restrict__ list_count) {
     __shared__ __align__(16) uint32_t hist[kSpLowBins];
     __shared__ uint32_t s_warp[34];
-    const uint64_t npairs = (uint64_t)nrec * nb;
+    // list == NULL: every (record, bucket) pair; otherwise the listed pairs only (buckets too large for 16-bit bins)
+    const uint64_t npairs = list ? (uint64_t)*list_count : (uint64_t)nrec * nb;
     constexpr uint32_t kBinsPer = kSpLowBins / kSpBucketThreads;  // 16 consecutive bins per thread
-    for (uint64_t p = blockIdx.x; p < npairs; p += gridDim.x) {
+    for (uint64_t q = blockIdx.x; q < npairs; q += gridDim.x) {
+        const uint64_t p = list ? list[q] : q;
         const uint32_t rec = (uint32_t)(p / nb), b = (uint32_t)(p % nb);
         const uint32_t* bp = bucket_ptr + (size_t)rec * (nb + 1);
         const uint32_t s0 = bp[b], n = bp[b + 1] - s0;
@@ -253,6 +255,72 @@ k_sp_bucket(const uint16_t* __restrict__ lowbuf, const uint64_t* __restrict__ of
         }
         if (threadIdx.x == 0) bucket_nnz[p] = nnz;
         __syncthreads();
+    }
+}
+
+// pass 2, warp form: ONE WARP per (record, bucket) - no block barriers, 8 KB of shared memory per warp (4,096 bins
+// as 16-bit halves of 2,048 words, safe while the bucket has fewer than 65,536 keys; larger buckets are listed and
+// left to k_sp_bucket).  The bins are walked one word per lane and iteration, so that the 32 lanes hold 64
+// consecutive bins and the non-zero ones are compacted with two ballots: consecutive lanes write consecutive
+// output slots (coalesced), and no counting pre-pass is needed.
+constexpr int kSpWarpsPerCta = 8;
+__global__ void __launch_bounds__(32 * kSpWarpsPerCta)
+k_sp_bucket_warp(const uint16_t* __restrict__ lowbuf, const uint64_t* __restrict__ offsets,
+                 const uint32_t* __restrict__ bucket_ptr, uint32_t nrec, uint32_t nb, uint32_t* __restrict__ out_idx,
+                 uint32_t* __restrict__ out_cnt, uint32_t* __restrict__ bucket_nnz, uint64_t* __restrict__ big_list,
+                 uint32_t* __restrict__ big_count) {
+    extern __shared__ __align__(16) uint32_t sp_wsmem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* h = sp_wsmem + warp * (kSpLowBins / 2);
+    const uint64_t npairs = (uint64_t)nrec * nb;
+    const uint32_t lt = (1u << lane) - 1u;
+    for (uint64_t p = (uint64_t)blockIdx.x * kSpWarpsPerCta + warp; p < npairs; p += (uint64_t)gridDim.x * kSpWarpsPerCta) {
+        const uint32_t rec = (uint32_t)(p / nb), b = (uint32_t)(p % nb);
+        const uint32_t* bp = bucket_ptr + (size_t)rec * (nb + 1);
+        const uint32_t s0 = bp[b], n = bp[b + 1] - s0;
+        if (n == 0) {
+            if (lane == 0) bucket_nnz[p] = 0;
+            continue;
+        }
+        if (n > 65535u) {  // a 16-bit half could overflow: the CTA kernel with 32-bit bins takes this bucket
+            if (lane == 0) big_list[atomicAdd(big_count, 1u)] = p;
+            continue;
+        }
+        const uint64_t base = offsets[rec] + s0;
+        uint4* h4 = reinterpret_cast<uint4*>(h);
+#pragma unroll 4
+        for (uint32_t i = lane; i < kSpLowBins / 8; i += 32) h4[i] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        for (uint32_t e = lane; e < n; e += 32) {
+            const uint32_t key = lowbuf[base + e];
+            atomicAdd(&h[key >> 1], (key & 1u) ? 0x10000u : 1u);
+        }
+        __syncwarp();
+        uint32_t run = 0;
+        const uint32_t idx_hi = b << kSpLowBits;
+#pragma unroll 4
+        for (uint32_t i = 0; i < kSpLowBins / 64; ++i) {
+            const uint32_t wd = i * 32 + lane, v = h[wd];
+            const uint32_t lo = v & 0xFFFFu, hi = v >> 16;
+            const uint32_t mlo = __ballot_sync(0xffffffffu, lo != 0), mhi = __ballot_sync(0xffffffffu, hi != 0);
+            uint32_t pos = run + __popc(mlo & lt) + __popc(mhi & lt);
+            if (lo) {
+                out_idx[base + pos] = idx_hi | (2 * wd);
+                out_cnt[base + pos] = lo;
+                ++pos;
+            }
+            if (hi) {
+                out_idx[base + pos] = idx_hi | (2 * wd + 1);
+                out_cnt[base + pos] = hi;
+            }
+            run += __popc(mlo) + __popc(mhi);
+        }
+        for (uint32_t e = run + lane; e < n; e += 32) {  // unused slots of the bucket: "no entry"
+            out_idx[base + e] = 0xFFFFFFFFu;
+            out_cnt[base + e] = 0u;
+        }
+        if (lane == 0) bucket_nnz[p] = run;
+        __syncwarp();
     }
 }
 
@@ -445,11 +513,35 @@ int dvs_count_kmers_sparse(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_sta
         ctx->launches++;
         TRY_P(cudaGetLastError());
         const uint64_t npairs = (uint64_t)nrec * nb;
-        const unsigned g_b = (unsigned)std::min<uint64_t>(npairs, (uint64_t)ctx->sm_count * 8 * 4);
-        k_sp_bucket<<<g_b, kSpBucketThreads, 0, st>>>(d_low.p, sp->offsets.p, sp->bucket_ptr.p, nrec, nb, sp->idx.p,
-                                                      sp->cnt.p, sp->bucket_nnz.p);
-        ctx->launches++;
-        TRY_P(cudaGetLastError());
+        // DVS_SPARSE_CTA_BUCKETS=1: the CTA-per-bucket kernel for everything (A/B measurements)
+        const char* cta_env = getenv("DVS_SPARSE_CTA_BUCKETS");
+        if (cta_env && cta_env[0] == '1') {
+            const unsigned g_b = (unsigned)std::min<uint64_t>(npairs, (uint64_t)ctx->sm_count * 8 * 4);
+            k_sp_bucket<<<g_b, kSpBucketThreads, 0, st>>>(d_low.p, sp->offsets.p, sp->bucket_ptr.p, nrec, nb, sp->idx.p,
+                                                          sp->cnt.p, sp->bucket_nnz.p, nullptr, nullptr);
+            ctx->launches++;
+            TRY_P(cudaGetLastError());
+        } else {
+            // a bucket of more than 65,535 keys needs >= 65,536 k-mers that share their first k - 6 bases in one record
+            DevBuf<uint64_t> d_big;
+            DevBuf<uint32_t> d_nbig;
+            const uint64_t big_cap = std::max<uint64_t>(s->total / 65536 + nrec, 1);
+            if (d_big.alloc(big_cap) != DVS_OK || d_nbig.alloc(1) != DVS_OK) return fail(DVS_ERR_CUDA);
+            TRY_P(cudaMemsetAsync(d_nbig.p, 0, sizeof(uint32_t), st));
+            const size_t smem_w = (size_t)kSpWarpsPerCta * (kSpLowBins / 2) * sizeof(uint32_t);
+            TRY_P(cudaFuncSetAttribute(k_sp_bucket_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+            const unsigned g_w = (unsigned)std::min<uint64_t>((npairs + kSpWarpsPerCta - 1) / kSpWarpsPerCta,
+                                                              (uint64_t)ctx->sm_count * 3 * 4);
+            k_sp_bucket_warp<<<g_w, 32 * kSpWarpsPerCta, smem_w, st>>>(d_low.p, sp->offsets.p, sp->bucket_ptr.p, nrec, nb,
+                                                                       sp->idx.p, sp->cnt.p, sp->bucket_nnz.p, d_big.p,
+                                                                       d_nbig.p);
+            ctx->launches++;
+            TRY_P(cudaGetLastError());
+            k_sp_bucket<<<(unsigned)std::min<uint64_t>(big_cap, (uint64_t)ctx->sm_count * 8), kSpBucketThreads, 0, st>>>(
+                d_low.p, sp->offsets.p, sp->bucket_ptr.p, nrec, nb, sp->idx.p, sp->cnt.p, sp->bucket_nnz.p, d_big.p, d_nbig.p);
+            ctx->launches++;
+            TRY_P(cudaGetLastError());
+        }
         k_sp_nnz<<<nrec, 256, 0, st>>>(sp->bucket_nnz.p, nb, sp->nnz.p);
         ctx->launches++;
         TRY_P(cudaGetLastError());
