@@ -56,6 +56,10 @@ def parse_args():
                     help="N>1 selection: 'sharded' = ONE single-pass selection over all records, candidate-sharded "
                          "with a per-round all-reduce(min) over NVLink; 'chunked' = the reference's -np N semantics "
                          "(select per GPU, merge with final_nmost)")
+    ap.add_argument("--overlap", default="off", choices=["on", "off"],
+                    help="N=1: dvs_count_select (nmost rounds trail the counting on the same GPU) instead of the two "
+                         "calls; measured slower than the two calls (profiles/r2_overlap_ab.txt), hence off")
+    ap.add_argument("--chunks", type=int, default=0, help="counting launches of dvs_count_select (0 = library default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ctree", action="store_true", help="skip the ctree pairs/s side measurements (N=1 only)")
@@ -75,6 +79,9 @@ def workload_config(a, world):
                         f"records sharded x{world} (rows pushed to all peers during counting); ONE single-pass nmost "
                         f"over all {world}x{a.nrec} records, candidate-sharded, all-reduce(min) per round over NVLink"),
         "l2": "inputs (~42 GB/GPU) are far larger than the 126 MB L2, no flush needed",
+        "overlap": ("dvs_count_select: records counted in the selection's examination order on a second stream, the "
+                    "nmost rounds trail the published rows on the same GPU" if world == 1 and a.overlap == "on" else
+                    "none (count, then select)"),
     }
 
 
@@ -496,6 +503,19 @@ def main():
             idx, delta, stats = shard.select_sharded(ctx, comm, kf, order, _lib.MODE_NMOST, a.n)
             kf.close()
         else:
+            if world == 1 and a.overlap == "on":
+                # counting with the nmost rounds trailing it (dvs_count_select): one call, two streams
+                kf, idx, delta, stats = _lib.KFreqs.count_select(ctx, ss, a.k, order, _lib.MODE_NMOST, a.n, a.n,
+                                                                 chunks=a.chunks)
+                t1 = time.perf_counter()
+                kf.close()
+                phase["trail_accepts"] = int(ctx._lib.dvs_select_last_trail_accepts(ctx.handle))
+                phase["count_ms"] = ctx.phase_ms(_lib.PHASE_COUNT_LAUNCHES)  # the counting launches alone, summed
+                phase["count_region_ms"] = ctx.phase_ms(_lib.PHASE_COUNT_KERNEL)  # first launch .. last entropy launch
+                phase["freq_entropy_ms"] = 0.0  # (inside the chunk loop)
+                phase["select_ms"] = ctx.phase_ms(_lib.PHASE_SELECT)
+                phase["host_wall_ms"] = {"count_select_call": (t1 - t0) * 1e3}
+                return idx, delta, stats
             kf = _lib.KFreqs.count(ctx, ss, a.k)
             t1 = time.perf_counter()
             if world > 1:
@@ -545,6 +565,18 @@ def main():
     accepts = int(ctx._lib.dvs_select_last_accepts(ctx.handle))
     value = total_bases / (ms_step * 1e-3) / 1e9
 
+    overlapped = world == 1 and a.overlap == "on"
+    alone_ms = None
+    if overlapped:  # the same kernel without the selection beside it (explains the in-step figure; not the headline)
+        _lib.KFreqs.count(ctx, seqset, a.k).close()
+        al = []
+        for _ in range(3):
+            kfa = _lib.KFreqs.count(ctx, seqset, a.k)
+            ctx.sync()
+            al.append(ctx.phase_ms(_lib.PHASE_COUNT_KERNEL))
+            kfa.close()
+        alone_ms = float(np.median(al))
+
     # ---- roofline of the dominant kernel (k_count), timed live by CUDA events on its stream ----
     kc_ms = float(np.mean(count_ms))
     dim = 4 ** a.k
@@ -568,6 +600,11 @@ def main():
                 "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
                 "kernel_ms": kc_ms, "algorithmic_bytes_per_launch": algo_bytes}
+    if overlapped:
+        roofline["note"] = ("in-step: sum of the chunked counting launches while the selection kernel shares the SMs "
+                            "(56-register kernel shape); `alone` = the stand-alone launch of the same run")
+        roofline["alone"] = {"kernel_ms": alone_ms, "achieved": algo_bytes / (alone_ms * 1e-3) / 1e9,
+                             "frac": algo_bytes / (alone_ms * 1e-3) / 1e9 / peak}
 
     # ---- end to end through the host-buffer API: pinned host -> device copy inside the timed region ----
     e2e = None
@@ -647,7 +684,9 @@ def main():
                           "freq_entropy_ms": float(np.mean(fe_ms)), "nmost_wall_s": float(np.mean(sel_ms)) * 1e-3,
                           "nmost_accepts": accepts, "total_gbp": total_bases / 1e9,
                           "selected_head": idx[:8].tolist(), "total_jsd": float(stats[0]),
-                          "host_wall_ms_last_step": phase.get("host_wall_ms"), "ctree": ctree}}
+                          "host_wall_ms_last_step": phase.get("host_wall_ms"),
+                          "count_region_ms": phase.get("count_region_ms"), "trail_accepts": phase.get("trail_accepts"),
+                          "ctree": ctree}}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

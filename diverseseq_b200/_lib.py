@@ -20,6 +20,7 @@ PHASE_COUNT_KERNEL, PHASE_FREQ_ENTROPY, PHASE_SELECT, PHASE_SKETCH, PHASE_MASH_P
 PHASE_PREP = 7
 PHASE_CLUSTER = 8
 PHASE_SPARSE = 9
+PHASE_COUNT_LAUNCHES = 10
 
 _vp = C.c_void_p
 _u32, _u64, _i32, _f64 = C.c_uint32, C.c_uint64, C.c_int, C.c_double
@@ -69,8 +70,13 @@ SIGNATURES = {
     "dvs_ksparse_download": (_i32, [_vp, _vp, _u32, _vp, _vp, _u64, C.POINTER(_u64)]),
     "dvs_ksparse_free": (None, [_vp]),
     "dvs_select": (_i32, [_vp, _vp, _vp, _u32, _i32, _u32, _u32, _vp, _vp, _vp, C.POINTER(_u32)]),
+    "dvs_count_select": (_i32, [_vp, _vp, _i32, _i32, _vp, _u32, _i32, _u32, _u32, _u32, C.POINTER(_vp), _vp, _vp, _vp,
+                                C.POINTER(_u32)]),
     "dvs_select_last_accepts": (_u32, [_vp]),
     "dvs_select_last_exact_evals": (_u32, [_vp]),
+    "dvs_select_last_trail_accepts": (_u32, [_vp]),
+    "dvs_select_last_trail_launches": (_u32, [_vp]),
+    "dvs_select_last_trail_sms": (_u32, [_vp]),
     "dvs_summed_create": (_i32, [_vp, _vp, _vp, _u32, C.POINTER(_vp)]),
     "dvs_summed_delta_jsd": (_i32, [_vp, _vp, _vp, _u32, _i32, C.POINTER(_f64)]),
     "dvs_summed_delta_jsd_batch": (_i32, [_vp, _vp, _vp, _vp, _vp]),
@@ -407,6 +413,26 @@ class KFreqs(_Handle):
         h = _vp()
         check(ctx._lib.dvs_count_kmers(ctx.handle, seqset.handle, int(k), int(num_states), C.byref(h)))
         return cls(ctx, h)
+
+    @classmethod
+    def count_select(cls, ctx: Context, seqset: SeqSet, k: int, order, mode: int, min_size: int, max_size: int = 0,
+                     num_states: int = 4, chunks: int = 0):
+        """dvs_count_select: counting with the nmost rounds trailing it; returns (KFreqs, indices, delta_jsd, stats5)"""
+        order = np.ascontiguousarray(order, dtype=np.uint32)
+        cap = max(int(min_size), int(max_size), 1) + 1
+        if int(mode) != MODE_NMOST and int(max_size) < int(min_size):
+            cap = order.size + 1
+        idx = np.zeros(cap, dtype=np.uint32)
+        delta = np.zeros(cap, dtype=np.float64)
+        stats = np.zeros(5, dtype=np.float64)
+        size = _u32(0)
+        h = _vp()
+        check(ctx._lib.dvs_count_select(ctx.handle, seqset.handle, int(k), int(num_states),
+                                        ptr(order) if order.size else None, order.size, int(mode), int(min_size),
+                                        int(max_size), int(chunks), C.byref(h), ptr(idx), ptr(delta), ptr(stats),
+                                        C.byref(size)))
+        n = size.value
+        return cls(ctx, h), idx[:n].copy(), delta[:n].copy(), stats
 
     @classmethod
     def count_sharded(cls, ctx: Context, comm: "Comm", seqset: SeqSet, k: int, nrec_per_rank, num_states: int = 4) -> "KFreqs":

@@ -106,8 +106,15 @@ struct dvs_ctx {
     int sm_count = 0;
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;  // second stream (created on demand): counting of dvs_count_select
+    cudaEvent_t ev_first = nullptr, ev_count_done = nullptr, ev_fork = nullptr;
+    unsigned* d_ready = nullptr;      // trailing selection: positions published so far
     uint64_t launches = 0;
+    cudaEvent_t ev_chunk[128] = {};   // per-chunk start/stop of the counting launches (DVS_PHASE_COUNT_LAUNCHES)
+    uint32_t n_chunk_ev = 0;          // pairs recorded by the last chunked counting
     uint32_t last_accepts = 0;
+    uint32_t last_trail_launches = 0, last_trail_sms = 0;  // trailing kernel launches / fewest distinct SMs one sat on
+    uint32_t last_trail_accepts = 0;  // of those, made while the counting was still running (dvs_count_select)
     uint32_t last_exact_evals = 0;  // exact re-evaluations forced by the fast path's error bound
     uint64_t last_upload_wire_bytes = 0;
     uint32_t last_euclid_fallback_pairs = 0;  // pairs the Gram-form Euclid kernel handed to the difference form
@@ -162,6 +169,7 @@ struct dvs_seqset {
     mutable dvs::DevBuf<uint8_t> work_cache;
     mutable uint64_t work_chunk = 0;
     mutable uint32_t work_nparts = 0, work_items = 0;
+    mutable std::vector<uint32_t> work_seq;  // the record sequence the cached list follows (empty: 0..nrec-1)
     mutable std::vector<uint32_t> work_item_begin;  // nrec+1: first work item of every record (items are record-major)
     const uint8_t* data() const { return raw.p + kSeqFrontPad; }
     uint8_t* data() { return raw.p + kSeqFrontPad; }

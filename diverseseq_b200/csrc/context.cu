@@ -81,6 +81,16 @@ void dvs_ctx_destroy(dvs_ctx* ctx) {
         cudaStreamSynchronize(ctx->stream);
         cudaStreamDestroy(ctx->stream);
     }
+    if (ctx->stream2) {
+        cudaStreamSynchronize(ctx->stream2);
+        cudaStreamDestroy(ctx->stream2);
+        cudaEventDestroy(ctx->ev_first);
+        cudaEventDestroy(ctx->ev_count_done);
+        cudaEventDestroy(ctx->ev_fork);
+        cudaFree(ctx->d_ready);
+    }
+    for (cudaEvent_t e : ctx->ev_chunk)
+        if (e) cudaEventDestroy(e);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     upload_stage_free(ctx->upload_stage);
     for (int i = 0; i < kNumPhases; ++i) {
@@ -109,6 +119,18 @@ int dvs_ctx_enable_timing(dvs_ctx* ctx, int on) {
 }
 
 double dvs_ctx_phase_ms(dvs_ctx* ctx, int phase) {
+    if (phase == DVS_PHASE_COUNT_LAUNCHES) {  // sum over the chunk launches of the last chunked counting
+        if (!ctx->n_chunk_ev) return -1.0;
+        double sum = 0.0;
+        for (uint32_t c = 0; c < ctx->n_chunk_ev; ++c) {
+            float ms = 0.0f;
+            if (cudaEventSynchronize(ctx->ev_chunk[2 * c + 1]) != cudaSuccess ||
+                cudaEventElapsedTime(&ms, ctx->ev_chunk[2 * c], ctx->ev_chunk[2 * c + 1]) != cudaSuccess)
+                return -1.0;
+            sum += ms;
+        }
+        return sum;
+    }
     if (phase < 0 || phase >= kNumPhases || !ctx->ev_valid[phase]) return -1.0;
     if (cudaEventSynchronize(ctx->ev_stop[phase]) != cudaSuccess) return -1.0;
     float ms = -1.0f;

@@ -23,6 +23,7 @@
 
 #include "comm.cuh"
 #include "common.cuh"
+#include "fused.cuh"
 #include "entropy.cuh"
 
 namespace dvs {
@@ -339,12 +340,15 @@ __device__ __forceinline__ uint32_t pack16w(uint32_t x, uint32_t y, uint32_t z, 
 }
 
 template <bool SCR, int THREADS, int PF>
-__global__ void __launch_bounds__(THREADS, 1)
-k_count_s3(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offsets, const CountWork* __restrict__ work,
+__device__ __forceinline__ void
+count_s3_body(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offsets, const CountWork* __restrict__ work,
            uint32_t nwork, uint32_t* __restrict__ next_item, int k, uint64_t dim, uint32_t* __restrict__ counts,
-           CountWork* __restrict__ retry, uint32_t* __restrict__ retry_count) {
+           CountWork* __restrict__ retry, uint32_t* __restrict__ retry_count, uint32_t* resident) {
     extern __shared__ uint32_t hist[];  // [4^(k+2) / 2] packed halves, then side[4^k]
     __shared__ uint32_t s_item, s_sum, s_inc;
+    // dvs_count_select: how many counting CTAs are resident right now (the trailing selection kernel is launched
+    // when every SM holds one, so that exactly one of its CTAs fits beside each)
+    if (resident && threadIdx.x == 0) atomicAdd(resident, 1u);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int kWarps = THREADS / 32;
     constexpr uint32_t kFull = 0xffffffffu, kStep = 1024u;
@@ -523,16 +527,35 @@ k_count_s3(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offset
         }
         __syncthreads();  // s_item / hist reuse
     }
+    if (resident && threadIdx.x == 0) atomicSub(resident, 1u);
+}
+
+template <bool SCR, int THREADS, int PF>
+__global__ void __launch_bounds__(THREADS, 1)
+k_count_s3(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offsets, const CountWork* __restrict__ work,
+           uint32_t nwork, uint32_t* __restrict__ next_item, int k, uint64_t dim, uint32_t* __restrict__ counts,
+           CountWork* __restrict__ retry, uint32_t* __restrict__ retry_count) {
+    count_s3_body<SCR, THREADS, PF>(seqs, offsets, work, nwork, next_item, k, dim, counts, retry, retry_count, nullptr);
+}
+// the form dvs_count_select launches: 1,024 threads x 56 registers leave 8,192 registers - one CTA of the trailing
+// selection kernel - free on the SM
+template <int MAXR>
+__global__ void __maxnreg__(MAXR)
+k_count_s3_trail(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ offsets,
+                 const CountWork* __restrict__ work, uint32_t nwork, uint32_t* __restrict__ next_item, int k,
+                 uint64_t dim, uint32_t* __restrict__ counts, CountWork* __restrict__ retry,
+                 uint32_t* __restrict__ retry_count, uint32_t* resident) {
+    count_s3_body<false, 1024, 2>(seqs, offsets, work, nwork, next_item, k, dim, counts, retry, retry_count, resident);
 }
 
 // one block per record: total, validity, frequency row, exact entropy
 __global__ void __launch_bounds__(kEntThreads)
 k_freq_entropy(const uint32_t* __restrict__ counts, uint64_t dim, double* __restrict__ freqs,
                uint64_t* __restrict__ totals, double* __restrict__ entropy, uint8_t* __restrict__ valid,
-               uint8_t* __restrict__ err, double* __restrict__ err_total) {
+               uint8_t* __restrict__ err, double* __restrict__ err_total, const uint32_t* __restrict__ rec_list) {
     extern __shared__ __align__(16) double ent_smem[];
     __shared__ unsigned long long s_total;
-    const uint32_t r = blockIdx.x;
+    const uint32_t r = rec_list ? rec_list[blockIdx.x] : blockIdx.x;  // (records counted in a caller-given sequence)
     const uint32_t* c = counts + (size_t)r * dim;
     double* f = freqs + (size_t)r * dim;
     if (threadIdx.x == 0) s_total = 0ULL;
@@ -662,6 +685,12 @@ struct CountDest {
     double* err_total;
     uint32_t chunks;                                   // >= 1
     std::function<int(uint32_t, uint32_t)> after_chunk;  // (first record, end record) of the chunk just enqueued
+    // optional: the sequence in which the records are counted (a permutation of 0..nrec-1; chunk c covers
+    // rec_seq[rb..re)) - dvs_count_select counts in the selection's examination order so that the rounds can trail
+    const uint32_t* rec_seq = nullptr;
+    int s3_shape = -1;  // >= 0 overrides DVS_COUNT_S3_SHAPE (the trailing selection needs the 56-register form)
+    uint32_t* resident = nullptr;  // device word: k_count_s3 CTAs resident right now
+    int trail_regs = 56;           // register cap of the counting kernel beside the trailing selection
 };
 
 static int count_core(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, uint32_t* d_counts, uint64_t dim,
@@ -737,11 +766,20 @@ static int count_core(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, 
         // time with 8 KB items (measured at k=12: 37 Gbp/s with 9 rows in flight, DRAM sector bound)
         if (mode == MODE_GLOBAL && dim * 4 >= (16u << 20)) chunk = 8192;
     }
-    if (s->work_chunk != chunk || s->work_nparts != nparts || !s->work_cache.p) {
+    DevBuf<uint32_t> d_rec_seq;
+    if (dst.rec_seq) {
+        if (d_rec_seq.alloc(std::max<uint32_t>(s->nrec, 1)) != DVS_OK) return DVS_ERR_CUDA;
+        TRY_F(cudaMemcpyAsync(d_rec_seq.p, dst.rec_seq, (size_t)s->nrec * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    }
+    const bool same_seq = dst.rec_seq ? (s->work_seq.size() == s->nrec &&
+                                         std::equal(s->work_seq.begin(), s->work_seq.end(), dst.rec_seq))
+                                      : s->work_seq.empty();
+    if (s->work_chunk != chunk || s->work_nparts != nparts || !s->work_cache.p || !same_seq) {
         std::vector<CountWork> work;
         s->work_item_begin.assign(s->nrec + 1, 0);
-        for (uint32_t r = 0; r < s->nrec; ++r) {
-            s->work_item_begin[r] = (uint32_t)work.size();
+        for (uint32_t q = 0; q < s->nrec; ++q) {
+            const uint32_t r = dst.rec_seq ? dst.rec_seq[q] : q;  // items are grouped by position in the counting sequence
+            s->work_item_begin[q] = (uint32_t)work.size();
             uint64_t b = s->h_offsets[r], e = s->h_offsets[r + 1];
             if (e <= b) continue;
             uint64_t a0 = b & ~31ULL, a1 = (e + 15) & ~15ULL;  // (32-byte aligned starts: k_count_s3 loads 32 bytes per lane)
@@ -760,6 +798,10 @@ static int count_core(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, 
         s->work_chunk = chunk;
         s->work_nparts = nparts;
         s->work_items = (uint32_t)work.size();
+        if (dst.rec_seq)
+            s->work_seq.assign(dst.rec_seq, dst.rec_seq + s->nrec);  // (the list is cached per counting sequence)
+        else
+            s->work_seq.clear();
     }
     const CountWork* d_work_all = reinterpret_cast<const CountWork*>(s->work_cache.p);
     const uint32_t nchunks = std::max<uint32_t>(1, std::min<uint32_t>(dst.chunks, std::max<uint32_t>(s->nrec, 1)));
@@ -780,6 +822,11 @@ static int count_core(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, 
         ~TimingGuard() { c->timing = saved; }
     } timing_guard{ctx, ctx->timing};
     if (nchunks > 1) ctx->timing = false;
+    const bool chunk_ev = nchunks > 1 && timing_guard.saved && nchunks <= 64;
+    ctx->n_chunk_ev = 0;
+    if (chunk_ev)
+        for (uint32_t i = 0; i < 2 * nchunks; ++i)
+            if (!ctx->ev_chunk[i]) TRY_F(cudaEventCreate(&ctx->ev_chunk[i]));
     for (uint32_t ch = 0; ch < nchunks; ++ch) {
         const uint32_t rb = (uint32_t)((uint64_t)s->nrec * ch / nchunks), re = (uint32_t)((uint64_t)s->nrec * (ch + 1) / nchunks);
         const uint32_t ib = s->work_item_begin[rb], ie = s->work_item_begin[re];
@@ -811,6 +858,7 @@ static int count_core(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, 
             };
             cudaError_t e;
             PhaseTimer pt(ctx, DVS_PHASE_COUNT_KERNEL);
+            if (chunk_ev) cudaEventRecord(ctx->ev_chunk[2 * ctx->n_chunk_ev], st);
             if (!ns4)
                 e = smem ? launch_generic(k_count_generic<true>) : launch_generic(k_count_generic<false>);
             else if (mode == MODE_SUPER3) {
@@ -821,19 +869,36 @@ static int count_core(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, 
                 // DVS_COUNT_S3_SHAPE (A/B measurements): 0 = 1024 threads x 3 KB-steps in flight per warp (8.78 ms on
                 // the bench set), 1 = 1024 threads x 2 steps (8.97 ms), 2 = 512 threads x 4 steps (9.03 ms)
                 const char* shape_env = getenv("DVS_COUNT_S3_SHAPE");
-                const int shape = shape_env ? atoi(shape_env) : 0;
+                const int shape = dst.s3_shape >= 0 ? dst.s3_shape : (shape_env ? atoi(shape_env) : 0);
                 auto s3 = scr3 ? k_count_s3<true, 1024, 2>
                                : (shape == 1 ? k_count_s3<false, 1024, 2>
                                              : (shape == 2 ? k_count_s3<false, 512, 4> : k_count_s3<false, 1024, 3>));
                 const int s3_threads = (!scr3 && shape == 2) ? 512 : 1024;
                 auto rk = scramble ? k_count<MODE_SUPER, true, 512> : k_count<MODE_SUPER, false, 512>;
-                TRY_F(cudaFuncSetAttribute(s3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
+                // DVS_COUNT_SMEM_PAD (A/B measurements): extra dynamic shared memory, i.e. a smaller L1 for the
+                // in-flight loads - what a co-resident kernel's shared memory costs the counting
+                const char* pad_env = getenv("DVS_COUNT_SMEM_PAD");
+                const size_t s3_bytes = hist_bytes + (pad_env ? (size_t)atoi(pad_env) : 0);
+                TRY_F(cudaFuncSetAttribute(s3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3_bytes));
                 const size_t retry_bytes = (size_t)dim * 20;
                 if (retry_bytes > 48 * 1024)
                     TRY_F(cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)retry_bytes));
                 uint32_t* rc2 = d_rc.p + 2 * ch;
-                s3<<<g, s3_threads, hist_bytes, st>>>(s->data(), s->offsets.p, d_work, n_work, d_nx, k, dim, d_counts,
-                                                d_retry.p + ib, rc2);
+                if (dst.resident) {
+                    auto k_count_s3_trail = dst.trail_regs <= 40 ? dvs::k_count_s3_trail<40>
+                                            : (dst.trail_regs <= 48 ? dvs::k_count_s3_trail<48> : dvs::k_count_s3_trail<56>);
+                    TRY_F(cudaFuncSetAttribute(k_count_s3_trail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3_bytes));
+                    // the SM's shared-memory / L1 split cannot change while a CTA is resident: ask for the largest
+                    // split up front, or no selection CTA ever fits beside this one (tools/microbench/coresident.cu,
+                    // profiles/r2_coresident.txt); costs the counting ~3 % (28 KB of L1 for the loads in flight)
+                    TRY_F(cudaFuncSetAttribute(k_count_s3_trail, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                               (int)cudaSharedmemCarveoutMaxShared));
+                    k_count_s3_trail<<<g, 1024, s3_bytes, st>>>(s->data(), s->offsets.p, d_work, n_work, d_nx, k, dim,
+                                                                d_counts, d_retry.p + ib, rc2, dst.resident);
+                } else {
+                    s3<<<g, s3_threads, s3_bytes, st>>>(s->data(), s->offsets.p, d_work, n_work, d_nx, k, dim, d_counts,
+                                                        d_retry.p + ib, rc2);
+                }
                 ctx->launches++;
                 e = cudaGetLastError();
                 if (e == cudaSuccess) {
@@ -852,6 +917,7 @@ static int count_core(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, 
             else
                 e = launch4(k_count<MODE_GLOBAL, false, 512>);
             pt.stop();
+            if (chunk_ev) cudaEventRecord(ctx->ev_chunk[2 * ctx->n_chunk_ev++ + 1], st);
             if (e != cudaSuccess) {
                 set_error("k_count launch failed: %s", cudaGetErrorString(e));
                 return DVS_ERR_CUDA;
@@ -859,9 +925,13 @@ static int count_core(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, 
         }
         if (re > rb) {
             PhaseTimer pt(ctx, DVS_PHASE_FREQ_ENTROPY);
-            k_freq_entropy<<<re - rb, kEntThreads, kEntSmemBytes, st>>>(
-                d_counts + (size_t)rb * dim, dim, dst.freqs + (size_t)rb * dim, dst.totals + rb, dst.entropy + rb,
-                dst.valid + rb, dst.err + rb, dst.err_total + rb);
+            if (dst.rec_seq)
+                k_freq_entropy<<<re - rb, kEntThreads, kEntSmemBytes, st>>>(d_counts, dim, dst.freqs, dst.totals, dst.entropy,
+                                                                            dst.valid, dst.err, dst.err_total, d_rec_seq.p + rb);
+            else
+                k_freq_entropy<<<re - rb, kEntThreads, kEntSmemBytes, st>>>(
+                    d_counts + (size_t)rb * dim, dim, dst.freqs + (size_t)rb * dim, dst.totals + rb, dst.entropy + rb,
+                    dst.valid + rb, dst.err + rb, dst.err_total + rb, nullptr);
             ctx->launches++;
             TRY_F(cudaGetLastError());
         }
@@ -931,6 +1001,143 @@ int dvs_count_kmers(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, dv
     }
     // (no synchronisation: the work list is cached in the seqset and every scratch buffer is released in
     // stream order, so the caller's next call can be enqueued while the counting is still running)
+    *out = f;
+    return DVS_OK;
+}
+
+// ---- counting with the selection rounds trailing it (one GPU) ---------------------------------------------
+__global__ void k_set_word(unsigned* w, unsigned v) { *w = v; }
+
+// The records are counted on a second stream in `order`'s sequence, `chunks` launches; after each one the number of
+// positions whose rows / entropies / flags exist is published in a device word, and the nmost rounds (select.cu:
+// slim SM-replicated kernel, co-resident with the counting CTAs) only examine positions below it.  The result is
+// the one dvs_count_kmers + dvs_select give (same kernels' arithmetic; tests/test_gpu_fused.py).
+int dvs_count_select(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, const uint32_t* order, uint32_t num,
+                     int mode, uint32_t min_size, uint32_t max_size, uint32_t chunks, dvs_kfreqs** out,
+                     uint32_t* sel_idx, double* sel_delta, double* stats5, uint32_t* size_out) {
+    uint64_t dim = 0;
+    DVS_TRY(count_args_ok(ctx, s, k, num_states, out, &dim));
+    if ((!order && num) || !size_out) {
+        set_error("dvs_count_select: NULL argument");
+        return DVS_ERR_ARG;
+    }
+    for (uint32_t i = 0; i < num; ++i)
+        if (order[i] >= s->nrec) {
+            set_error("dvs_count_select: order[%u]=%u out of range (nrec=%u)", i, order[i], s->nrec);
+            return DVS_ERR_ARG;
+        }
+    DVS_CUDA_TRY(dvs::enter(ctx));
+    DVS_TRY(dense_rows_fit((double)s->nrec * (double)dim * 12.0, "dvs_count_select", s->nrec, dim));
+    if (!ctx->stream2) {
+        DVS_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+        DVS_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_first, cudaEventDisableTiming));
+        DVS_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_count_done, cudaEventDisableTiming));
+        DVS_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        DVS_CUDA_TRY(cudaMalloc(&ctx->d_ready, 4096));
+    }
+    dvs_kfreqs* f = nullptr;
+    DVS_TRY(kfreqs_alloc(ctx, s->nrec, dim, true, &f));
+    f->k = k;
+    f->num_states = num_states;
+
+    // counting sequence: the records in order of first appearance in `order`, then the ones it does not name
+    std::vector<uint32_t> seq, seqpos(s->nrec, 0xFFFFFFFFu);
+    seq.reserve(s->nrec);
+    for (uint32_t i = 0; i < num; ++i)
+        if (seqpos[order[i]] == 0xFFFFFFFFu) {
+            seqpos[order[i]] = (uint32_t)seq.size();
+            seq.push_back(order[i]);
+        }
+    for (uint32_t r = 0; r < s->nrec; ++r)
+        if (seqpos[r] == 0xFFFFFFFFu) {
+            seqpos[r] = (uint32_t)seq.size();
+            seq.push_back(r);
+        }
+    // need[i] = records (in sequence) that must be counted before positions 0..i are all there (non-decreasing)
+    std::vector<uint32_t> need(num);
+    for (uint32_t i = 0, m = 0; i < num; ++i) {
+        m = std::max(m, seqpos[order[i]] + 1);
+        need[i] = m;
+    }
+    auto ready_after = [&](uint32_t re) {  // positions published once seq[0..re) is counted
+        return (uint32_t)(std::upper_bound(need.begin(), need.end(), re) - need.begin());
+    };
+    if (chunks == 0) chunks = 8;
+    chunks = std::min<uint32_t>(chunks, 64);
+    // the first chunk has to hold the initial set
+    while (chunks > 1 && ready_after((uint32_t)((uint64_t)s->nrec / chunks)) < std::max<uint32_t>(min_size, 1)) --chunks;
+    // (only beside k_count_s3 - k = 4..6 over 4 states - whose CTA leaves room for exactly one selection CTA)
+    const char* s3_env = getenv("DVS_COUNT_S3");
+    const bool s3 = num_states == 4 && k >= 4 && k <= 6 && !(s3_env && s3_env[0] == '0');
+    const bool trail = chunks > 1 && mode == DVS_MODE_NMOST && num > 0 && s3;
+    // DVS_TRAIL=0 (A/B measurements): same chunked counting, but the selection starts when it has finished
+    const char* trail_env = getenv("DVS_TRAIL");
+    const bool trail_rounds = !(trail_env && trail_env[0] == '0');
+
+    cudaStream_t main_st = ctx->stream;
+    int rc;
+    if (!trail) {  // nothing to overlap: the two calls back to back
+        CountDest dst{f->freqs.p, f->totals.p, f->entropy.p, f->valid.p, f->err.p, f->err_total.p, 1, nullptr};
+        rc = count_core(ctx, s, k, num_states, f->counts.p, dim, dst);
+        if (rc == DVS_OK)
+            rc = dvs::select_with_trail(ctx, f, order, num, mode, min_size, max_size, sel_idx, sel_delta, stats5,
+                                        size_out, nullptr);
+    } else {
+        dvs::TrailArgs ta{ctx->d_ready, 0, ctx->ev_first, ctx->ev_count_done, ctx->d_ready + 1};
+        DVS_CUDA_TRY(cudaMemsetAsync(ctx->d_ready, 0, 8, main_st));
+        DVS_CUDA_TRY(cudaEventRecord(ctx->ev_fork, main_st));
+        DVS_CUDA_TRY(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+        CountDest dst{f->freqs.p, f->totals.p, f->entropy.p, f->valid.p, f->err.p, f->err_total.p, chunks, nullptr};
+        dst.rec_seq = seq.data();
+        dst.s3_shape = 1;  // 56 registers: leaves 8,192 for the selection CTA on the same SM
+        dst.resident = ctx->d_ready + 1;
+        dst.trail_regs = dvs::trail_count_regs();
+        bool first = true;
+        cudaStream_t side = ctx->stream2;
+        dst.after_chunk = [&](uint32_t, uint32_t re) -> int {
+            const uint32_t rdy = ready_after(re);
+            k_set_word<<<1, 1, 0, side>>>(ctx->d_ready, rdy);
+            DVS_CUDA_TRY(cudaGetLastError());
+            if (first) {
+                first = false;
+                ta.limit0 = rdy;
+                DVS_CUDA_TRY(cudaEventRecord(ctx->ev_first, side));
+            }
+            return DVS_OK;
+        };
+        ctx->stream = side;  // count_core and its scratch buffers live on the second stream
+        dvs::tl_stream = side;
+        rc = count_core(ctx, s, k, num_states, f->counts.p, dim, dst);
+        cudaError_t e1 = first ? cudaEventRecord(ctx->ev_first, side) : cudaSuccess;  // (never leave a waiter behind)
+        cudaError_t e2 = cudaEventRecord(ctx->ev_count_done, side);
+        ctx->stream = main_st;
+        dvs::tl_stream = main_st;
+        if (rc == DVS_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) {
+            set_error("dvs_count_select: cudaEventRecord failed");
+            rc = DVS_ERR_CUDA;
+        }
+        if (rc == DVS_OK && !trail_rounds) cudaStreamWaitEvent(main_st, ctx->ev_count_done, 0);
+        if (rc == DVS_OK)
+            rc = dvs::select_with_trail(ctx, f, order, num, mode, min_size, max_size, sel_idx, sel_delta, stats5,
+                                        size_out, trail_rounds ? &ta : nullptr);
+        cudaStreamWaitEvent(main_st, ctx->ev_count_done, 0);  // join, whatever happened
+        if (getenv("DVS_TRAIL_DEBUG") && ctx->timing) {  // per-launch counting times of this call
+            cudaStreamSynchronize(main_st);
+            fprintf(stderr, "[dvs] count launches (ms):");
+            for (uint32_t c = 0; c < ctx->n_chunk_ev; ++c) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, ctx->ev_chunk[2 * c], ctx->ev_chunk[2 * c + 1]);
+                fprintf(stderr, " %.3f", ms);
+            }
+            fprintf(stderr, "  trailing launches %u, fewest SMs %u, accepts while counting %u\n", ctx->last_trail_launches,
+                    ctx->last_trail_launches ? ctx->last_trail_sms : 0, ctx->last_trail_accepts);
+        }
+    }
+    if (rc != DVS_OK) {
+        cudaStreamSynchronize(main_st);
+        dvs_kfreqs_free(f);
+        return rc;
+    }
     *out = f;
     return DVS_OK;
 }

@@ -25,6 +25,7 @@
 #include "comm.cuh"
 #include "common.cuh"
 #include "entropy.cuh"
+#include "fused.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -59,6 +60,7 @@ struct SelScal {
     unsigned halt;           // 1: the host must resolve an undecided candidate / state exactly
     unsigned accepts;        // candidates that replaced the lowest record so far
     unsigned which;          // which copy of the double-buffered S / member list is current
+    unsigned limit;          // trailing rounds: positions below it had been published when the kernel returned
 };
 
 struct SelState {
@@ -301,6 +303,27 @@ k_sel_scan(const double* __restrict__ F, const double* __restrict__ H, uint64_t 
 #include "select_grow.cuh"
 #include "select_sm.cuh"
 
+// waits (bounded: ~150 us) until `want` counting CTAs are resident, or the counting is over
+__global__ void k_wait_resident(const unsigned* resident, unsigned want, const unsigned* ready, unsigned num) {
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        if (*reinterpret_cast<const volatile unsigned*>(resident) >= want) break;
+        if (*reinterpret_cast<const volatile unsigned*>(ready) >= num) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > 150000ull) break;
+        __nanosleep(500);
+    }
+}
+
+constexpr auto k_sel_persist_sm_full = k_sel_persist_sm_t<kFastThreads, 1, kSmMaxN, kSmChunk>;
+// the trailing form: 128 threads x <= 64 registers and ~66 KB of shared memory fit beside one counting CTA
+// (1,024 threads x 56 registers, 144 KB) on every SM
+template <int NT>
+struct SlimKernel {
+    static constexpr auto fn = k_sel_persist_sm_t<NT, (1024 + NT - 1) / NT, kSmSlimMaxN, kSmSlimChunk>;  // (<= 64 registers)
+};
+
 // test hook: the two building blocks of block_entropy_ilp on arbitrary operands
 __global__ void k_debug_fast_terms(const double* a, const double* b, double* m_out, double* l_out, int* sp_out, uint64_t n) {
     __shared__ double2 ltab[64];
@@ -447,7 +470,7 @@ extern "C" {
 // candidates are scored candidate-sharded with an all-reduce(min) of the first interesting position.
 static int select_core(dvs_ctx* ctx, dvs_comm* comm, const dvs_kfreqs* f, const uint32_t* order, uint32_t num, int mode,
                        uint32_t min_size, uint32_t max_size, uint32_t* sel_idx, double* sel_delta, double* stats5,
-                       uint32_t* size_out) {
+                       uint32_t* size_out, const TrailArgs* trail = nullptr) {
     if (!ctx || !f || (!order && num) || !size_out) {
         set_error("dvs_select: NULL argument");
         return DVS_ERR_ARG;
@@ -457,6 +480,9 @@ static int select_core(dvs_ctx* ctx, dvs_comm* comm, const dvs_kfreqs* f, const 
         return DVS_ERR_ARG;
     }
     ctx->last_accepts = 0;
+    ctx->last_trail_accepts = 0;
+    ctx->last_trail_launches = 0;
+    ctx->last_trail_sms = 0xFFFFFFFFu;
     if (num < min_size) {  // records.rs:323-325, :404-410
         set_error("The number of sequences %u is < n %u", num, min_size);
         return DVS_ERR_VALUE;
@@ -478,6 +504,17 @@ static int select_core(dvs_ctx* ctx, dvs_comm* comm, const dvs_kfreqs* f, const 
     shard.world = (int)world;
     for (unsigned r = 0; r < world && comm; ++r) shard.xbase[r] = comm->peer[r];
     if (world > 1) DVS_TRY(comm_barrier(ctx, comm));  // every rank is here: exchange slots of earlier calls are dead
+    // trailing mode (dvs_count_select): the rows are still being produced on another stream; positions below
+    // `trail_limit` have been published.  Start once the first chunk (>= min_size positions) is there.
+    unsigned trail_limit = num;
+    if (trail) {
+        DVS_CUDA_TRY(cudaStreamWaitEvent(st, trail->first_ready, 0));
+        trail_limit = std::min(trail->limit0, num);
+        if (mode != DVS_MODE_NMOST || trail_limit < min_size) {  // nothing to gain / not enough rows yet: wait for all
+            DVS_CUDA_TRY(cudaStreamWaitEvent(st, trail->count_done, 0));
+            trail_limit = num;
+        }
+    }
 
     // validity / panic flags of the records, needed on the host to form the initial set
     std::vector<uint8_t> valid(f->nrec), err(f->nrec);
@@ -490,7 +527,8 @@ static int select_core(dvs_ctx* ctx, dvs_comm* comm, const dvs_kfreqs* f, const 
         DVS_CUDA_TRY(cudaStreamSynchronize(st));
     }
     // every record in `order` goes through KmerSeq::new -> entropy(); a failing sum check panics
-    for (uint32_t i = 0; i < num; ++i)
+    // (trailing mode: the records published so far; all of them once the counting has finished, below)
+    for (uint32_t i = 0; i < trail_limit; ++i)
         if (valid[order[i]] && err[order[i]]) {
             set_error("cannot calculate entropy as frequency vector total %.17g!=1.0", err_total[order[i]]);
             return DVS_ERR_VALUE;
@@ -564,14 +602,24 @@ static int select_core(dvs_ctx* ctx, dvs_comm* comm, const dvs_kfreqs* f, const 
     const unsigned persist_grid = std::min((unsigned)ctx->sm_count * (unsigned)std::min(per_sm, 2), std::max(1u, std::min(grid_cap, 0x7FFFFFFFu)));
     bool sm_ok = use_persist && !(per_env && per_env[0] == '1') && dim <= kSmMaxDim;
     if (sm_ok) {
-        sm_ok = cudaFuncSetAttribute(k_sel_persist_sm, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        sm_ok = cudaFuncSetAttribute(k_sel_persist_sm_full, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(SmShared)) == cudaSuccess &&
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_sel_persist_sm, kFastThreads,
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_sel_persist_sm_full, kFastThreads,
                                                               sizeof(SmShared)) == cudaSuccess &&
                 per_sm2 > 0;
         (void)cudaGetLastError();
     }
     const unsigned sm_grid = std::min(std::min<unsigned>((unsigned)ctx->sm_count, kSmMaxGrid), grid_cap);
+    const int slim_threads = 128 * (trail_shape() + 1);
+    const auto k_slim = slim_threads == 384 ? SlimKernel<384>::fn : (slim_threads == 256 ? SlimKernel<256>::fn : SlimKernel<128>::fn);
+    bool slim_ok = false;
+    if (trail && sm_ok) {
+        slim_ok = cudaFuncSetAttribute(k_slim, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(SmSharedSlim)) == cudaSuccess &&
+                  cudaFuncSetAttribute(k_slim, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       (int)cudaSharedmemCarveoutMaxShared) == cudaSuccess;
+        (void)cudaGetLastError();
+    }
     DevBuf<SmPart> d_spart, d_upart, d_dpart;
     if (sm_ok) {
         DVS_TRY(d_spart.alloc(2 * kSmMaxGrid));
@@ -657,9 +705,19 @@ static int select_core(dvs_ctx* ctx, dvs_comm* comm, const dvs_kfreqs* f, const 
             single_candidate = true;
             continue;
         }
+        if (trail && trail_limit < num && !use_persist) {  // only the persistent kernel knows how to trail
+            DVS_CUDA_TRY(cudaStreamWaitEvent(st, trail->count_done, 0));
+            trail_limit = num;
+        }
         if (use_persist && (!grow_mode || n == max_size)) {
             // every remaining round in one cooperative launch (until done, or halted for the host)
             const bool use_sm = sm_ok && n <= kSmMaxN;
+            // trailing rounds need the slim SM-replicated kernel; anything else waits for the counting to finish
+            const bool trailing = trail && trail_limit < num && use_sm && slim_ok && n <= kSmSlimMaxN && world == 1;
+            if (trail && trail_limit < num && !trailing) {
+                DVS_CUDA_TRY(cudaStreamWaitEvent(st, trail->count_done, 0));
+                trail_limit = num;
+            }
             const unsigned grid = use_sm ? sm_grid : persist_grid;
             k_sel_set_dev<<<1, 1, 0, st>>>(cur->sc.p, cursor, std::min(window, grid * world), grid * world, num, accepts,
                                            (unsigned)cur->which);
@@ -700,10 +758,25 @@ static int select_core(dvs_ctx* ctx, dvs_comm* comm, const dvs_kfreqs* f, const 
                 // exchange tags restart at 1 in every launch
                 DVS_CUDA_TRY(cudaMemsetAsync(d_spart.p, 0, 2 * kSmMaxGrid * sizeof(SmPart), st));
                 DVS_CUDA_TRY(cudaMemsetAsync(d_upart.p, 0, (kSmMaxN + 1) * sizeof(SmPart), st));
+                const unsigned* a_ready = trailing ? trail->d_ready : nullptr;
+                unsigned a_limit0 = trail_limit;
                 void* args[] = {&a_F, &a_H, &a_dim32, &a_S, &a_M, &a_mem, &a_md, &a_mb, &a_sc, &a_valid, &a_order,
-                                &a_sp, &a_up, &a_dp, &a_trace, &a_trace_all, &shard};
-                DVS_CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_sel_persist_sm, dim3(grid), dim3(kFastThreads), args,
-                                                         sizeof(SmShared), st));
+                                &a_sp, &a_up, &a_dp, &a_trace, &a_trace_all, &shard, &a_ready, &a_limit0};
+                if (trailing) {
+                    // a plain launch, made when every SM holds a counting CTA: beside it exactly one of these CTAs
+                    // fits (registers), so they land one per SM.  Launched between two counting launches they
+                    // would pack three to an SM and keep the counting off a third of the GPU.
+                    k_wait_resident<<<1, 1, 0, st>>>(trail->d_resident, std::min<unsigned>(grid, (unsigned)ctx->sm_count),
+                                                     trail->d_ready, num);
+                    DVS_LAUNCHED(ctx);
+                }
+                if (trailing)
+                    k_slim<<<grid, slim_threads, sizeof(SmSharedSlim), st>>>(
+                        a_F, a_H, a_dim32, a_S, a_M, a_mem, a_md, a_mb, a_sc, a_valid, a_order, a_sp, a_up, a_dp, a_trace,
+                        a_trace_all, shard, a_ready, a_limit0);
+                else
+                    DVS_CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_sel_persist_sm_full, dim3(grid), dim3(kFastThreads),
+                                                             args, sizeof(SmShared), st));
             } else {
                 void* args[] = {&a_F, &a_H, &a_dim, &a_S0, &a_S1, &a_M0, &a_M1, &a_mem, &a_md, &a_mb, &a_sc, &a_valid,
                                 &a_order, &a_rounds, &a_trace, &shard};
@@ -735,11 +808,23 @@ static int select_core(dvs_ctx* ctx, dvs_comm* comm, const dvs_kfreqs* f, const 
             }
             const SelScal hd = *sel.h_sc;
             if (hd.panic) return panic_error(hd);
+            if (trailing) {
+                ctx->last_trail_accepts += hd.accepts - accepts;
+                ++ctx->last_trail_launches;
+                std::vector<unsigned> smid(grid);
+                DVS_CUDA_TRY(cudaMemcpyAsync(smid.data(), trail->d_ready + kTrailSmidOff, grid * sizeof(unsigned),
+                                             cudaMemcpyDeviceToHost, st));
+                DVS_CUDA_TRY(cudaStreamSynchronize(st));
+                std::sort(smid.begin(), smid.end());
+                const unsigned distinct = (unsigned)(std::unique(smid.begin(), smid.end()) - smid.begin());
+                ctx->last_trail_sms = std::min(ctx->last_trail_sms, distinct);
+            }
             cursor = hd.cursor;
             window = hd.window;
             accepts = hd.accepts;
             cur->which = (int)hd.which;
-            if (!hd.halt) continue;  // finished
+            if (trailing) trail_limit = std::max(trail_limit, std::min(hd.limit, num));
+            if (!hd.halt) continue;  // finished (or, trailing, everything is published: the stand-alone kernel goes on)
             DVS_TRY(sel.reset_scan(*cur));
             if (cursor >= num) break;
         } else if (use_dev && world == 1 && (!grow_mode || n == max_size)) {
@@ -771,7 +856,11 @@ static int select_core(dvs_ctx* ctx, dvs_comm* comm, const dvs_kfreqs* f, const 
             DVS_TRY(sel.reset_scan(*cur));
             if (cursor >= num) break;
         }
-        const unsigned count = single_candidate ? 1u : std::min(window, num - cursor);
+        if (cursor >= trail_limit) {  // (trailing) nothing published beyond the cursor: wait for all of it
+            DVS_CUDA_TRY(cudaStreamWaitEvent(st, trail->count_done, 0));
+            trail_limit = num;
+        }
+        const unsigned count = single_candidate ? 1u : std::min(window, trail_limit - cursor);
         single_candidate = false;
         SelScal h;
         unsigned pos = kNone;
@@ -888,6 +977,18 @@ static int select_core(dvs_ctx* ctx, dvs_comm* comm, const dvs_kfreqs* f, const 
             DVS_TRY(sel.reset_scan(*cur));  // candidate discarded: re-arm the min-index reduction of `cur`
         }
     }
+    if (trail) {  // the records that were not published when the selection started: the reference's panic check
+        DVS_CUDA_TRY(cudaStreamWaitEvent(st, trail->count_done, 0));
+        DVS_CUDA_TRY(cudaMemcpyAsync(valid.data(), f->valid.p, f->nrec, cudaMemcpyDeviceToHost, st));
+        DVS_CUDA_TRY(cudaMemcpyAsync(err.data(), f->err.p, f->nrec, cudaMemcpyDeviceToHost, st));
+        DVS_CUDA_TRY(cudaMemcpyAsync(err_total.data(), f->err_total.p, f->nrec * sizeof(double), cudaMemcpyDeviceToHost, st));
+        DVS_CUDA_TRY(cudaStreamSynchronize(st));
+        for (uint32_t i = 0; i < num; ++i)
+            if (valid[order[i]] && err[order[i]]) {
+                set_error("cannot calculate entropy as frequency vector total %.17g!=1.0", err_total[order[i]]);
+                return DVS_ERR_VALUE;
+            }
+    }
     DVS_TRY(sel.read(*cur));
     if (!sel.h_sc->exact || sel.h_sc->state_unsure) DVS_TRY(sel.update(*cur, n));  // reported numbers are exact
     ctx->last_exact_evals = exact_evals;
@@ -909,6 +1010,16 @@ static int select_core(dvs_ctx* ctx, dvs_comm* comm, const dvs_kfreqs* f, const 
     if (world > 1) DVS_TRY(comm_check_error(ctx, comm, "dvs_select_sharded"));
     return DVS_OK;
 }
+
+}  // extern "C"
+namespace dvs {
+int select_with_trail(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_t num, int mode, uint32_t min_size,
+                      uint32_t max_size, uint32_t* sel_idx, double* sel_delta, double* stats5, uint32_t* size_out,
+                      const TrailArgs* trail) {
+    return select_core(ctx, nullptr, f, order, num, mode, min_size, max_size, sel_idx, sel_delta, stats5, size_out, trail);
+}
+}  // namespace dvs
+extern "C" {
 
 int dvs_select(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* order, uint32_t num, int mode, uint32_t min_size,
                uint32_t max_size, uint32_t* sel_idx, double* sel_delta, double* stats5, uint32_t* size_out) {
@@ -950,6 +1061,9 @@ int dvs_debug_fast_terms(dvs_ctx* ctx, const double* a, const double* b, double*
 
 uint32_t dvs_select_last_accepts(dvs_ctx* ctx) { return ctx->last_accepts; }
 uint32_t dvs_select_last_exact_evals(dvs_ctx* ctx) { return ctx->last_exact_evals; }
+uint32_t dvs_select_last_trail_accepts(dvs_ctx* ctx) { return ctx->last_trail_accepts; }
+uint32_t dvs_select_last_trail_launches(dvs_ctx* ctx) { return ctx->last_trail_launches; }
+uint32_t dvs_select_last_trail_sms(dvs_ctx* ctx) { return ctx->last_trail_launches ? ctx->last_trail_sms : 0; }
 
 int dvs_summed_create(dvs_ctx* ctx, const dvs_kfreqs* f, const uint32_t* members, uint32_t n, dvs_summed** out) {
     if (!ctx || !f || !out || (!members && n)) {

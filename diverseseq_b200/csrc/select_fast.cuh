@@ -97,18 +97,18 @@ __device__ __forceinline__ bool fast_term_ok(double m) {
     return (uint32_t)__double2hiint(m) - 0x07b00000u < 0x3feea4afu - 0x07b00000u;
 }
 
-template <bool CLAMP, int BATCH, class Num>
+template <bool CLAMP, int BATCH, int NT = kFastThreads, class Num>
 __device__ FastSum block_entropy_ilp(unsigned lo, unsigned hi, Num num, const FastDiv dv,
                                      const double2* __restrict__ ltab) {
-    __shared__ double s_part[3][kFastThreads / 32];
-    __shared__ int s_bad[kFastThreads / 32];
+    __shared__ double s_part[3][NT / 32];
+    __shared__ int s_bad[NT / 32];
     double e0 = 0.0, e1 = 0.0, t0 = 0.0, t1 = 0.0, a0 = 0.0, a1 = 0.0;
     bool bad = false;
-    for (unsigned base = lo; base < hi; base += BATCH * kFastThreads) {
+    for (unsigned base = lo; base < hi; base += BATCH * NT) {
         double x[BATCH], l[BATCH];
 #pragma unroll
         for (int q = 0; q < BATCH; ++q) {
-            const unsigned i = base + threadIdx.x + (unsigned)q * kFastThreads;
+            const unsigned i = base + threadIdx.x + (unsigned)q * NT;
             x[q] = i < hi ? num(i) : 0.0;
         }
 #pragma unroll
@@ -148,7 +148,7 @@ __device__ FastSum block_entropy_ilp(unsigned lo, unsigned hi, Num num, const Fa
     }
     __syncthreads();
     FastSum r{0.0, 0.0, 0.0, 0};
-    for (int q = 0; q < kFastThreads / 32; ++q) {
+    for (int q = 0; q < NT / 32; ++q) {
         r.e += s_part[0][q]; r.t += s_part[1][q]; r.a += s_part[2][q]; r.bad |= s_bad[q];
     }
     __syncthreads();

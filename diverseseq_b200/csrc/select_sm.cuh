@@ -39,20 +39,24 @@ struct __align__(16) SmPart {
     unsigned long long w[4];  // {e, bad<<32 | tag}, {t, float_ru(a)<<32 | tag}
 };
 
-struct SmShared {
+template <unsigned MAXN, unsigned CHUNK>
+struct SmSharedT {
     double S[kSmMaxDim];
-    double mH[2][kSmMaxN + 1];
-    double md[kSmMaxN + 1];
-    double mb[kSmMaxN + 1];
-    unsigned members[2][kSmMaxN + 1];
-    double cH[kSmChunk];
-    unsigned crow[kSmChunk];
-    unsigned char cvalid[kSmChunk];
+    double mH[2][MAXN + 1];
+    double md[MAXN + 1];
+    double mb[MAXN + 1];
+    unsigned members[2][MAXN + 1];
+    double cH[CHUNK];
+    unsigned crow[CHUNK];
+    unsigned char cvalid[CHUNK];
     double pe[kSmMaxGrid], pt[kSmMaxGrid], pa[kSmMaxGrid];
     unsigned char pbad[kSmMaxGrid], wskip[kSmMaxGrid];
-    unsigned ft, fu, unsure, xft, xfu, dead;
+    unsigned ft, fu, unsure, xft, xfu, dead, limit;
     double2 ltab[64];  // glibc log2 table {1/c, log2 c}
 };
+using SmShared = SmSharedT<kSmMaxN, kSmChunk>;           // stand-alone kernel: ~105 KB
+constexpr unsigned kSmSlimMaxN = 256, kSmSlimChunk = 1280;
+using SmSharedSlim = SmSharedT<kSmSlimMaxN, kSmSlimChunk>;  // trailing kernel beside the counting CTA: ~62 KB
 
 __device__ __forceinline__ void sm_st128(void* p, unsigned long long lo, unsigned long long hi) {
     asm volatile("{ .reg .b128 v; mov.b128 v, {%1, %2}; st.relaxed.gpu.global.b128 [%0], v; }" ::"l"(p), "l"(lo), "l"(hi)
@@ -79,10 +83,11 @@ __device__ __forceinline__ FastSum sm_gather(const SmPart* slot, unsigned tag) {
 
 // finalize_fast_block on this CTA's shared-memory copies, with the cross-warp step done redundantly by
 // every thread (one barrier less, no serial tail on thread 0)
+template <int NT>
 __device__ __forceinline__ unsigned sm_finalize(double* md, const double* mb_, unsigned n, double total,
                                                 double total_bound, unsigned* low_out) {
-    __shared__ double s_mn[kFastThreads / 32], s_mb[kFastThreads / 32];
-    __shared__ unsigned s_ix[kFastThreads / 32];
+    __shared__ double s_mn[NT / 32], s_mb[NT / 32];
+    __shared__ unsigned s_ix[NT / 32];
     double mn = 1e300, mb = 0.0;
     unsigned ix = kNone;
     for (unsigned t = threadIdx.x; t < n; t += blockDim.x) {
@@ -105,7 +110,7 @@ __device__ __forceinline__ unsigned sm_finalize(double* md, const double* mb_, u
     __syncthreads();
     mn = s_mn[0]; mb = s_mb[0]; ix = s_ix[0];
 #pragma unroll
-    for (unsigned w = 1; w < kFastThreads / 32; ++w) {
+    for (unsigned w = 1; w < NT / 32; ++w) {
         const double wmn = s_mn[w];
         const unsigned wix = s_ix[w];
         if (wmn < mn || (wmn == mn && wix < ix)) {
@@ -123,15 +128,32 @@ __device__ __forceinline__ unsigned sm_finalize(double* md, const double* mb_, u
 }
 
 constexpr int kSmTraceSlots = 8;
+constexpr unsigned kTrailSmidOff = 64;  // words behind the ready word: %smid of every CTA of the last trailing launch
 
-__global__ void __launch_bounds__(kFastThreads, 1)
-k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, unsigned dim, double* S_glob,
+// NT = threads per CTA: 512 for the stand-alone selection (one CTA owns its SM); 128 for the TRAILING form that runs
+// beside the counting kernel in the registers and shared memory it leaves free (dvs_count_select): it examines a
+// position only once the record's row has been published (`ready_pos`), so the rounds trail the counting.
+template <int NT, int MINB, unsigned MAXN, unsigned CHUNK>
+__global__ void __launch_bounds__(NT, MINB)
+k_sel_persist_sm_t(const double* __restrict__ F, const double* __restrict__ H, unsigned dim, double* S_glob,
                  unsigned* M_glob, uint8_t* is_member, double* mdelta_g, double* mbound_g, SelScal* sc,
                  const uint8_t* __restrict__ valid, const unsigned* __restrict__ order, SmPart* spart, SmPart* upart,
-                 SmPart* dpart, unsigned long long* trace, int trace_all, const ShardArgs sh) {
+                 SmPart* dpart, unsigned long long* trace, int trace_all, const ShardArgs sh,
+                 const unsigned* ready_pos, unsigned limit0) {
+    // ready_pos != NULL: TRAILING mode.  Positions below *ready_pos (a device word that only grows, written in stream
+    // order behind the kernels that produce the rows) may be examined; `limit` is the value all CTAs agree on: the
+    // leader samples the word when it takes a round's decision and broadcasts it with the decision, so every CTA
+    // sizes the next window from the same number.  Window sizes never change a decision (only the first acceptance
+    // of a window is applied, the rest is re-scored), so the result does not depend on the timing.  The kernel
+    // returns to the host when everything has been published (the stand-alone kernel finishes the job).
     extern __shared__ __align__(16) unsigned char sm_raw[];
-    SmShared& sm = *reinterpret_cast<SmShared*>(sm_raw);
+    SmSharedT<MAXN, CHUNK>& sm = *reinterpret_cast<SmSharedT<MAXN, CHUNK>*>(sm_raw);
     const unsigned tid = threadIdx.x, b = blockIdx.x, G = gridDim.x;
+    if (ready_pos && tid == 0) {  // placement record of the trailing launch (dvs_select_last_trail_sms)
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        const_cast<unsigned*>(ready_pos)[kTrailSmidOff + b] = smid;
+    }
     unsigned tr_round = 0;
     // DVS_SELECT_TRACE: CTA 0's timeline of the first 256 rounds; DVS_SELECT_TRACE_ALL: every CTA's
     auto stamp = [&](int slot) {
@@ -154,8 +176,8 @@ k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, uns
     unsigned state_unsure = sc->state_unsure, halt = state_unsure ? 1u : 0u, mw = 0;
     bool touched = false;  // an acceptance happened in this launch: md / mb / total are this kernel's
     dvs_log2_stage_table(sm.ltab);
-    for (unsigned i = tid; i < dim; i += kFastThreads) sm.S[i] = S_glob[i];
-    for (unsigned j = tid; j < n; j += kFastThreads) {
+    for (unsigned i = tid; i < dim; i += NT) sm.S[i] = S_glob[i];
+    for (unsigned j = tid; j < n; j += NT) {
         const unsigned r = M_glob[j];
         sm.members[0][j] = r;
         sm.mH[0][j] = H[r];
@@ -172,6 +194,7 @@ k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, uns
     auto total_ok = [](double t, double lim) { return lim > 0.0 && fabs(t - 1.0) <= lim; };
     unsigned xs = 0, xu = 0;       // scan / update exchanges so far (= tags)
     unsigned cbase = 0, cend = 0;  // positions [cbase, cend) of `order` are staged in shared memory
+    unsigned limit = ready_pos ? min(limit0, num) : num;  // positions below it may be examined
 
     while (!halt && cursor < num) {
         stamp(0);
@@ -179,26 +202,29 @@ k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, uns
             halt = 1;
             break;
         }
-        window = max(1u, min(window, Gw));
+        if (ready_pos && limit >= num) break;  // everything is published: hand over to the stand-alone kernel
+        window = max(1u, min(window, min(Gw, CHUNK)));
         const unsigned P = (dim >= 2048u && window * 4u <= Gw) ? 4u : ((dim >= 2048u && window * 2u <= Gw) ? 2u : 1u);
-        const unsigned count = min(window, num - cursor);
+        const unsigned count = min(window, limit - cursor);
         // this GPU's candidates: window positions p with p % world == rank, i.e. offsets woff + world * i
         const unsigned woff = (rank + world - cursor % world) % world;
         const unsigned nloc = count > woff ? (count - woff + world - 1u) / world : 0u;
         if (cursor < cbase || cursor + count > cend) {  // stage the next chunk of positions (CTA-uniform)
             __syncthreads();
             cbase = cursor;
-            cend = min(num, cbase + kSmChunk);
-            for (unsigned q = tid; cbase + q < cend; q += kFastThreads) {
+            cend = min(limit, cbase + CHUNK);
+            for (unsigned q = tid; cbase + q < cend; q += NT) {
                 const unsigned row = order[cbase + q];
                 sm.crow[q] = row;
-                sm.cvalid[q] = valid[row];
-                sm.cH[q] = H[row];
+                // (through L2: in trailing mode a neighbouring entry of the same line may have been cached before
+                // its record was published)
+                sm.cvalid[q] = __ldcg(valid + row);
+                sm.cH[q] = __ldcg(H + row);
             }
             // ... and pull the rows this GPU will score towards L2, one 128-byte line per prefetch, dealt over the CTAs
             for (unsigned r = (rank + world - cbase % world) % world + world * b; r < cend - cbase; r += world * G) {
                 const double* fr = F + (size_t)order[cbase + r] * dim;
-                for (unsigned l = tid * 16u; l < dim; l += kFastThreads * 16u)
+                for (unsigned l = tid * 16u; l < dim; l += NT * 16u)
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(fr + l));
             }
             __syncthreads();
@@ -208,7 +234,7 @@ k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, uns
             sm.ft = kNone;
             sm.fu = kNone;
         }
-        if (tid < nloc) sm.wskip[tid] = sm.cvalid[coff + woff + world * tid] ? 0 : 1;
+        for (unsigned q = tid; q < nloc; q += NT) sm.wskip[q] = sm.cvalid[coff + woff + world * q] ? 0 : 1;
         // ---- scan: slice p of candidate c ----
         ++xs;
         SmPart* const sbuf = spart + (xs & 1u) * kSmMaxGrid;
@@ -219,9 +245,9 @@ k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, uns
             const double* fc = F + (size_t)sm.crow[coff + cw] * dim;
             const unsigned lo = (unsigned)(((uint64_t)dim * p) / P), hi = (unsigned)(((uint64_t)dim * (p + 1)) / P);
             auto num = [&](unsigned i) { return __dadd_rn(__dsub_rn(sm.S[i], fl[i]), fc[i]); };
-            const FastSum h = P == 4u   ? block_entropy_ilp<false, 2>(lo, hi, num, div_n, sm.ltab)
-                              : P == 2u ? block_entropy_ilp<false, 4>(lo, hi, num, div_n, sm.ltab)
-                                        : block_entropy_ilp<false, 8>(lo, hi, num, div_n, sm.ltab);
+            const FastSum h = P == 4u   ? block_entropy_ilp<false, 2, NT>(lo, hi, num, div_n, sm.ltab)
+                              : P == 2u ? block_entropy_ilp<false, 4, NT>(lo, hi, num, div_n, sm.ltab)
+                                        : block_entropy_ilp<false, 8, NT>(lo, hi, num, div_n, sm.ltab);
             if (tid == 0) sm_publish(sbuf + b, h, xs);
         } else if (tid == 0) {
             // every CTA publishes in every scan exchange: the leader's wait for all G slots is what bounds
@@ -238,27 +264,28 @@ k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, uns
             // is the ground truth, searched while the partials are still in flight (thread j holds member j
             // and walks the window)
             __syncthreads();  // wskip initialised (a CTA without a candidate has not passed a barrier yet)
-            for (unsigned j = tid; j < n; j += kFastThreads) {
+            for (unsigned j = tid; j < n; j += NT) {
                 const unsigned r = sm.members[mw][j];
                 for (unsigned cc = 0; cc < nloc; ++cc)
                     if (sm.crow[coff + woff + world * cc] == r) sm.wskip[cc] = 1;
             }
             __syncthreads();
-            if (tid < G) {
-                const FastSum g = sm_gather(sbuf + tid, xs);
-                if (tid < nloc * P && !sm.wskip[tid / P]) {
-                    sm.pe[tid] = g.e; sm.pt[tid] = g.t; sm.pa[tid] = g.a; sm.pbad[tid] = (unsigned char)g.bad;
+            for (unsigned q = tid; q < G; q += NT) {
+                const FastSum g = sm_gather(sbuf + q, xs);
+                if (q < nloc * P && !sm.wskip[q / P]) {
+                    sm.pe[q] = g.e; sm.pt[q] = g.t; sm.pa[q] = g.a; sm.pbad[q] = (unsigned char)g.bad;
                 }
             }
             __syncthreads();
             stamp(2);
-            if (tid < nloc && !sm.wskip[tid]) {
-                FastSum h{sm.pe[tid * P], sm.pt[tid * P], sm.pa[tid * P], sm.pbad[tid * P]};
+            for (unsigned lc = tid; lc < nloc; lc += NT) {
+                if (sm.wskip[lc]) continue;
+                FastSum h{sm.pe[lc * P], sm.pt[lc * P], sm.pa[lc * P], sm.pbad[lc * P]};
                 for (unsigned q = 1; q < P; ++q) {
-                    h.e += sm.pe[tid * P + q]; h.t += sm.pt[tid * P + q]; h.a += sm.pa[tid * P + q];
-                    h.bad |= sm.pbad[tid * P + q];
+                    h.e += sm.pe[lc * P + q]; h.t += sm.pt[lc * P + q]; h.a += sm.pa[lc * P + q];
+                    h.bad |= sm.pbad[lc * P + q];
                 }
-                const unsigned pos = cursor + woff + world * tid;
+                const unsigned pos = cursor + woff + world * lc;
                 const double mean_entropy =
                     div_exact(__dadd_rn(__dsub_rn(E, sm.mH[mw][lowest]), sm.cH[pos - cbase]), div_n);
                 const double d = h.e - mean_entropy;
@@ -287,27 +314,36 @@ k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, uns
                     __syncthreads();
                 }
             }
-            if (tid == 0) sm_st128(&dslot->w[0], ((unsigned long long)sm.fu << 32) | sm.ft, xs);
+            if (tid == 0) {
+                unsigned nl = limit;
+                if (ready_pos) nl = max(limit, min(num, *reinterpret_cast<const volatile unsigned*>(ready_pos)));
+                sm.limit = nl;
+                sm_st128(&dslot->w[0], ((unsigned long long)sm.fu << 32) | sm.ft, ((unsigned long long)nl << 32) | xs);
+            }
+            __syncthreads();  // sm.limit
         } else {
             if (tid == 0) {
                 unsigned long long w0, w1;
                 do sm_ld128(&dslot->w[0], w0, w1); while ((unsigned)w1 != xs);
                 sm.ft = (unsigned)w0;
                 sm.fu = (unsigned)(w0 >> 32);
+                sm.limit = (unsigned)(w1 >> 32);
             }
             stamp(2);
             __syncthreads();
         }
         const unsigned ft = sm.ft, fu = sm.fu;
+        const unsigned next_limit = sm.limit;
         __syncthreads();
         stamp(3);
         if (fu < ft) {  // the first interesting candidate is undecided: the host resolves it exactly
             halt = 1;
             break;
         }
-        if (ft == kNone) {  // empty window
+        if (ft == kNone) {  // empty window (or, trailing, nothing published beyond the cursor yet)
             cursor += count;
-            window = min(window * 2u, Gw);
+            if (count) window = min(window * 2u, Gw);
+            limit = next_limit;
             stamp(4); stamp(5); stamp(6);
             ++tr_round;
             continue;
@@ -330,14 +366,14 @@ k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, uns
         for (unsigned j = b; j <= n; j += G) {
             FastSum h;
             if (j == n) {
-                h = block_entropy_ilp<false, 8>(0u, dim, [&](unsigned i) {
+                h = block_entropy_ilp<false, 8, NT>(0u, dim, [&](unsigned i) {
                     const double s = have_S ? sm.S[i] : s_new(i);
                     if (!have_S) sm.S[i] = s;
                     return s;
                 }, div_n, sm.ltab);
             } else {
                 const double* f = F + (size_t)member_after(j) * dim;
-                h = block_entropy_ilp<true, 8>(0u, dim, [&](unsigned i) {
+                h = block_entropy_ilp<true, 8, NT>(0u, dim, [&](unsigned i) {
                     const double s = have_S ? sm.S[i] : s_new(i);
                     if (!have_S) sm.S[i] = s;
                     return __dsub_rn(s, f[i]);
@@ -347,10 +383,10 @@ k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, uns
             have_S = true;
         }
         if (!have_S)
-            for (unsigned i = tid; i < dim; i += kFastThreads) sm.S[i] = s_new(i);
+            for (unsigned i = tid; i < dim; i += NT) sm.S[i] = s_new(i);
         stamp(4);
         // ---- every CTA: new member list; the leader: deltas + certified argmin, broadcast ----
-        for (unsigned t = tid; t < n; t += kFastThreads) {
+        for (unsigned t = tid; t < n; t += NT) {
             sm.members[mw ^ 1][t] = member_after(t);
             sm.mH[mw ^ 1][t] = t < lowest ? sm.mH[mw][t] : (t + 1 < n ? sm.mH[mw][t + 1] : Hc);
         }
@@ -362,7 +398,7 @@ k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, uns
         SmPart* const fslot = dpart + 2;
         if (b == 0) {
             int uns = 0;
-            for (unsigned t = tid; t <= n; t += kFastThreads) {
+            for (unsigned t = tid; t <= n; t += NT) {
                 const FastSum g = sm_gather(upart + t, xu);
                 if (t == n) {
                     sm.pe[0] = g.e; sm.pa[0] = g.a;  // (scan staging is free again)
@@ -379,7 +415,7 @@ k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, uns
             const double me = div_exact(E, div_n);
             total_jsd = sm.pe[0] - me;
             total_bound = kb0 * (sm.pa[0] + fabs(me) + 1.0);
-            unsure = sm_finalize(sm.md, sm.mb, n, total_jsd, total_bound, &lo2);
+            unsure = sm_finalize<NT>(sm.md, sm.mb, n, total_jsd, total_bound, &lo2);
             unsure |= sm.unsure;
             if (tid == 0) {
                 sm_st128(&fslot->w[0], (unsigned long long)__double_as_longlong(total_jsd), ((unsigned long long)lo2 << 32) | xu);
@@ -406,6 +442,7 @@ k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, uns
         }
         lowest = lo2;
         touched = true;
+        limit = next_limit;
         window = max(wmin, min(Gw, 2u * (ft - cursor + 1u)));
         cursor = ft + 1u;
         ++accepts;
@@ -423,10 +460,10 @@ k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, uns
     if (b == 0) {
         __syncthreads();
         if (touched) {
-            for (unsigned i = tid; i < dim; i += kFastThreads) S_glob[i] = sm.S[i];
-            for (unsigned j = tid; j < n; j += kFastThreads) is_member[M_glob[j]] = 0;  // the set at entry
+            for (unsigned i = tid; i < dim; i += NT) S_glob[i] = sm.S[i];
+            for (unsigned j = tid; j < n; j += NT) is_member[M_glob[j]] = 0;  // the set at entry
             __syncthreads();
-            for (unsigned j = tid; j < n; j += kFastThreads) {
+            for (unsigned j = tid; j < n; j += NT) {
                 const unsigned r = sm.members[mw][j];
                 M_glob[j] = r;
                 is_member[r] = 1;
@@ -451,6 +488,7 @@ k_sel_persist_sm(const double* __restrict__ F, const double* __restrict__ H, uns
             sc->window = window;
             sc->accepts = accepts;
             sc->halt = halt;
+            sc->limit = limit;
         }
     }
 }

@@ -76,6 +76,7 @@ uint64_t dvs_ctx_launch_count(dvs_ctx* ctx);
 #define DVS_PHASE_UPLOAD 6         /* host->device sequence copy of dvs_seqset_upload */
 #define DVS_PHASE_CLUSTER 8        /* k_cl_symmetrise + k_cl_nn_chain of one dvs_linkage_average */
 #define DVS_PHASE_SPARSE 9         /* the partition passes of one dvs_count_kmers_sparse (without the optional entropies) */
+#define DVS_PHASE_COUNT_LAUNCHES 10 /* chunked counting (sharded / dvs_count_select): sum of the counting launches alone */
 #define DVS_PHASE_PREP 7           /* all device work of one dvs_prep_fasta (k_prep x2 + k_prep_carry) */
 /* bytes that actually crossed PCIe during the last dvs_seqset_upload (2-bit packed + exceptions for
  * large uploads, see csrc/upload.cu; equal to the input size for the plain copy) */
@@ -190,6 +191,11 @@ uint32_t dvs_select_last_accepts(dvs_ctx* ctx);
  * dvs_select (0 when every decision was far from a tie; environment DVS_SELECT_EXACT_ONLY=1
  * disables the fast path altogether) */
 uint32_t dvs_select_last_exact_evals(dvs_ctx* ctx);
+/* ... and how many were accepted while the counting of dvs_count_select was still running */
+uint32_t dvs_select_last_trail_accepts(dvs_ctx* ctx);
+/* launches of the trailing kernel in that call, and the fewest distinct SMs the CTAs of one of them sat on */
+uint32_t dvs_select_last_trail_launches(dvs_ctx* ctx);
+uint32_t dvs_select_last_trail_sms(dvs_ctx* ctx);
 
 /* SummedRecords::new over the listed rows + delta_jsd queries: make_summed_records and
  * SummedRecordsWrapper (src/records.rs:509-524, src/records_py.rs:90-125) */
@@ -305,6 +311,17 @@ int dvs_euclid_distances_sharded(dvs_ctx* ctx, dvs_comm* c, const dvs_kfreqs* f_
 int dvs_select_sharded(dvs_ctx* ctx, dvs_comm* c, const dvs_kfreqs* f_all, const uint32_t* order, uint32_t num,
                        int mode, uint32_t min_size, uint32_t max_size, uint32_t* sel_idx, double* sel_delta,
                        double* stats5, uint32_t* size_out);
+
+/* dvs_count_kmers + dvs_select in one call with the two OVERLAPPED on one GPU (the `dvs prep` -> `dvs nmost` flow of
+ * BASELINE.json configs[1]; reference: src/lib.rs nmost() over the records src/record.rs KmerSeq::new builds).
+ * The records are counted on a second stream in the sequence `order` examines them, `chunks` launches (0 = default
+ * 8, at most 64); after each launch the number of positions whose rows exist is published in a device word and the
+ * nmost rounds - a slim SM-replicated kernel co-resident with the counting CTAs - examine only positions below it.
+ * Results (rows in *out, selection, stats) are bit-identical to the two separate calls.  Modes other than
+ * DVS_MODE_NMOST, n > 256, dim > 4096 or min_size larger than the first chunk run the two steps back to back. */
+int dvs_count_select(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, const uint32_t* order, uint32_t num,
+                     int mode, uint32_t min_size, uint32_t max_size, uint32_t chunks, dvs_kfreqs** out,
+                     uint32_t* sel_idx, double* sel_delta, double* stats5, uint32_t* size_out);
 
 /* ---- test hooks ---------------------------------------------------------------------------- */
 /* host half of the packed upload (transfer encoding, no GPU needed): packs src[0..n) 4 bases per

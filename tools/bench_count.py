@@ -21,6 +21,13 @@ VARIANTS = {
     "s3_1024x2": {"DVS_COUNT_S3_SHAPE": "1"},
     "s3_512x4": {"DVS_COUNT_S3_SHAPE": "2"},
     "s3scr": {"DVS_COUNT_SCRAMBLE": "1"},
+    # a smaller L1 (what a co-resident kernel's shared memory costs): 144 KB table + pad -> carve-out 196 / 228 KB
+    "x2_pad18": {"DVS_COUNT_S3_SHAPE": "1", "DVS_COUNT_SMEM_PAD": "18000"},
+    "x2_pad48": {"DVS_COUNT_S3_SHAPE": "1", "DVS_COUNT_SMEM_PAD": "48000"},
+    "x2_pad66": {"DVS_COUNT_S3_SHAPE": "1", "DVS_COUNT_SMEM_PAD": "66000"},
+    "x2_pad80": {"DVS_COUNT_S3_SHAPE": "1", "DVS_COUNT_SMEM_PAD": "80000"},
+    "x3_pad48": {"DVS_COUNT_SMEM_PAD": "48000"},
+    "x3_pad80": {"DVS_COUNT_SMEM_PAD": "80000"},
     "super": {"DVS_COUNT_S3": "0"},                   # (k+1)-mer kernel of round 1
     "super_noscr": {"DVS_COUNT_S3": "0", "DVS_COUNT_SCRAMBLE": "0"},
 }
