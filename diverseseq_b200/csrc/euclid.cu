@@ -281,37 +281,56 @@ k_eg_gram(const double* __restrict__ F, uint64_t dim, uint32_t n, const EgTile* 
                 make_double2(c[m][q][0], c[m][q][1]);
 }
 
-// partial tiles -> distances; pairs whose d^2 is too small for the Gram form go to the list
+// partial tiles -> distances; pairs whose d^2 is too small for the Gram form go to the list.
+// A tile is finished in 32 x 32 sub-blocks that pass through shared memory, so that BOTH the (i, j) and the mirrored
+// (j, i) stores are 256-byte row segments: with up to 8 destination matrices behind NVLink, element-wise mirrored
+// stores (8 bytes each, stride n) made the 8-GPU run slower than one GPU (533 ms against 255 ms).
 __global__ void __launch_bounds__(256)
 k_eg_finish(const double* __restrict__ P, const double* __restrict__ nrm, const EgTile* __restrict__ tiles, uint32_t ntiles,
             uint32_t nslices, uint32_t n, uint32_t row_begin, uint32_t row_end, const EuOuts outs,
             uint2* __restrict__ flagged, uint32_t flag_cap, uint32_t* __restrict__ flag_count) {
+    __shared__ double sd[32][33];  // < 0: nothing to store (outside the matrix / the triangle, or listed)
     const uint32_t tile = blockIdx.x;
     const EgTile tt = tiles[tile];
     const uint32_t i0 = tt.ti * kEgT, j0 = tt.tj * kEgT;
-    for (uint32_t e = threadIdx.x; e < kEgT * kEgT; e += blockDim.x) {
-        const uint32_t i = i0 + e / kEgT, j = j0 + e % kEgT;
-        if (i >= n || j >= n || j > i) continue;  // (diagonal tiles: the lower half only)
-        const bool wr_ij = i >= row_begin && i < row_end, wr_ji = j >= row_begin && j < row_end;
-        if (!wr_ij && !wr_ji) continue;
-        double d = 0.0;
-        bool flag = false;
-        if (i != j) {
-            double gsum = 0.0;
-            for (uint32_t sl = 0; sl < nslices; ++sl) gsum += P[((size_t)sl * ntiles + tile) * kEgT * kEgT + e];
-            const double na = nrm[i], nb = nrm[j], d2 = (na + nb) - 2.0 * gsum;
-            if (d2 >= kEgTau * (na + nb)) d = sqrt(d2);
-            else flag = true;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    constexpr uint32_t kSub = kEgT / 32;
+    for (uint32_t sb = 0; sb < kSub * kSub; ++sb) {
+        const uint32_t si = (sb / kSub) * 32, sj = (sb % kSub) * 32;
+        if (i0 + si >= n || j0 + sj >= n || j0 + sj > i0 + si + 31) continue;  // (block-uniform)
+        for (uint32_t q = 0; q < 4; ++q) {
+            const uint32_t r = warp * 4 + q;
+            const uint32_t i = i0 + si + r, j = j0 + sj + lane;
+            double d = -1.0;
+            if (i < n && j < n && j <= i) {
+                d = 0.0;
+                if (i != j) {
+                    const uint32_t e = (si + r) * kEgT + sj + lane;
+                    double gsum = 0.0;
+                    for (uint32_t sl = 0; sl < nslices; ++sl) gsum += P[((size_t)sl * ntiles + tile) * kEgT * kEgT + e];
+                    const double na = nrm[i], nb = nrm[j], d2 = (na + nb) - 2.0 * gsum;
+                    if (d2 >= kEgTau * (na + nb)) {
+                        d = sqrt(d2);
+                    } else {  // written by k_eg_pairs (or by the difference-form kernel if the list overflows)
+                        const uint32_t at = atomicAdd(flag_count, 1u);
+                        if (at < flag_cap) flagged[at] = make_uint2(i, j);
+                        d = -1.0;
+                    }
+                }
+            }
+            sd[r][lane] = d;
+            if (d >= 0.0 && i >= row_begin && i < row_end)
+                for (int o = 0; o < outs.count; ++o) outs.p[o][(size_t)(i - row_begin) * n + j] = d;
         }
-        if (flag) {
-            const uint32_t at = atomicAdd(flag_count, 1u);
-            if (at < flag_cap) flagged[at] = make_uint2(i, j);
-            continue;  // written by k_eg_pairs (or by the difference-form kernel if the list overflows)
+        __syncthreads();
+        for (uint32_t q = 0; q < 4; ++q) {  // the mirror image: row j of the output, columns i
+            const uint32_t c = warp * 4 + q;
+            const uint32_t i = i0 + si + lane, j = j0 + sj + c;
+            const double d = sd[lane][c];
+            if (d >= 0.0 && j >= row_begin && j < row_end)
+                for (int o = 0; o < outs.count; ++o) outs.p[o][(size_t)(j - row_begin) * n + i] = d;
         }
-        for (int r = 0; r < outs.count; ++r) {
-            if (wr_ij) outs.p[r][(size_t)(i - row_begin) * n + j] = d;
-            if (wr_ji) outs.p[r][(size_t)(j - row_begin) * n + i] = d;
-        }
+        __syncthreads();
     }
 }
 
