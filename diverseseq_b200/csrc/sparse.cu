@@ -268,14 +268,18 @@ __global__ void __launch_bounds__(32 * kSpWarpsPerCta)
 k_sp_bucket_warp(const uint16_t* __restrict__ lowbuf, const uint64_t* __restrict__ offsets,
                  const uint32_t* __restrict__ bucket_ptr, uint32_t nrec, uint32_t nb, uint32_t* __restrict__ out_idx,
                  uint32_t* __restrict__ out_cnt, uint32_t* __restrict__ bucket_nnz, uint64_t* __restrict__ big_list,
-                 uint32_t* __restrict__ big_count) {
+                 uint32_t* __restrict__ big_count, const uint64_t* __restrict__ list,
+                 const uint32_t* __restrict__ list_count) {
     extern __shared__ __align__(16) uint32_t sp_wsmem[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* h = sp_wsmem + warp * (kSpLowBins / 2);
-    const uint64_t npairs = (uint64_t)nrec * nb;
+    // list == NULL: every (record, bucket) pair; otherwise the pairs k_sp_bucket_bits left
+    const uint64_t npairs = list ? (uint64_t)*list_count : (uint64_t)nrec * nb;
     const uint32_t lt = (1u << lane) - 1u;
-    for (uint64_t p = (uint64_t)blockIdx.x * kSpWarpsPerCta + warp; p < npairs; p += (uint64_t)gridDim.x * kSpWarpsPerCta) {
-        const uint32_t rec = (uint32_t)(p / nb), b = (uint32_t)(p % nb);
+    const int nb_log2 = __ffs(nb) - 1;
+    for (uint64_t q = (uint64_t)blockIdx.x * kSpWarpsPerCta + warp; q < npairs; q += (uint64_t)gridDim.x * kSpWarpsPerCta) {
+        const uint64_t p = list ? list[q] : q;
+        const uint32_t rec = (uint32_t)(p >> nb_log2), b = (uint32_t)p & (nb - 1u);  // (nb = 4^(k-6))
         const uint32_t* bp = bucket_ptr + (size_t)rec * (nb + 1);
         const uint32_t s0 = bp[b], n = bp[b + 1] - s0;
         if (n == 0) {
@@ -320,6 +324,141 @@ k_sp_bucket_warp(const uint16_t* __restrict__ lowbuf, const uint64_t* __restrict
             out_cnt[base + e] = 0u;
         }
         if (lane == 0) bucket_nnz[p] = run;
+        __syncwarp();
+    }
+}
+
+// pass 2, bitmap form - for the SPARSELY occupied buckets of k = 11, 12 (a bucket of ~1,000 keys over 4,096 bins:
+// three quarters of the keys are the only one of their bin).  Walking 4,096 counters for 1,000 keys made
+// k_sp_bucket_warp instruction bound (4.2 warp instructions per key); here a warp
+//   1. sets the bit of every key in a 4,096-bit occupancy bitmap (atomicOr),
+//   2. forms the prefix of the bitmap's word popcounts: rank(bin) = pre[word] + popc(bits below) is the position of
+//      the bin among the distinct ones,
+//   3. reads the keys again (L1 hits) and, for each, stores the bin at its rank in a 16-bit stage and adds one to a
+//      16-bit count stage at that rank (every occurrence writes the same bin: no "first occurrence" logic),
+//   4. writes the row from the two stages with coalesced stores.
+// All loops are warp-uniform.  Buckets with more than kSpBitsMaxDistinct distinct keys (or 65,535 keys) are listed
+// for k_sp_bucket_warp.
+constexpr uint32_t kSpBitsMaxDistinct = 2048;
+constexpr int kSpBitsWarps = 8;
+struct __align__(16) SpBitsWarp {
+    uint32_t bm[kSpLowBins / 32];
+    uint32_t pre[kSpLowBins / 32];
+    uint32_t cnt[kSpBitsMaxDistinct / 2];  // 16-bit halves
+    uint16_t idx[kSpBitsMaxDistinct];
+};
+__global__ void __launch_bounds__(32 * kSpBitsWarps)
+k_sp_bucket_bits(const uint16_t* __restrict__ lowbuf, const uint64_t* __restrict__ offsets,
+                 const uint32_t* __restrict__ bucket_ptr, uint32_t nrec, uint32_t nb, uint32_t* __restrict__ out_idx,
+                 uint32_t* __restrict__ out_cnt, uint32_t* __restrict__ bucket_nnz, uint64_t* __restrict__ mid_list,
+                 uint32_t* __restrict__ mid_count) {
+    extern __shared__ __align__(16) unsigned char sp_bits_raw[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SpBitsWarp& sw = reinterpret_cast<SpBitsWarp*>(sp_bits_raw)[warp];
+    const uint64_t npairs = (uint64_t)nrec * nb, stride = (uint64_t)gridDim.x * kSpBitsWarps;
+    const int nb_log2 = __ffs(nb) - 1;
+    // (s0, n, record base) of a pair; the next pair's are fetched while the current one is processed
+    auto fetch = [&](uint64_t p, uint32_t& s0, uint32_t& n, uint64_t& rbase) {
+        if (p < npairs) {
+            const uint32_t rec = (uint32_t)(p >> nb_log2), b = (uint32_t)p & (nb - 1u);  // (nb = 4^(k-6))
+            const uint32_t* bp = bucket_ptr + (size_t)rec * (nb + 1);
+            s0 = __ldg(bp + b);
+            n = __ldg(bp + b + 1) - s0;
+            rbase = __ldg(offsets + rec);
+        }
+    };
+    uint64_t p = (uint64_t)blockIdx.x * kSpBitsWarps + warp;
+    uint32_t s0 = 0, n = 0, s0_next = 0, n_next = 0;
+    uint64_t rbase = 0, rbase_next = 0;
+    fetch(p, s0, n, rbase);
+    for (; p < npairs; p += stride, s0 = s0_next, n = n_next, rbase = rbase_next) {
+        fetch(p + stride, s0_next, n_next, rbase_next);
+        if (n == 0) {
+            if (lane == 0) bucket_nnz[p] = 0;
+            continue;
+        }
+        if (n > 65535u) {  // (warp-uniform) a 16-bit count could overflow
+            if (lane == 0) mid_list[atomicAdd(mid_count, 1u)] = p;
+            continue;
+        }
+        const uint64_t base = rbase + s0;
+        const uint16_t* __restrict__ src = lowbuf + base;
+        uint32_t* __restrict__ oi = out_idx + base;
+        uint32_t* __restrict__ oc = out_cnt + base;
+        reinterpret_cast<uint4*>(sw.bm)[lane] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        // (the loops are kept compact on purpose: a fully unrolled, register-resident variant ran into instruction
+        // cache misses - stall_no_instruction 5.8 per issue - and was slower)
+        uint32_t e0 = 0;
+        for (; e0 + 256 <= n; e0 += 256) {  // eight loads in flight per lane
+            uint32_t kk[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) kk[q] = __ldg(src + e0 + lane + 32 * q);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) atomicOr(&sw.bm[kk[q] >> 5], 1u << (kk[q] & 31u));
+        }
+        for (uint32_t e = e0 + lane; e < n; e += 32) {
+            const uint32_t key = __ldg(src + e);
+            atomicOr(&sw.bm[key >> 5], 1u << (key & 31u));
+        }
+        __syncwarp();
+        // rank of every bitmap word among the distinct bins
+        const uint4 m4 = reinterpret_cast<const uint4*>(sw.bm)[lane];
+        const uint32_t c0 = __popc(m4.x), c1 = __popc(m4.y), c2 = __popc(m4.z), c3 = __popc(m4.w);
+        const uint32_t mine = c0 + c1 + c2 + c3;
+        uint32_t inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o) inc += t;
+        }
+        const uint32_t nnz = __shfl_sync(0xffffffffu, inc, 31), excl = inc - mine;
+        if (nnz > kSpBitsMaxDistinct) {  // (warp-uniform)
+            if (lane == 0) mid_list[atomicAdd(mid_count, 1u)] = p;
+            __syncwarp();
+            continue;
+        }
+        reinterpret_cast<uint4*>(sw.pre)[lane] = make_uint4(excl, excl + c0, excl + c0 + c1, excl + c0 + c1 + c2);
+        for (uint32_t i = lane; i < (nnz + 7) / 8; i += 32) reinterpret_cast<uint4*>(sw.cnt)[i] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        auto place = [&](uint32_t key) {
+            const uint32_t w = key >> 5;
+            const uint32_t r = sw.pre[w] + __popc(sw.bm[w] & ((1u << (key & 31u)) - 1u));
+            sw.idx[r] = (uint16_t)key;
+            atomicAdd(&sw.cnt[r >> 1], (r & 1u) ? 0x10000u : 1u);
+        };
+        for (e0 = 0; e0 + 256 <= n; e0 += 256) {  // (L1 hits)
+            uint32_t kk[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) kk[q] = __ldg(src + e0 + lane + 32 * q);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) place(kk[q]);
+        }
+        for (uint32_t e = e0 + lane; e < n; e += 32) place(__ldg(src + e));
+        __syncwarp();
+        const uint32_t idx_hi = ((uint32_t)p & (nb - 1u)) << kSpLowBits;
+        // two entries per lane and step, from the first slot that is 8-byte aligned in the output
+        const uint16_t* cnt16 = reinterpret_cast<const uint16_t*>(sw.cnt);
+        const uint32_t first = (uint32_t)base & 1u;
+        if (first && lane == 0) {
+            oi[0] = idx_hi | sw.idx[0];
+            oc[0] = cnt16[0];
+        }
+        const uint32_t pairs = (nnz - first) >> 1;
+        for (uint32_t q = lane; q < pairs; q += 32) {
+            const uint32_t a = first + 2u * q;
+            *reinterpret_cast<uint2*>(oi + a) = make_uint2(idx_hi | sw.idx[a], idx_hi | sw.idx[a + 1]);
+            *reinterpret_cast<uint2*>(oc + a) = make_uint2(cnt16[a], cnt16[a + 1]);
+        }
+        if (((nnz - first) & 1u) && lane == 0) {
+            oi[nnz - 1] = idx_hi | sw.idx[nnz - 1];
+            oc[nnz - 1] = cnt16[nnz - 1];
+        }
+        for (uint32_t q = nnz + lane; q < n; q += 32) {  // unused slots of the bucket: "no entry"
+            oi[q] = 0xFFFFFFFFu;
+            oc[q] = 0u;
+        }
+        if (lane == 0) bucket_nnz[p] = nnz;
         __syncwarp();
     }
 }
@@ -532,9 +671,29 @@ int dvs_count_kmers_sparse(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_sta
             TRY_P(cudaFuncSetAttribute(k_sp_bucket_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
             const unsigned g_w = (unsigned)std::min<uint64_t>((npairs + kSpWarpsPerCta - 1) / kSpWarpsPerCta,
                                                               (uint64_t)ctx->sm_count * 3 * 4);
+            // sparsely occupied buckets (k >= 11: 4^k bins against ~L keys) go through the bitmap kernel first;
+            // DVS_SPARSE_BITS=0 keeps the counter-walking warp kernel for everything (A/B measurements)
+            const char* bits_env = getenv("DVS_SPARSE_BITS");
+            const bool use_bits = k >= 11 && !(bits_env && bits_env[0] == '0');
+            DevBuf<uint64_t> d_mid;
+            DevBuf<uint32_t> d_nmid;
+            if (use_bits) {
+                if (d_mid.alloc(std::max<uint64_t>(npairs, 1)) != DVS_OK || d_nmid.alloc(1) != DVS_OK) return fail(DVS_ERR_CUDA);
+                TRY_P(cudaMemsetAsync(d_nmid.p, 0, sizeof(uint32_t), st));
+                const size_t smem_b = (size_t)kSpBitsWarps * sizeof(SpBitsWarp);
+                TRY_P(cudaFuncSetAttribute(k_sp_bucket_bits, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+                const unsigned g_b = (unsigned)std::min<uint64_t>((npairs + kSpBitsWarps - 1) / kSpBitsWarps,
+                                                                  (uint64_t)ctx->sm_count * 2 * 4);
+                k_sp_bucket_bits<<<g_b, 32 * kSpBitsWarps, smem_b, st>>>(d_low.p, sp->offsets.p, sp->bucket_ptr.p, nrec, nb,
+                                                                         sp->idx.p, sp->cnt.p, sp->bucket_nnz.p, d_mid.p,
+                                                                         d_nmid.p);
+                ctx->launches++;
+                TRY_P(cudaGetLastError());
+            }
             k_sp_bucket_warp<<<g_w, 32 * kSpWarpsPerCta, smem_w, st>>>(d_low.p, sp->offsets.p, sp->bucket_ptr.p, nrec, nb,
                                                                        sp->idx.p, sp->cnt.p, sp->bucket_nnz.p, d_big.p,
-                                                                       d_nbig.p);
+                                                                       d_nbig.p, use_bits ? d_mid.p : nullptr,
+                                                                       use_bits ? d_nmid.p : nullptr);
             ctx->launches++;
             TRY_P(cudaGetLastError());
             k_sp_bucket<<<(unsigned)std::min<uint64_t>(big_cap, (uint64_t)ctx->sm_count * 8), kSpBucketThreads, 0, st>>>(
