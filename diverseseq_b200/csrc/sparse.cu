@@ -171,8 +171,7 @@ k_sp_partition(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ of
     __shared__ uint32_t s_warp[34];
     uint32_t* stage = sp_smem;                 // [kSpItemBytes] bucket-sorted keys of the item
     uint32_t* lcur = stage + kSpItemBytes;     // [nb] cursor inside the stage
-    uint32_t* lstart = lcur + nb;              // [nb] first stage slot of the bucket
-    uint32_t* goff = lstart + nb;              // [nb] first slot of this item's run inside the record's region
+    uint32_t* goff = lcur + nb;                // [nb] (first slot of this item's run in the record's region) - (its stage slot)
     const uint32_t mask = (1u << (2 * k)) - 1u;
     const uint32_t per = (nb + kSpThreads - 1) / kSpThreads, b0 = threadIdx.x * per;
     for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x) {
@@ -189,8 +188,8 @@ k_sp_partition(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ of
         uint32_t base = sp_block_exscan(mine, s_warp, &n);
         for (uint32_t q = 0; q < per; ++q)
             if (b0 + q < nb) {
-                lstart[b0 + q] = base;
                 lcur[b0 + q] = base;
+                goff[b0 + q] -= base;  // stage slot e of bucket b goes to slot goff[b] + e of the record's region
                 base += cnt[q];
             }
         __syncthreads();
@@ -202,7 +201,7 @@ k_sp_partition(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ of
         uint16_t* dst = lowbuf + start;  // the record's region starts at its byte offset (#k-mers <= #bytes)
         for (uint32_t e = threadIdx.x; e < n; e += kSpThreads) {
             const uint32_t key = stage[e], b = key >> kSpLowBits;
-            dst[goff[b] + (e - lstart[b])] = (uint16_t)(key & (kSpLowBins - 1u));
+            dst[goff[b] + e] = (uint16_t)(key & (kSpLowBins - 1u));  // (mod 2^32: goff may have wrapped)
         }
         __syncthreads();
     }
@@ -389,17 +388,25 @@ k_sp_bucket_bits(const uint16_t* __restrict__ lowbuf, const uint64_t* __restrict
         __syncwarp();
         // (the loops are kept compact on purpose: a fully unrolled, register-resident variant ran into instruction
         // cache misses - stall_no_instruction 5.8 per issue - and was slower)
-        uint32_t e0 = 0;
-        for (; e0 + 256 <= n; e0 += 256) {  // eight loads in flight per lane
-            uint32_t kk[8];
+        // batches of 256 keys (8 per lane); the next batch is loaded before the current one is used, and the last,
+        // partial batch is a predicated one (0xFFFFFFFF = no key): one exposed memory latency per bucket instead of
+        // one per batch plus one per 32 keys of the remainder
+        auto load8 = [&](uint32_t e0, uint32_t (&kk)[8]) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) kk[q] = __ldg(src + e0 + lane + 32 * q);
+            for (int q = 0; q < 8; ++q) {
+                const uint32_t e = e0 + lane + 32u * q;
+                kk[q] = e < n ? (uint32_t)__ldg(src + e) : 0xFFFFFFFFu;
+            }
+        };
+        uint32_t ka[8], kb[8];
+        load8(0, ka);
+        for (uint32_t e0 = 0; e0 < n; e0 += 256) {
+            load8(e0 + 256, kb);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) atomicOr(&sw.bm[kk[q] >> 5], 1u << (kk[q] & 31u));
-        }
-        for (uint32_t e = e0 + lane; e < n; e += 32) {
-            const uint32_t key = __ldg(src + e);
-            atomicOr(&sw.bm[key >> 5], 1u << (key & 31u));
+            for (int q = 0; q < 8; ++q) {
+                if (ka[q] != 0xFFFFFFFFu) atomicOr(&sw.bm[ka[q] >> 5], 1u << (ka[q] & 31u));
+                ka[q] = kb[q];
+            }
         }
         __syncwarp();
         // rank of every bitmap word among the distinct bins
@@ -427,14 +434,15 @@ k_sp_bucket_bits(const uint16_t* __restrict__ lowbuf, const uint64_t* __restrict
             sw.idx[r] = (uint16_t)key;
             atomicAdd(&sw.cnt[r >> 1], (r & 1u) ? 0x10000u : 1u);
         };
-        for (e0 = 0; e0 + 256 <= n; e0 += 256) {  // (L1 hits)
-            uint32_t kk[8];
+        load8(0, ka);  // (L1 hits)
+        for (uint32_t e0 = 0; e0 < n; e0 += 256) {
+            load8(e0 + 256, kb);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) kk[q] = __ldg(src + e0 + lane + 32 * q);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) place(kk[q]);
+            for (int q = 0; q < 8; ++q) {
+                if (ka[q] != 0xFFFFFFFFu) place(ka[q]);
+                ka[q] = kb[q];
+            }
         }
-        for (uint32_t e = e0 + lane; e < n; e += 32) place(__ldg(src + e));
         __syncwarp();
         const uint32_t idx_hi = ((uint32_t)p & (nb - 1u)) << kSpLowBits;
         // two entries per lane and step, from the first slot that is 8-byte aligned in the output
@@ -636,7 +644,7 @@ int dvs_count_kmers_sparse(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_sta
     TRY_P(cudaMemsetAsync(sp->entropy.p, 0, n1 * sizeof(double), st));
     if (nrec && nitems) {
         PhaseTimer pt(ctx, DVS_PHASE_SPARSE);
-        const size_t smem_hist = (size_t)nb * 4, smem_part = ((size_t)kSpItemBytes + 3 * (size_t)nb) * 4;
+        const size_t smem_hist = (size_t)nb * 4, smem_part = ((size_t)kSpItemBytes + 2 * (size_t)nb) * 4;
         TRY_P(cudaFuncSetAttribute(k_sp_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_part));
         const unsigned g_hist = (unsigned)std::min<size_t>(nitems, (size_t)ctx->sm_count * 2);
         const unsigned g_part = (unsigned)std::min<size_t>(nitems, (size_t)ctx->sm_count);
