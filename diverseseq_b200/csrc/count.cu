@@ -827,8 +827,9 @@ static int count_core(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, 
     if (chunk_ev)
         for (uint32_t i = 0; i < 2 * nchunks; ++i)
             if (!ctx->ev_chunk[i]) TRY_F(cudaEventCreate(&ctx->ev_chunk[i]));
+    auto chunk_first = [&](uint32_t c) { return (uint32_t)((uint64_t)s->nrec * c / nchunks); };
     for (uint32_t ch = 0; ch < nchunks; ++ch) {
-        const uint32_t rb = (uint32_t)((uint64_t)s->nrec * ch / nchunks), re = (uint32_t)((uint64_t)s->nrec * (ch + 1) / nchunks);
+        const uint32_t rb = chunk_first(ch), re = chunk_first(ch + 1);
         const uint32_t ib = s->work_item_begin[rb], ie = s->work_item_begin[re];
         const CountWork* d_work = d_work_all + ib;
         const uint32_t n_work = ie - ib;
@@ -1252,7 +1253,11 @@ int dvs_count_kmers_sharded(dvs_ctx* ctx, dvs_comm* c, const dvs_seqset* s, int 
     if (rc == DVS_OK) rc = comm_barrier(ctx, c);
     if (rc != DVS_OK) return fail(rc);
     const char* ch_env = getenv("DVS_SHARD_CHUNKS");
-    const uint32_t chunks = c->world == 1 ? 1u : (uint32_t)std::max(1, std::min(64, ch_env ? atoi(ch_env) : 8));
+    // every launch costs the counting ~0.12 ms (2 GPUs: 3 chunks 9.52 ms, 4: 9.60, 8: 10.11, 12: 10.79), while what the last
+    // chunk leaves to push - 1/chunks of the rows to world - 1 peers - is exposed: few chunks, a few more with more peers
+    // (chunks tapering towards the end were measured too: the small last launches balance badly, 10.27 ms at 4)
+    const int dflt_chunks = c->world <= 2 ? 4 : 6;
+    const uint32_t chunks = c->world == 1 ? 1u : (uint32_t)std::max(1, std::min(64, ch_env ? atoi(ch_env) : dflt_chunks));
     const size_t r0 = a.row0;
     CountDest dst{a.f->freqs.p + r0 * dim, a.f->totals.p + r0, a.f->entropy.p + r0, a.f->valid.p + r0, a.f->err.p + r0,
                   a.f->err_total.p + r0, chunks, nullptr};
