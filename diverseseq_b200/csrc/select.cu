@@ -620,6 +620,8 @@ static int select_core(dvs_ctx* ctx, dvs_comm* comm, const dvs_kfreqs* f, const 
                                        (int)cudaSharedmemCarveoutMaxShared) == cudaSuccess;
         (void)cudaGetLastError();
     }
+    DevBuf<SlicePart> d_slparts;  // k_sel_persist: partial sums of sliced vectors and their arrival tickets
+    DevBuf<unsigned> d_slticks;
     DevBuf<SmPart> d_spart, d_upart, d_dpart;
     if (sm_ok) {
         DVS_TRY(d_spart.alloc(2 * kSmMaxGrid));
@@ -778,8 +780,21 @@ static int select_core(dvs_ctx* ctx, dvs_comm* comm, const dvs_kfreqs* f, const 
                     DVS_CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_sel_persist_sm_full, dim3(grid), dim3(kFastThreads),
                                                              args, sizeof(SmShared), st));
             } else {
+                // DVS_SELECT_SLICES (A/B measurements): 0 = one CTA per candidate / member slot, 1 = candidates of a short
+                // window are cut into slices (default), 2 = member slots of the update too (measured slower: a slice
+                // repeats the slot's set-up and pays a fence + ticket, 55 us against 33 us per update at k = 8, n = 100)
+                const char* sl_env = getenv("DVS_SELECT_SLICES");
+                unsigned a_slice_mode = sl_env ? (unsigned)atoi(sl_env) : 1u;
+                if (!d_slparts.p && a_slice_mode) {
+                    const size_t slots = std::max<size_t>(grid, (size_t)cap + 1);
+                    DVS_TRY(d_slparts.alloc(slots * kMaxSlices));
+                    DVS_TRY(d_slticks.alloc(slots));
+                    DVS_CUDA_TRY(cudaMemsetAsync(d_slticks.p, 0, slots * sizeof(unsigned), st));
+                }
+                SlicePart* a_parts = d_slparts.p;
+                unsigned* a_ticks = d_slticks.p;
                 void* args[] = {&a_F, &a_H, &a_dim, &a_S0, &a_S1, &a_M0, &a_M1, &a_mem, &a_md, &a_mb, &a_sc, &a_valid,
-                                &a_order, &a_rounds, &a_trace, &shard};
+                                &a_order, &a_rounds, &a_trace, &shard, &a_parts, &a_ticks, &a_slice_mode};
                 DVS_CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_sel_persist, dim3(grid), dim3(kFastThreads), args, 0, st));
             }
             ctx->launches++;

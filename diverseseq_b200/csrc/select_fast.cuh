@@ -569,6 +569,159 @@ k_sel_round_dev(const double* __restrict__ F, const double* __restrict__ H, uint
     }
 }
 
+// ---- sliced evaluation for the cooperative kernel (vectors that do not fit shared memory: k >= 7) ----
+// With one CTA per candidate / member slot the rounds are THROUGHPUT bound at 4^8 elements: a round scans ~60
+// candidates and updates n + 1 = 101 slots on 296 resident CTAs, i.e. a fifth / a third of the GPU works for the
+// 51 us / 58 us one vector costs one CTA (tools/trace_select.py --k 8).  Here a vector is cut into P <= 8 slices that
+// different CTAs evaluate; each publishes its partial sums, and the CTA that arrives last at the vector's ticket adds
+// them in slice order and does what the unsliced body does with the sum.  The P - 1 extra sequential additions
+// enter the error bounds as `depth` (fast_slack), exactly as in the SM-replicated kernel.
+struct __align__(16) SlicePart {
+    double e, t, a;
+    int bad, pad;
+};
+constexpr unsigned kMaxSlices = 8;
+
+__device__ __forceinline__ void slice_publish(SlicePart* p, const FastSum& h) {
+    __stcg(&p->e, h.e);
+    __stcg(&p->t, h.t);
+    __stcg(&p->a, h.a);
+    __stcg(&p->bad, h.bad);
+}
+__device__ __forceinline__ FastSum slice_combine(const SlicePart* part, unsigned P) {
+    FastSum r{__ldcg(&part[0].e), __ldcg(&part[0].t), __ldcg(&part[0].a), __ldcg(&part[0].bad)};
+    for (unsigned s = 1; s < P; ++s) {
+        r.e += __ldcg(&part[s].e);
+        r.t += __ldcg(&part[s].t);
+        r.a += __ldcg(&part[s].a);
+        r.bad |= __ldcg(&part[s].bad);
+    }
+    return r;
+}
+// thread 0 of the CTA: publish slice s; true (with the combined sums in h) for the last of the P CTAs to arrive
+__device__ __forceinline__ bool slice_arrive(SlicePart* part, unsigned* tick, unsigned s, unsigned P, FastSum& h) {
+    slice_publish(part + s, h);
+    __threadfence();
+    if (atomicAdd(tick, 1u) != P - 1u) return false;
+    __threadfence();
+    *tick = 0u;  // (next use is behind a grid barrier)
+    h = slice_combine(part, P);
+    return true;
+}
+
+// scan_fast_body for slice s of P of the candidate at `pos`
+__device__ __forceinline__ void scan_sliced_body(const double* __restrict__ F, const double* __restrict__ H, uint64_t dim,
+                                                 const double* __restrict__ S, SelScal* sc, const ScanScal& q,
+                                                 const uint8_t* __restrict__ valid, const uint8_t* __restrict__ is_member,
+                                                 const unsigned* __restrict__ order, unsigned pos, unsigned s, unsigned P,
+                                                 SlicePart* part, unsigned* tick) {
+    __shared__ double2 s_ltab_sl[64];
+    const unsigned row = order[pos];
+    if (!valid[row] || __ldcg(is_member + row)) return;  // (the same for every slice: no ticket is taken)
+    dvs_log2_stage_table(s_ltab_sl);
+    __syncthreads();
+    const double nd = (double)q.n;
+    const double* fl = F + (size_t)q.low_row * dim;
+    const double* fc = F + (size_t)row * dim;
+    const unsigned lo = (unsigned)(dim * s / P), hi = (unsigned)(dim * (s + 1) / P);
+    FastSum h = block_entropy_ilp<false, 8>(
+        lo, hi, [&](unsigned i) { return __dadd_rn(__dsub_rn(__ldcg(S + i), fl[i]), fc[i]); }, make_fast_div(nd), s_ltab_sl);
+    if (threadIdx.x == 0 && slice_arrive(part, tick, s, P, h)) {
+        const double depth = (double)P;
+        const double mean_entropy = __ddiv_rn(__dadd_rn(__dsub_rn(q.E, H[q.low_row]), H[row]), nd);
+        const double d = h.e - mean_entropy;
+        const double b = fast_bound(dim, h.a, mean_entropy, depth);
+        const double thr = q.total_jsd + kEps, tb = q.total_bound + 4.0 * kEps;
+        if (h.bad || !fast_total_ok(dim, h.t, depth) || !(d == d)) {
+            atomicMin(&sc->first_unsure, pos);
+        } else if (d - b > thr + tb) {
+            atomicMin(&sc->first_true, pos);
+        } else if (!(d + b < thr - tb)) {
+            atomicMin(&sc->first_unsure, pos);
+        }
+    }
+}
+
+// replace_update_fast_body (device-driven form) for slice s of P of member slot j
+__device__ __forceinline__ void replace_update_sliced_body(
+    const double* __restrict__ F, const double* __restrict__ H, uint64_t dim, const double* __restrict__ S_in,
+    double* __restrict__ S_out, const unsigned* __restrict__ m_in, unsigned* __restrict__ m_out,
+    uint8_t* __restrict__ is_member, double* __restrict__ mdelta, double* __restrict__ mbound, SelScal* sc,
+    unsigned cand_row, unsigned dev_pos, unsigned dev_cursor, unsigned j, unsigned s, unsigned P, unsigned n, unsigned low,
+    double E_old, SlicePart* part, unsigned* tick) {
+    __shared__ unsigned s_last_sl;
+    __shared__ double2 s_ltab_up[64];
+    dvs_log2_stage_table(s_ltab_up);
+    __syncthreads();
+    const double nd = (double)n, depth = (double)P;
+    const unsigned low_row = __ldcg(m_in + low);
+    const double* fl = F + (size_t)low_row * dim;
+    const double* fc = F + (size_t)cand_row * dim;
+    const double E_new = __dadd_rn(__dsub_rn(E_old, H[low_row]), H[cand_row]);  // records.rs:101,129
+    auto s_new = [&](unsigned i) {
+        double v = __dsub_rn(__ldcg(S_in + i), fl[i]);
+        if (v <= kEps) v = 0.0;
+        return __dadd_rn(v, fc[i]);
+    };
+    const unsigned lo = (unsigned)(dim * s / P), hi = (unsigned)(dim * (s + 1) / P);
+    const unsigned row = j == n ? 0u : (j < low ? __ldcg(m_in + j) : (j + 1 < n ? __ldcg(m_in + j + 1) : cand_row));
+    FastSum h;
+    if (j == n) {
+        h = block_entropy_ilp<false, 8>(lo, hi, [&](unsigned i) {
+            const double v = s_new(i);
+            S_out[i] = v;
+            return v;
+        }, make_fast_div(nd), s_ltab_up);
+    } else {
+        const double* f = F + (size_t)row * dim;
+        h = block_entropy_ilp<true, 8>(lo, hi, [&](unsigned i) { return __dsub_rn(s_new(i), f[i]); },
+                                       make_fast_div(__dsub_rn(nd, 1.0)), s_ltab_up);
+    }
+    if (threadIdx.x == 0) {
+        unsigned last = 0;
+        if (slice_arrive(part, tick, s, P, h)) {
+            if (j == n) {
+                const double me = __ddiv_rn(E_new, nd);
+                sc->total_jsd = h.e - me;
+                sc->total_bound = fast_bound(dim, h.a, me, depth);
+            } else {
+                const double mean_entropy = __ddiv_rn(__dsub_rn(E_new, H[row]), __dsub_rn(nd, 1.0));
+                mdelta[j] = h.e - mean_entropy;
+                mbound[j] = fast_bound(dim, h.a, mean_entropy, depth);
+            }
+            if (h.bad || !fast_total_ok(dim, h.t, depth)) atomicExch(&sc->state_unsure, 1u);
+            __threadfence();
+            last = (atomicAdd(&sc->ticket, 1u) == n) ? 1u : 0u;
+        }
+        s_last_sl = last;
+    }
+    __syncthreads();
+    if (s_last_sl) {  // block-uniform: the whole last CTA finishes the round (as in replace_update_fast_body)
+        __threadfence();
+        for (unsigned t = threadIdx.x; t < n; t += blockDim.x)
+            m_out[t] = t < low ? __ldcg(m_in + t) : (t + 1 < n ? __ldcg(m_in + t + 1) : cand_row);
+        const double total = __ldcg(&sc->total_jsd), tb = __ldcg(&sc->total_bound);
+        unsigned lo2 = 0;
+        const unsigned unsure = finalize_fast_block(mdelta, mbound, n, total, tb, &lo2);
+        if (threadIdx.x == 0) {
+            is_member[low_row] = 0;
+            is_member[cand_row] = 1;
+            sc->E = E_new;
+            sc->lowest = lo2;
+            if (unsure) atomicExch(&sc->state_unsure, 1u);
+            sc->exact = 0;
+            sc->ticket = 0;
+            sc->first_true = kNone;
+            sc->first_panic = kNone;
+            sc->first_unsure = kNone;
+            sc->window = max(64u, min(__ldcg(&sc->window_max), 2u * (dev_pos - dev_cursor + 1u)));
+            sc->cursor = dev_pos + 1u;
+            sc->accepts = __ldcg(&sc->accepts) + 1u;
+            sc->which = __ldcg(&sc->which) ^ 1u;
+        }
+    }
+}
+
 // All device-driven rounds in ONE cooperative launch: the CTAs stay resident, a round is
 //   scan (one candidate per CTA and pass) | grid barrier | accept: fused replace + update over n+1 member
 //   slots, or advance / halt | grid barrier
@@ -585,7 +738,7 @@ __global__ void __launch_bounds__(kFastThreads)
 k_sel_persist(const double* __restrict__ F, const double* __restrict__ H, uint64_t dim, double* S0, double* S1,
               unsigned* M0, unsigned* M1, uint8_t* is_member, double* mdelta, double* mbound, SelScal* sc,
               const uint8_t* __restrict__ valid, const unsigned* __restrict__ order, unsigned max_rounds,
-              unsigned long long* trace, const ShardArgs sh) {
+              unsigned long long* trace, const ShardArgs sh, SlicePart* parts, unsigned* ticks, unsigned slice_mode) {
     cg::grid_group grid = cg::this_grid();
     __shared__ RoundScal rs;
     __shared__ unsigned s_xft, s_xfu, s_xdead;
@@ -616,8 +769,20 @@ k_sel_persist(const double* __restrict__ F, const double* __restrict__ H, uint64
         const ScanScal q = rs.q;
         // candidate-sharded over the GPUs: this one scores the window positions p with p % world == rank
         const unsigned woff = (rank + world - cursor % world) % world;
-        for (unsigned c = woff + world * blockIdx.x; c < count; c += world * gridDim.x)
-            scan_fast_body(F, H, dim, which ? S1 : S0, sc, q, valid, is_member, order, cursor + c);
+        // (slicing needs the exact-division / table range of block_entropy_div and room for the partial sums)
+        const bool slice_ok = parts && dim <= (1ull << 30) && n >= 2u && n <= 4096u;
+        const unsigned nloc = count > woff ? (count - woff + world - 1u) / world : 0u;
+        unsigned P = 1;
+        if (slice_ok)
+            while (P < kMaxSlices && nloc * P * 2u <= gridDim.x) P *= 2u;
+        if (P == 1u) {
+            for (unsigned c = woff + world * blockIdx.x; c < count; c += world * gridDim.x)
+                scan_fast_body(F, H, dim, which ? S1 : S0, sc, q, valid, is_member, order, cursor + c);
+        } else if (blockIdx.x < nloc * P) {  // slice s of this GPU's candidate c of the window
+            const unsigned c = blockIdx.x / P, s = blockIdx.x % P;
+            scan_sliced_body(F, H, dim, which ? S1 : S0, sc, q, valid, is_member, order, cursor + woff + world * c, s, P,
+                             parts + (size_t)c * kMaxSlices, ticks + c);
+        }
         stamp(round, 1);
         grid.sync();
         if (world > 1u) {  // all-reduce(min) of {first_true, first_unsure} over NVLink by CTA 0 (select_sm.cuh)
@@ -655,9 +820,30 @@ k_sel_persist(const double* __restrict__ F, const double* __restrict__ H, uint64
         const unsigned ft = rs.ft, fu = rs.fu, su = rs.su;
         if (!su && !(fu < ft) && ft != kNone) {
             const unsigned cand_row = order[ft];
-            for (unsigned j = blockIdx.x; j <= n; j += gridDim.x)
-                replace_update_fast_body(F, H, dim, which ? S1 : S0, which ? S0 : S1, which ? M1 : M0, which ? M0 : M1,
-                                         is_member, mdelta, mbound, sc, cand_row, ft, cursor, j, n, rs.lowest, q.E);
+            // slices per member slot: the P in {1, 2, 4, 8} with the fewest (waves of CTAs) / P
+            unsigned Pu = 1;
+            if (slice_ok && slice_mode >= 2u) {
+                unsigned best = (n + gridDim.x) / gridDim.x * kMaxSlices;  // waves at P = 1, in units of 1/8 vector
+                for (unsigned Pc = 2; Pc <= kMaxSlices; Pc *= 2u) {
+                    const unsigned waves = ((n + 1u) * Pc + gridDim.x - 1u) / gridDim.x, cost = waves * (kMaxSlices / Pc);
+                    if (cost < best) {
+                        best = cost;
+                        Pu = Pc;
+                    }
+                }
+            }
+            if (Pu == 1u) {
+                for (unsigned j = blockIdx.x; j <= n; j += gridDim.x)
+                    replace_update_fast_body(F, H, dim, which ? S1 : S0, which ? S0 : S1, which ? M1 : M0, which ? M0 : M1,
+                                             is_member, mdelta, mbound, sc, cand_row, ft, cursor, j, n, rs.lowest, q.E);
+            } else {
+                for (unsigned u = blockIdx.x; u < (n + 1u) * Pu; u += gridDim.x) {
+                    const unsigned j = u / Pu, s = u % Pu;
+                    replace_update_sliced_body(F, H, dim, which ? S1 : S0, which ? S0 : S1, which ? M1 : M0,
+                                               which ? M0 : M1, is_member, mdelta, mbound, sc, cand_row, ft, cursor, j, s,
+                                               Pu, n, rs.lowest, q.E, parts + (size_t)j * kMaxSlices, ticks + j);
+                }
+            }
         } else if (blockIdx.x == 0 && threadIdx.x == 0) {
             if (su || fu < ft) {
                 sc->halt = 1u;
