@@ -273,6 +273,11 @@ int dvs_comm_create(dvs_ctx* ctx, int rank, int world, uint64_t window_bytes, dv
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_pushed, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fan, cudaEventDisableTiming);
+    for (int d = 1; d < world && e == cudaSuccess; ++d) {
+        e = cudaStreamCreateWithFlags(&c->peer_stream[d], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->peer_ev[d], cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaEventRecord(c->ev_pushed, c->side);
     if (e != cudaSuccess) {
         set_error("dvs_comm_create: %s (window of %llu bytes)", cudaGetErrorString(e), (unsigned long long)c->window_bytes);
@@ -418,6 +423,14 @@ void dvs_comm_destroy(dvs_comm* c) {
     }
     for (int r = 0; r < c->world; ++r)
         if (c->ipc_opened[r]) cudaIpcCloseMemHandle(c->peer[r]);
+    for (int d = 0; d < kCommMaxWorld; ++d) {
+        if (c->peer_stream[d]) {
+            cudaStreamSynchronize(c->peer_stream[d]);
+            cudaStreamDestroy(c->peer_stream[d]);
+        }
+        if (c->peer_ev[d]) cudaEventDestroy(c->peer_ev[d]);
+    }
+    if (c->ev_fan) cudaEventDestroy(c->ev_fan);
     if (c->ev_ready) cudaEventDestroy(c->ev_ready);
     if (c->ev_pushed) cudaEventDestroy(c->ev_pushed);
     if (c->d_epoch_src) cudaFree(c->d_epoch_src);

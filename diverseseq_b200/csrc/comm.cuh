@@ -40,6 +40,11 @@ struct dvs_comm {
     uint64_t* d_epoch_src = nullptr;  // device word holding the current push epoch (source of flag copies)
     cudaStream_t side = nullptr;      // pushes run here, behind an event of the main stream
     cudaEvent_t ev_ready = nullptr, ev_pushed = nullptr;
+    // one stream per peer for the row pushes of dvs_count_kmers_sharded: the copies to different peers run on
+    // different copy engines instead of one after the other (they fork from / join `side`)
+    cudaStream_t peer_stream[kCommMaxWorld] = {};
+    cudaEvent_t peer_ev[kCommMaxWorld] = {};
+    cudaEvent_t ev_fan = nullptr;
     std::vector<CommBlock> blocks;    // symmetric heap (first fit over [kCommCtrlBytes, window_bytes))
     // Host-synchronised mode (dvs_comm_set_host_barrier): for ranks that SHARE one GPU (threads of one process in
     // the tests).  There, a kernel of one rank that spins on a peer can deadlock against a peer's host call that

@@ -1195,12 +1195,16 @@ static int allrows_push(dvs_comm* c, const AllRows& a, uint32_t rb, uint32_t re,
     if (re <= rb) return DVS_OK;
     const uint64_t dim = a.f->dim, hoff = a.f->heap_off;
     const size_t g0 = (size_t)a.row0 + rb, cnt = re - rb;
+    // fork from `side` (which is behind the rows' producer): one stream per peer, joined back into `side`
+    DVS_CUDA_TRY(cudaEventRecord(c->ev_fan, c->side));
     for (int d = 1; d < c->world; ++d) {
         const int r = (c->rank + d) % c->world;
         uint8_t* pb = c->peer[r] + hoff;
         const uint8_t* mb = c->window + hoff;
+        cudaStream_t ps = c->peer_stream[d];
+        DVS_CUDA_TRY(cudaStreamWaitEvent(ps, c->ev_fan, 0));
         auto cp = [&](uint64_t off, size_t elem) {
-            return cudaMemcpyAsync(pb + off + g0 * elem, mb + off + g0 * elem, cnt * elem, cudaMemcpyDeviceToDevice, c->side);
+            return cudaMemcpyAsync(pb + off + g0 * elem, mb + off + g0 * elem, cnt * elem, cudaMemcpyDeviceToDevice, ps);
         };
         DVS_CUDA_TRY(cp(a.off_freqs, dim * 8));
         if (scalars) {
@@ -1210,6 +1214,8 @@ static int allrows_push(dvs_comm* c, const AllRows& a, uint32_t rb, uint32_t re,
             DVS_CUDA_TRY(cp(a.off_valid, 1));
             DVS_CUDA_TRY(cp(a.off_err, 1));
         }
+        DVS_CUDA_TRY(cudaEventRecord(c->peer_ev[d], ps));
+        DVS_CUDA_TRY(cudaStreamWaitEvent(c->side, c->peer_ev[d], 0));
     }
     return DVS_OK;
 }
