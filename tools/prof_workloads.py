@@ -47,6 +47,9 @@ def main():
         ss = _lib.SeqSet.synth(ctx, SEED, 10500, 64, 400_000)
         kf = _lib.KFreqs.count(ctx, ss, 8)
         order = np.random.default_rng(SEED).permutation(10500).astype(np.uint32)
+        for _ in range(2):  # nmost: the cooperative rounds (k_sel_persist); `max` below its max_size runs the grow kernels
+            kf.select(order, _lib.MODE_NMOST, 100, 100)
+        print("nmost ms", ctx.phase_ms(_lib.PHASE_SELECT))
         for _ in range(2):
             kf.select(order, _lib.MODE_MAX_STDEV, 10, 100)
         print("max ms", ctx.phase_ms(_lib.PHASE_SELECT))
