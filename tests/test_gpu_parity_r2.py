@@ -144,3 +144,20 @@ def test_include_rerun_matches_oracle(lib, orc, brca1):
     m = records.select_max(store, 5, 9, k, stat="cov", seed=seed)
     mexp = orc.select_seqs(flat, off, np.arange(len(order)), k, "cov", 5, 9)
     assert m.record_names == [order[i] for i in mexp.ids]
+
+
+@pytest.mark.parametrize("slices", ["0", "1", "2"])
+def test_k8_round_slicing_modes_give_the_same_selection(lib, ctx, orc, k8_set, slices, monkeypatch):
+    """DVS_SELECT_SLICES: candidates (1) and member slots (2) cut into slices over the idle CTAs of the cooperative
+    kernel - partial sums combined in slice order, the extra additions covered by the error bounds, so every form
+    must give the oracle's selection bit for bit"""
+    kf, of, oe, ov, order = k8_set
+    monkeypatch.setenv("DVS_SELECT_SLICES", slices)
+    exp = orc.select_rows(of, oe, order, "nmost", 24, 24, valid=ov)
+    idx, delta, stats = kf.select(order, lib.MODE_NMOST, 24, 24)
+    assert idx.tolist() == exp.ids.tolist()
+    assert np.array_equal(delta, exp.delta_jsd)
+    assert stats[0] == exp.total_jsd and stats[1] == exp.mean_delta_jsd and stats[2] == exp.std_delta_jsd
+    exp2 = orc.select_rows(of, oe, order, "cov", 6, 12, valid=ov)
+    idx2, delta2, _ = kf.select(order, lib.MODE_MAX_COV, 6, 12)
+    assert idx2.tolist() == exp2.ids.tolist() and np.array_equal(delta2, exp2.delta_jsd)
