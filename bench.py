@@ -56,9 +56,9 @@ def parse_args():
                     help="N>1 selection: 'sharded' = ONE single-pass selection over all records, candidate-sharded "
                          "with a per-round all-reduce(min) over NVLink; 'chunked' = the reference's -np N semantics "
                          "(select per GPU, merge with final_nmost)")
-    ap.add_argument("--overlap", default="off", choices=["on", "off"],
-                    help="N=1: dvs_count_select (nmost rounds trail the counting on the same GPU) instead of the two "
-                         "calls; measured slower than the two calls (profiles/r2_overlap_ab.txt), hence off")
+    ap.add_argument("--overlap", default="on", choices=["on", "off"],
+                    help="N=1: dvs_count_select (the nmost rounds trail the counting on SMs of their own) instead of the "
+                         "two calls back to back (profiles/r2_overlap_ab.txt)")
     ap.add_argument("--chunks", type=int, default=0, help="counting launches of dvs_count_select (0 = library default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -79,9 +79,9 @@ def workload_config(a, world):
                         f"records sharded x{world} (rows pushed to all peers during counting); ONE single-pass nmost "
                         f"over all {world}x{a.nrec} records, candidate-sharded, all-reduce(min) per round over NVLink"),
         "l2": "inputs (~42 GB/GPU) are far larger than the 126 MB L2, no flush needed",
-        "overlap": ("dvs_count_select: records counted in the selection's examination order on a second stream, the "
-                    "nmost rounds trail the published rows on the same GPU" if world == 1 and a.overlap == "on" else
-                    "none (count, then select)"),
+        "overlap": ("dvs_count_select: records counted in the selection's examination order on a second stream in 6 "
+                    "launches; the nmost rounds trail the published rows on 36 SMs of their own, the counting keeps the "
+                    "other 112" if world == 1 and a.overlap == "on" else "none (count, then select)"),
     }
 
 
@@ -610,8 +610,11 @@ def main():
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
                 "kernel_ms": kc_ms, "algorithmic_bytes_per_launch": algo_bytes}
     if overlapped:
-        roofline["note"] = ("in-step: sum of the chunked counting launches while the selection kernel shares the SMs "
-                            "(56-register kernel shape); `alone` = the stand-alone launch of the same run")
+        roofline["note"] = ("in-step: sum of the 6 counting launches of a step; from the third launch on the selection "
+                            "kernel owns 36 of the 148 SMs, so the counting runs on 112; `alone` = the same kernel as one "
+                            "launch on the whole GPU, timed in the same run after the timed region; `step_frac` = "
+                            "algorithmic bytes / ms_per_step / peak")
+        roofline["step_frac"] = algo_bytes / (ms_step * 1e-3) / 1e9 / peak
         roofline["alone"] = {"kernel_ms": alone_ms, "achieved": algo_bytes / (alone_ms * 1e-3) / 1e9,
                              "frac": algo_bytes / (alone_ms * 1e-3) / 1e9 / peak}
 

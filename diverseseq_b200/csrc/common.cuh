@@ -107,6 +107,8 @@ struct dvs_ctx {
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;  // second stream (created on demand): counting of dvs_count_select
+    cudaStream_t stream_hi = nullptr;  // high-priority stream: the trailing selection kernel on its own SMs
+    cudaEvent_t ev_hi_in = nullptr, ev_hi_out = nullptr;
     cudaEvent_t ev_first = nullptr, ev_count_done = nullptr, ev_fork = nullptr;
     unsigned* d_ready = nullptr;      // trailing selection: positions published so far
     uint64_t launches = 0;

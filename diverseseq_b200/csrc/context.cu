@@ -81,6 +81,12 @@ void dvs_ctx_destroy(dvs_ctx* ctx) {
         cudaStreamSynchronize(ctx->stream);
         cudaStreamDestroy(ctx->stream);
     }
+    if (ctx->stream_hi) {
+        cudaStreamSynchronize(ctx->stream_hi);
+        cudaStreamDestroy(ctx->stream_hi);
+        cudaEventDestroy(ctx->ev_hi_in);
+        cudaEventDestroy(ctx->ev_hi_out);
+    }
     if (ctx->stream2) {
         cudaStreamSynchronize(ctx->stream2);
         cudaStreamDestroy(ctx->stream2);

@@ -691,6 +691,7 @@ struct CountDest {
     int s3_shape = -1;  // >= 0 overrides DVS_COUNT_S3_SHAPE (the trailing selection needs the 56-register form)
     uint32_t* resident = nullptr;  // device word: k_count_s3 CTAs resident right now
     int trail_regs = 56;           // register cap of the counting kernel beside the trailing selection
+    const uint32_t* weights = nullptr;  // [chunks] relative chunk sizes (NULL: equal)
 };
 
 static int count_core(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, uint32_t* d_counts, uint64_t dim,
@@ -827,7 +828,16 @@ static int count_core(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, 
     if (chunk_ev)
         for (uint32_t i = 0; i < 2 * nchunks; ++i)
             if (!ctx->ev_chunk[i]) TRY_F(cudaEventCreate(&ctx->ev_chunk[i]));
-    auto chunk_first = [&](uint32_t c) { return (uint32_t)((uint64_t)s->nrec * c / nchunks); };
+    // chunk c covers positions [chunk_first(c), chunk_first(c + 1)) of the counting sequence: equal shares unless the
+    // caller gives weights
+    uint64_t wsum = 0;
+    for (uint32_t c = 0; c < nchunks && dst.weights; ++c) wsum += dst.weights[c];
+    auto chunk_first = [&](uint32_t c) -> uint32_t {
+        if (!dst.weights || !wsum) return (uint32_t)((uint64_t)s->nrec * c / nchunks);
+        uint64_t acc = 0;
+        for (uint32_t i = 0; i < c; ++i) acc += dst.weights[i];
+        return (uint32_t)((unsigned __int128)s->nrec * acc / wsum);
+    };
     for (uint32_t ch = 0; ch < nchunks; ++ch) {
         const uint32_t rb = chunk_first(ch), re = chunk_first(ch + 1);
         const uint32_t ib = s->work_item_begin[rb], ie = s->work_item_begin[re];
@@ -1063,10 +1073,38 @@ int dvs_count_select(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, c
     auto ready_after = [&](uint32_t re) {  // positions published once seq[0..re) is counted
         return (uint32_t)(std::upper_bound(need.begin(), need.end(), re) - need.begin());
     };
-    if (chunks == 0) chunks = 8;
+    // chunk sizes: DVS_TRAIL_WEIGHTS="w0,w1,..." (relative sizes, also sets the number of chunks) for measurements
+    std::vector<uint32_t> weights;
+    if (const char* w_env = getenv("DVS_TRAIL_WEIGHTS")) {
+        for (const char* p = w_env; *p;) {
+            char* end = nullptr;
+            const unsigned long v = strtoul(p, &end, 10);
+            if (end == p) break;
+            weights.push_back((uint32_t)std::max<unsigned long>(v, 1));
+            p = *end ? end + 1 : end;
+        }
+        if (weights.size() >= 2 && weights.size() <= 64) chunks = (uint32_t)weights.size();
+        else weights.clear();
+    }
+    if (chunks == 0 && weights.empty()) {
+        // default: six launches, the middle ones large, the last ones small - the selection can take its SMs at the
+        // end of the second launch and little is left to examine once the counting has finished (measured on the
+        // bench set with 36 selection SMs: 12.34 ms/step; equal chunks 12.61; 7 chunks 12.44-12.50)
+        weights = {3, 4, 4, 3, 2, 1};
+        chunks = 6;
+    }
     chunks = std::min<uint32_t>(chunks, 64);
     // the first chunk has to hold the initial set
-    while (chunks > 1 && ready_after((uint32_t)((uint64_t)s->nrec / chunks)) < std::max<uint32_t>(min_size, 1)) --chunks;
+    auto first_chunk_end = [&]() -> uint32_t {
+        if (weights.size() != chunks) return (uint32_t)((uint64_t)s->nrec / chunks);
+        uint64_t ws = 0;
+        for (uint32_t w : weights) ws += w;
+        return (uint32_t)((uint64_t)s->nrec * weights[0] / ws);
+    };
+    while (chunks > 1 && ready_after(first_chunk_end()) < std::max<uint32_t>(min_size, 1)) {
+        --chunks;
+        weights.clear();
+    }
     // (only beside k_count_s3 - k = 4..6 over 4 states - whose CTA leaves room for exactly one selection CTA)
     const char* s3_env = getenv("DVS_COUNT_S3");
     const bool s3 = num_states == 4 && k >= 4 && k <= 6 && !(s3_env && s3_env[0] == '0');
@@ -1090,9 +1128,12 @@ int dvs_count_select(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, c
         DVS_CUDA_TRY(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
         CountDest dst{f->freqs.p, f->totals.p, f->entropy.p, f->valid.p, f->err.p, f->err_total.p, chunks, nullptr};
         dst.rec_seq = seq.data();
-        dst.s3_shape = 1;  // 56 registers: leaves 8,192 for the selection CTA on the same SM
-        dst.resident = ctx->d_ready + 1;
-        dst.trail_regs = dvs::trail_count_regs();
+        if (weights.size() == chunks) dst.weights = weights.data();
+        if (dvs::trail_shape() != 3) {  // co-resident forms: the counting CTA leaves registers / shared memory free
+            dst.s3_shape = 1;  // 56 registers: leaves 8,192 for the selection CTA on the same SM
+            dst.resident = ctx->d_ready + 1;
+            dst.trail_regs = dvs::trail_count_regs();
+        }
         bool first = true;
         cudaStream_t side = ctx->stream2;
         dst.after_chunk = [&](uint32_t, uint32_t re) -> int {

@@ -715,12 +715,15 @@ static int select_core(dvs_ctx* ctx, dvs_comm* comm, const dvs_kfreqs* f, const 
             // every remaining round in one cooperative launch (until done, or halted for the host)
             const bool use_sm = sm_ok && n <= kSmMaxN;
             // trailing rounds need the slim SM-replicated kernel; anything else waits for the counting to finish
-            const bool trailing = trail && trail_limit < num && use_sm && slim_ok && n <= kSmSlimMaxN && world == 1;
+            const bool dedicated = trail_shape() == 3;  // the selection owns whole SMs (fused.cuh)
+            const bool trailing = trail && trail_limit < num && use_sm && world == 1 &&
+                                  (dedicated || (slim_ok && n <= kSmSlimMaxN));
             if (trail && trail_limit < num && !trailing) {
                 DVS_CUDA_TRY(cudaStreamWaitEvent(st, trail->count_done, 0));
                 trail_limit = num;
             }
-            const unsigned grid = use_sm ? sm_grid : persist_grid;
+            const unsigned grid = (trailing && dedicated) ? std::min(sm_grid, trail_sms(ctx->sm_count))
+                                                           : (use_sm ? sm_grid : persist_grid);
             k_sel_set_dev<<<1, 1, 0, st>>>(cur->sc.p, cursor, std::min(window, grid * world), grid * world, num, accepts,
                                            (unsigned)cur->which);
             if (comm) {
@@ -764,7 +767,26 @@ static int select_core(dvs_ctx* ctx, dvs_comm* comm, const dvs_kfreqs* f, const 
                 unsigned a_limit0 = trail_limit;
                 void* args[] = {&a_F, &a_H, &a_dim32, &a_S, &a_M, &a_mem, &a_md, &a_mb, &a_sc, &a_valid, &a_order,
                                 &a_sp, &a_up, &a_dp, &a_trace, &a_trace_all, &shard, &a_ready, &a_limit0};
-                if (trailing) {
+                if (trailing && dedicated) {
+                    if (!ctx->stream_hi) {
+                        int lo_p = 0, hi_p = 0;
+                        DVS_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+                        DVS_CUDA_TRY(cudaStreamCreateWithPriority(&ctx->stream_hi, cudaStreamNonBlocking, hi_p));
+                        DVS_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_hi_in, cudaEventDisableTiming));
+                        DVS_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_hi_out, cudaEventDisableTiming));
+                    }
+                    // 512 threads x 128 registers: one CTA fills an SM's register file, so these CTAs take whole SMs -
+                    // the ones the counting CTAs of the launch in flight leave when it ends (the higher stream priority
+                    // puts them ahead of the next counting launch's CTAs)
+                    DVS_CUDA_TRY(cudaEventRecord(ctx->ev_hi_in, st));
+                    DVS_CUDA_TRY(cudaStreamWaitEvent(ctx->stream_hi, ctx->ev_hi_in, 0));
+                    k_sel_persist_sm_full<<<grid, kFastThreads, sizeof(SmShared), ctx->stream_hi>>>(
+                        a_F, a_H, a_dim32, a_S, a_M, a_mem, a_md, a_mb, a_sc, a_valid, a_order, a_sp, a_up, a_dp, a_trace,
+                        a_trace_all, shard, a_ready, a_limit0);
+                    DVS_CUDA_TRY(cudaGetLastError());
+                    DVS_CUDA_TRY(cudaEventRecord(ctx->ev_hi_out, ctx->stream_hi));
+                    DVS_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_hi_out, 0));
+                } else if (trailing) {
                     // a plain launch, made when every SM holds a counting CTA: beside it exactly one of these CTAs
                     // fits (registers), so they land one per SM.  Launched between two counting launches they
                     // would pack three to an SM and keep the counting off a third of the GPU.
@@ -772,7 +794,8 @@ static int select_core(dvs_ctx* ctx, dvs_comm* comm, const dvs_kfreqs* f, const 
                                                      trail->d_ready, num);
                     DVS_LAUNCHED(ctx);
                 }
-                if (trailing)
+                if (trailing && dedicated) {
+                } else if (trailing)
                     k_slim<<<grid, slim_threads, sizeof(SmSharedSlim), st>>>(
                         a_F, a_H, a_dim32, a_S, a_M, a_mem, a_md, a_mb, a_sc, a_valid, a_order, a_sp, a_up, a_dp, a_trace,
                         a_trace_all, shard, a_ready, a_limit0);
