@@ -314,11 +314,12 @@ int dvs_select_sharded(dvs_ctx* ctx, dvs_comm* c, const dvs_kfreqs* f_all, const
 
 /* dvs_count_kmers + dvs_select in one call with the two OVERLAPPED on one GPU (the `dvs prep` -> `dvs nmost` flow of
  * BASELINE.json configs[1]; reference: src/lib.rs nmost() over the records src/record.rs KmerSeq::new builds).
- * The records are counted on a second stream in the sequence `order` examines them, `chunks` launches (0 = default
- * 8, at most 64); after each launch the number of positions whose rows exist is published in a device word and the
- * nmost rounds - a slim SM-replicated kernel co-resident with the counting CTAs - examine only positions below it.
+ * The records are counted on a second stream in the sequence `order` examines them, `chunks` launches (0 = default:
+ * six launches of relative sizes 3,4,4,3,2,1; at most 64); after each launch the number of positions whose rows exist
+ * is published in a device word and the nmost rounds - the SM-replicated selection kernel on a high-priority stream,
+ * which takes ~36 SMs for itself while the counting keeps the rest - examine only positions below it.
  * Results (rows in *out, selection, stats) are bit-identical to the two separate calls.  Modes other than
- * DVS_MODE_NMOST, n > 256, dim > 4096 or min_size larger than the first chunk run the two steps back to back. */
+ * DVS_MODE_NMOST, k outside 4..6, n > 1024 or min_size larger than the first chunk run the two steps back to back. */
 int dvs_count_select(dvs_ctx* ctx, const dvs_seqset* s, int k, int num_states, const uint32_t* order, uint32_t num,
                      int mode, uint32_t min_size, uint32_t max_size, uint32_t chunks, dvs_kfreqs** out,
                      uint32_t* sel_idx, double* sel_delta, double* stats5, uint32_t* size_out);
