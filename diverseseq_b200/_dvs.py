@@ -215,8 +215,9 @@ def _select_from_store(store, seqids, k, num_states, mode, min_size, max_size) -
         raise ValueError("k cannot be 0")
     if len(seqids) < min_size:  # before any counting, like records.rs:323-325
         raise ValueError(f"The number of sequences {len(seqids)} is < n {min_size}")
-    kf = _lib.KFreqs.count(ctx, seqset, k, num_states)
-    idx, delta, stats = kf.select(order, mode, min_size, max_size)
+    # one call: for nmost at k = 4..6 the selection rounds trail the counting (dvs_count_select); every other case runs
+    # the two steps back to back inside it, with the same results and errors
+    kf, idx, delta, stats = _lib.KFreqs.count_select(ctx, seqset, k, order, mode, min_size, max_size, num_states)
     rows = kf.download_rows(idx)
     return _make_result([names[r] for r in idx], rows, delta, stats, k, num_states)
 
